@@ -1,0 +1,149 @@
+"""ctypes binding of libfamsa_b200.so (the C ABI declared in include/famsa_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+EXPORTED_SYMBOLS = [
+    "famsa_abi_version", "famsa_create", "famsa_destroy", "famsa_last_error", "famsa_kernel_launches",
+    "famsa_lcs_upload", "famsa_lcs_n_seqs", "famsa_lcs_triangle", "famsa_lcs_triangle_device",
+    "famsa_lcs_rows", "famsa_lcs_rows_device", "famsa_transform_f64", "famsa_transform_f32",
+    "famsa_lcs_last_timing",
+]
+
+
+class FamsaError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "lib", "libfamsa_b200.so")
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load the CUDA library; raise (never fall back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise FamsaError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(there is no CPU fallback)")
+    lib = C.CDLL(path)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    lib.famsa_abi_version.restype = i32
+    lib.famsa_create.argtypes = [i32, C.POINTER(vp)]
+    lib.famsa_destroy.argtypes = [vp]
+    lib.famsa_destroy.restype = None
+    lib.famsa_last_error.restype = C.c_char_p
+    lib.famsa_kernel_launches.argtypes = [vp]
+    lib.famsa_kernel_launches.restype = u64
+    lib.famsa_lcs_upload.argtypes = [vp, vp, vp, vp, u32]
+    lib.famsa_lcs_n_seqs.argtypes = [vp]
+    lib.famsa_lcs_n_seqs.restype = u32
+    lib.famsa_lcs_triangle.argtypes = [vp, u32, u32, vp, i32]
+    lib.famsa_lcs_triangle_device.argtypes = [vp, u32, u32, vp, i32, vp]
+    lib.famsa_lcs_rows.argtypes = [vp, vp, u32, vp, u32, vp, i32]
+    lib.famsa_lcs_rows_device.argtypes = [vp, vp, u32, vp, u32, vp, i32, vp]
+    lib.famsa_transform_f64.argtypes = [i32, u32, u32, u32]
+    lib.famsa_transform_f64.restype = C.c_double
+    lib.famsa_transform_f32.argtypes = [i32, u32, u32, u32]
+    lib.famsa_transform_f32.restype = C.c_float
+    lib.famsa_lcs_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(u64)]
+    _lib = lib
+    return lib
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def tri_size(row_begin: int, row_end: int) -> int:
+    f = lambda r: r * (r - 1) // 2 if r else 0
+    return f(row_end) - f(row_begin)
+
+
+class Engine:
+    """One context on one GPU.  Mirrors the reference's per-thread CLCSBP + batch drivers:
+    upload() ~ ComputeBitMasks for every sequence, triangle() ~ calculateDistanceMatrix,
+    rows() ~ calculateDistanceVector / Range / RangeSV (raw LCS lengths, Transform stays on host)."""
+
+    def __init__(self, device: int = -1):
+        self.lib = load_library()
+        h = C.c_void_p()
+        self._check(self.lib.famsa_create(device, C.byref(h)))
+        self.h = h
+        self.n = 0
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise FamsaError(f"[{rc}] {self.lib.famsa_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.famsa_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------- HP-1
+    def upload(self, codes: np.ndarray, offsets: np.ndarray, lens: np.ndarray):
+        codes = np.ascontiguousarray(codes, dtype=np.int8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        self._check(self.lib.famsa_lcs_upload(self.h, _ptr(codes), _ptr(offsets), _ptr(lens), len(lens)))
+        self.n = len(lens)
+
+    def triangle(self, row_begin: int = 0, row_end: int | None = None, dtype=np.uint16,
+                 out: np.ndarray | None = None) -> np.ndarray:
+        row_end = self.n if row_end is None else row_end
+        size = tri_size(row_begin, row_end)
+        if out is None:
+            out = np.empty(max(size, 1), dtype=dtype)
+        self._check(self.lib.famsa_lcs_triangle(self.h, row_begin, row_end, _ptr(out), out.dtype.itemsize))
+        return out[:size]
+
+    def triangle_device(self, row_begin: int, row_end: int, d_out_ptr: int, elem_bytes: int, stream: int = 0):
+        self._check(self.lib.famsa_lcs_triangle_device(self.h, row_begin, row_end, C.c_void_p(d_out_ptr),
+                                                       elem_bytes, C.c_void_p(stream) if stream else None))
+
+    def rows(self, ref_ids, col_ids=None, n_col: int | None = None, dtype=np.uint32) -> np.ndarray:
+        ref = np.ascontiguousarray(ref_ids, dtype=np.uint32)
+        cols = None if col_ids is None else np.ascontiguousarray(col_ids, dtype=np.uint32)
+        n_col = (self.n if n_col is None else n_col) if cols is None else len(cols)
+        out = np.empty((len(ref), max(n_col, 1)), dtype=dtype)
+        out = out[:, :n_col] if n_col else out[:, :0]
+        buf = np.empty(max(len(ref) * n_col, 1), dtype=dtype)
+        self._check(self.lib.famsa_lcs_rows(self.h, _ptr(ref), len(ref), _ptr(cols), n_col, _ptr(buf),
+                                            buf.dtype.itemsize))
+        return buf[:len(ref) * n_col].reshape(len(ref), n_col)
+
+    def rows_device(self, d_ref_ptr: int, n_ref: int, d_col_ptr: int, n_col: int, d_out_ptr: int,
+                    elem_bytes: int, stream: int = 0):
+        self._check(self.lib.famsa_lcs_rows_device(self.h, C.c_void_p(d_ref_ptr), n_ref,
+                                                   C.c_void_p(d_col_ptr) if d_col_ptr else None, n_col,
+                                                   C.c_void_p(d_out_ptr), elem_bytes,
+                                                   C.c_void_p(stream) if stream else None))
+
+    def last_timing(self) -> tuple[float, float, int]:
+        t, m, p = C.c_float(), C.c_float(), C.c_uint64()
+        self._check(self.lib.famsa_lcs_last_timing(self.h, C.byref(t), C.byref(m), C.byref(p)))
+        return t.value, m.value, p.value
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.famsa_kernel_launches(self.h))
+
+    def transform(self, kind: int, lcs: int, len1: int, len2: int, double: bool = True) -> float:
+        f = self.lib.famsa_transform_f64 if double else self.lib.famsa_transform_f32
+        return float(f(kind, lcs, len1, len2))

@@ -1,0 +1,249 @@
+// C ABI of libfamsa_b200.so -- see include/famsa_b200.h for the contract of every entry point.
+#include <cfloat>
+#include <cmath>
+#include <new>
+
+#include "ctx.h"
+
+namespace fb {
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+const char* get_error() { return g_error.c_str(); }
+} // namespace fb
+
+using fb::set_error;
+
+#define FB_CHECK_CTX(ctx)                          \
+    if (!(ctx)) {                                  \
+        set_error("famsa_ctx is NULL");            \
+        return FAMSA_E_INVALID;                    \
+    }
+
+extern "C" {
+
+int famsa_abi_version(void) { return FAMSA_B200_ABI_VERSION; }
+
+const char* famsa_last_error(void) { return fb::get_error(); }
+
+int famsa_create(int device, famsa_ctx** out_ctx)
+{
+    if (!out_ctx) { set_error("out_ctx is NULL"); return FAMSA_E_INVALID; }
+    *out_ctx = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        set_error(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                  "); libfamsa_b200 has no CPU fallback");
+        return FAMSA_E_NO_DEVICE;
+    }
+    if (device < 0) FB_CUDA(cudaGetDevice(&device));
+    if (device >= count) { set_error("device ordinal out of range"); return FAMSA_E_INVALID; }
+    FB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    FB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error(std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                  std::to_string(prop.minor) + "; this library is built for sm_100a only");
+        return FAMSA_E_NO_DEVICE;
+    }
+    famsa_ctx* ctx = new (std::nothrow) famsa_ctx();
+    if (!ctx) { set_error("out of host memory"); return FAMSA_E_NOMEM; }
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    FB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (auto& ev : ctx->ev) FB_CUDA(cudaEventCreate(&ev));
+    *out_ctx = ctx;
+    return FAMSA_OK;
+}
+
+void famsa_destroy(famsa_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    fb::LcsState& S = ctx->lcs;
+    for (fb::DevBuf* b : {&S.d_perm, &S.d_invperm, &S.d_len_sorted, &S.d_code_off, &S.d_codes, &S.d_blob,
+                          &S.d_group_blob, &S.d_raw_codes, &S.d_raw_off, &S.d_raw_len, &S.d_flags, &S.d_tiles,
+                          &S.d_res, &S.d_refpos, &S.d_ids_a, &S.d_ids_b, &S.d_out_stage, &S.d_masks64, &S.d_x64})
+        b->release();
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+uint64_t famsa_kernel_launches(const famsa_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ------------------------------------------------------------------ HP-1
+
+int famsa_lcs_upload(famsa_ctx* ctx, const int8_t* codes, const uint64_t* offsets, const uint32_t* lens,
+                     uint32_t n_seqs)
+{
+    FB_CHECK_CTX(ctx);
+    if (n_seqs && (!codes || !offsets || !lens)) { set_error("NULL sequence arrays"); return FAMSA_E_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    FB_CUDA(cudaSetDevice(ctx->device));
+    return fb::lcs_upload(ctx, codes, offsets, lens, n_seqs);
+}
+
+uint32_t famsa_lcs_n_seqs(const famsa_ctx* ctx) { return ctx ? ctx->lcs.n : 0; }
+
+static int check_elem(const famsa_ctx* ctx, int elem_bytes)
+{
+    if (elem_bytes != 2 && elem_bytes != 4) { set_error("elem_bytes must be 2 or 4"); return FAMSA_E_INVALID; }
+    if (elem_bytes == 2 && ctx->lcs.max_len >= 65536) {
+        set_error("elem_bytes == 2 needs every sequence shorter than 65536");
+        return FAMSA_E_INVALID;
+    }
+    return FAMSA_OK;
+}
+
+static int finish_timing(famsa_ctx* ctx)
+{
+    float total = 0.f, main_ms = 0.f;
+    FB_CUDA(cudaEventSynchronize(ctx->ev[3]));
+    FB_CUDA(cudaEventElapsedTime(&total, ctx->ev[0], ctx->ev[3]));
+    FB_CUDA(cudaEventElapsedTime(&main_ms, ctx->ev[1], ctx->ev[2]));
+    ctx->lcs.last_total_ms = total;
+    ctx->lcs.last_main_ms = main_ms;
+    return FAMSA_OK;
+}
+
+static int triangle_locked(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_out, int elem_bytes,
+                           void* stream)
+{
+    if (ctx->lcs.n == 0 && row_end > 0) { set_error("famsa_lcs_upload has not been called"); return FAMSA_E_STATE; }
+    if (row_begin > row_end || row_end > ctx->lcs.n) { set_error("row range out of bounds"); return FAMSA_E_INVALID; }
+    int rc = check_elem(ctx, elem_bytes);
+    if (rc) return rc;
+    if (!d_out && row_end > row_begin && row_end > 1) { set_error("d_out is NULL"); return FAMSA_E_INVALID; }
+    FB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    rc = fb::lcs_triangle(ctx, row_begin, row_end, d_out, elem_bytes, st);
+    if (rc) return rc;
+    if (!stream) { FB_CUDA(cudaStreamSynchronize(st)); return finish_timing(ctx); }
+    return FAMSA_OK;
+}
+
+int famsa_lcs_triangle_device(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_out, int elem_bytes,
+                              void* stream)
+{
+    FB_CHECK_CTX(ctx);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return triangle_locked(ctx, row_begin, row_end, d_out, elem_bytes, stream);
+}
+
+int famsa_lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* out, int elem_bytes)
+{
+    FB_CHECK_CTX(ctx);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (row_begin > row_end || row_end > ctx->lcs.n) { set_error("row range out of bounds"); return FAMSA_E_INVALID; }
+    if (elem_bytes != 2 && elem_bytes != 4) { set_error("elem_bytes must be 2 or 4"); return FAMSA_E_INVALID; }
+    const uint64_t pairs = (uint64_t)row_end * (row_end ? row_end - 1 : 0) / 2 -
+                           (uint64_t)row_begin * (row_begin ? row_begin - 1 : 0) / 2;
+    if (pairs && !out) { set_error("out is NULL"); return FAMSA_E_INVALID; }
+    FB_CUDA(cudaSetDevice(ctx->device));
+    int rc = ctx->lcs.d_out_stage.reserve(std::max<uint64_t>(pairs, 1) * elem_bytes);
+    if (rc) return rc;
+    void* d_out = ctx->lcs.d_out_stage.p;
+    rc = triangle_locked(ctx, row_begin, row_end, d_out, elem_bytes, nullptr);
+    if (rc) return rc;
+    if (pairs) FB_CUDA(cudaMemcpy(out, d_out, pairs * elem_bytes, cudaMemcpyDeviceToHost));
+    return FAMSA_OK;
+}
+
+static int rows_common(famsa_ctx* ctx, const uint32_t* d_ref_ids, const uint32_t* h_ref_ids, uint32_t n_ref,
+                       const uint32_t* d_col_ids, uint32_t n_col, void* d_out, int elem_bytes, void* stream)
+{
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    for (uint32_t r = 0; r < n_ref; ++r)
+        if (h_ref_ids[r] >= ctx->lcs.n) { set_error("ref id out of range"); return FAMSA_E_INVALID; }
+    int rc = fb::lcs_rows(ctx, d_ref_ids, h_ref_ids, n_ref, d_col_ids, n_col, d_out, elem_bytes, st);
+    if (rc) return rc;
+    if (!stream) { FB_CUDA(cudaStreamSynchronize(st)); return finish_timing(ctx); }
+    return FAMSA_OK;
+}
+
+int famsa_lcs_rows_device(famsa_ctx* ctx, const uint32_t* d_ref_ids, uint32_t n_ref, const uint32_t* d_col_ids,
+                          uint32_t n_col, void* d_out, int elem_bytes, void* stream)
+{
+    FB_CHECK_CTX(ctx);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->lcs.n == 0) { set_error("famsa_lcs_upload has not been called"); return FAMSA_E_STATE; }
+    int rc = check_elem(ctx, elem_bytes);
+    if (rc) return rc;
+    if (!d_col_ids && n_col > ctx->lcs.n) { set_error("n_col exceeds the number of sequences"); return FAMSA_E_INVALID; }
+    if (n_ref && !d_ref_ids) { set_error("d_ref_ids is NULL"); return FAMSA_E_INVALID; }
+    FB_CUDA(cudaSetDevice(ctx->device));
+    std::vector<uint32_t> h_ref(n_ref);
+    if (n_ref) FB_CUDA(cudaMemcpy(h_ref.data(), d_ref_ids, sizeof(uint32_t) * n_ref, cudaMemcpyDeviceToHost));
+    return rows_common(ctx, d_ref_ids, h_ref.data(), n_ref, d_col_ids, n_col, d_out, elem_bytes, stream);
+}
+
+int famsa_lcs_rows(famsa_ctx* ctx, const uint32_t* ref_ids, uint32_t n_ref, const uint32_t* col_ids, uint32_t n_col,
+                   void* out, int elem_bytes)
+{
+    FB_CHECK_CTX(ctx);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->lcs.n == 0) { set_error("famsa_lcs_upload has not been called"); return FAMSA_E_STATE; }
+    int rc = check_elem(ctx, elem_bytes);
+    if (rc) return rc;
+    if (!col_ids && n_col > ctx->lcs.n) { set_error("n_col exceeds the number of sequences"); return FAMSA_E_INVALID; }
+    if ((n_ref && !ref_ids) || ((uint64_t)n_ref * n_col && !out)) { set_error("NULL argument"); return FAMSA_E_INVALID; }
+    if (col_ids)
+        for (uint32_t k = 0; k < n_col; ++k)
+            if (col_ids[k] >= ctx->lcs.n) { set_error("col id out of range"); return FAMSA_E_INVALID; }
+    FB_CUDA(cudaSetDevice(ctx->device));
+    fb::LcsState& S = ctx->lcs;
+    const uint64_t cells = (uint64_t)n_ref * n_col;
+    rc = S.d_out_stage.reserve(std::max<uint64_t>(cells, 1) * elem_bytes);
+    if (rc) return rc;
+    rc = S.d_ids_a.reserve(sizeof(uint32_t) * std::max(1u, n_ref));
+    if (rc) return rc;
+    const uint32_t* d_cols = nullptr;
+    if (col_ids) {
+        rc = S.d_ids_b.reserve(sizeof(uint32_t) * std::max(1u, n_col));
+        if (rc) return rc;
+        FB_CUDA(cudaMemcpyAsync(S.d_ids_b.p, col_ids, sizeof(uint32_t) * n_col, cudaMemcpyHostToDevice, ctx->stream));
+        d_cols = S.d_ids_b.as<uint32_t>();
+    }
+    if (n_ref)
+        FB_CUDA(cudaMemcpyAsync(S.d_ids_a.p, ref_ids, sizeof(uint32_t) * n_ref, cudaMemcpyHostToDevice, ctx->stream));
+    rc = rows_common(ctx, S.d_ids_a.as<uint32_t>(), ref_ids, n_ref, d_cols, n_col, S.d_out_stage.p, elem_bytes, nullptr);
+    if (rc) return rc;
+    if (cells) FB_CUDA(cudaMemcpy(out, S.d_out_stage.p, cells * elem_bytes, cudaMemcpyDeviceToHost));
+    return FAMSA_OK;
+}
+
+int famsa_lcs_last_timing(const famsa_ctx* ctx, float* total_ms, float* main_kernel_ms, uint64_t* n_pairs)
+{
+    FB_CHECK_CTX(ctx);
+    if (total_ms) *total_ms = ctx->lcs.last_total_ms;
+    if (main_kernel_ms) *main_kernel_ms = ctx->lcs.last_main_ms;
+    if (n_pairs) *n_pairs = ctx->lcs.last_pairs;
+    return FAMSA_OK;
+}
+
+// ------------------------------------------------------------------ Transform<T, Distance>
+// reference src/tree/AbstractTreeGenerator.hpp:28-82; kept on the host so that distances are
+// bit-identical to the reference's (same libm pow, same float/double narrowing points).
+
+double famsa_transform_f64(int kind, uint32_t lcs, uint32_t len1, uint32_t len2)
+{
+    if (kind == 2) return (double)lcs / std::min(len1, len2);
+    const double indel = (double)(len1 + len2 - 2 * lcs);
+    if (!lcs) return std::nextafter(DBL_MAX, 0.0);
+    if (kind == 0) return (double)std::pow((double)(uint32_t)indel, 0.75) / (double)lcs;
+    return indel / lcs;
+}
+
+float famsa_transform_f32(int kind, uint32_t lcs, uint32_t len1, uint32_t len2)
+{
+    if (kind == 2) return (float)lcs / std::min(len1, len2);
+    const float indel = (float)(len1 + len2 - 2 * lcs);
+    if (!lcs) return (float)std::nextafter((double)FLT_MAX, 0.0);
+    if (kind == 0) return (float)std::pow((double)(uint32_t)indel, 0.75) / (float)lcs;
+    return indel / lcs;
+}
+
+} // extern "C"

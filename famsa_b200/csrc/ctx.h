@@ -1,0 +1,83 @@
+// Internal context of libfamsa_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/famsa_b200.h"
+
+namespace fb {
+
+void set_error(const std::string& msg);
+const char* get_error();
+
+#define FB_CUDA(expr)                                                                        \
+    do {                                                                                     \
+        cudaError_t err__ = (expr);                                                          \
+        if (err__ != cudaSuccess) {                                                          \
+            fb::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(err__) +     \
+                          " (" __FILE__ ":" + std::to_string(__LINE__) + ")");               \
+            return FAMSA_E_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+
+// Simple owning device buffer that only grows.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);   // returns FAMSA_* code
+    void release();
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// One 32-sequence mask group (sequences are grouped in length-descending order).
+struct LcsGroupInfo {
+    uint32_t nl;          // instantiated limb count of the tile kernel (0 = longer than the tile kernel handles)
+    uint64_t blob_word;   // offset (32-bit words) of the group's mask blob
+};
+
+struct LcsState {
+    uint32_t n = 0;            // sequences
+    uint32_t n_groups = 0;     // ceil(n/32)
+    bool identity_perm = true; // caller order already length-descending
+    uint32_t max_len = 0;
+    std::vector<uint32_t> h_perm;      // sorted position -> caller id
+    std::vector<uint32_t> h_invperm;   // caller id -> sorted position
+    std::vector<uint32_t> h_len_sorted;
+    std::vector<LcsGroupInfo> groups;
+    std::vector<uint32_t> h_quirky;    // caller ids whose masks contain an all-ones 64-bit word
+    std::vector<uint32_t> h_long;      // caller ids longer than the tile kernel handles as mask side
+    DevBuf d_perm, d_invperm, d_len_sorted, d_code_off, d_codes, d_blob, d_group_blob;
+    DevBuf d_raw_codes, d_raw_off, d_raw_len, d_flags;
+    // per-call scratch
+    DevBuf d_tiles, d_res, d_refpos, d_ids_a, d_ids_b, d_out_stage, d_masks64, d_x64;
+    // last-call timing
+    float last_total_ms = 0.f, last_main_ms = 0.f;
+    uint64_t last_pairs = 0;
+};
+
+} // namespace fb
+
+struct famsa_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::mutex mu;
+    uint64_t launches = 0;
+    int sm_count = 0;
+    fb::LcsState lcs;
+};
+
+namespace fb {
+// lcs.cu
+int lcs_upload(famsa_ctx* ctx, const int8_t* codes, const uint64_t* offsets, const uint32_t* lens,
+               uint32_t n);
+int lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_out, int elem_bytes,
+                 cudaStream_t stream);
+int lcs_rows(famsa_ctx* ctx, const uint32_t* d_ref_ids, const uint32_t* h_ref_ids, uint32_t n_ref,
+             const uint32_t* d_col_ids, uint32_t n_col, void* d_out, int elem_bytes,
+             cudaStream_t stream);
+} // namespace fb

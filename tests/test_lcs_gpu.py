@@ -1,0 +1,125 @@
+"""GPU parity tests for HP-1 (all go through the C ABI).  Bit-exact: LCS lengths are integers."""
+import numpy as np
+import pytest
+
+from conftest import QUIRK_LCS, QUIRK_SEQS, random_set
+from famsa_b200 import seqio
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+
+
+def tri_to_square(tri, n, base_row=0):
+    sq = np.zeros((n, n), dtype=np.int64)
+    i, j = np.tril_indices(n, -1)
+    keep = i >= base_row
+    i, j = i[keep], j[keep]
+    sq[i, j] = tri[i * (i - 1) // 2 + j - base_row * (base_row - 1) // 2 * (base_row > 0)]
+    return sq
+
+
+def test_adeno_triangle_matches_golden(engine, adeno):
+    """Unsorted input order (the -dist_export shape): every LCS pinned by pid.csv."""
+    n = len(adeno["lens"])
+    engine.upload(adeno["codes"], adeno["offsets"], adeno["lens"])
+    for dtype in (np.uint16, np.uint32):
+        tri = engine.triangle(dtype=dtype)
+        i, j = np.tril_indices(n, -1)
+        assert np.array_equal(tri[i * (i - 1) // 2 + j], adeno["lcs"][i, j])
+    part = engine.triangle(57, 131)
+    assert np.array_equal(part, tri[57 * 56 // 2:131 * 130 // 2])
+
+
+def test_adeno_rows_match_golden_square(engine, adeno):
+    """All 242 x 242 entries of pid_sq.csv incl. the diagonal, row = seq0."""
+    n = len(adeno["lens"])
+    engine.upload(adeno["codes"], adeno["offsets"], adeno["lens"])
+    got = engine.rows(np.arange(n))
+    assert np.array_equal(got, adeno["lcs"])
+    cols = np.array([5, 5, 200, 0, 17, 241, 3], dtype=np.uint32)      # duplicates allowed
+    got = engine.rows([7, 100, 7], cols, dtype=np.uint16)
+    assert np.array_equal(got, adeno["lcs"][np.ix_([7, 100, 7], cols)])
+    got = engine.rows([9], n_col=50)
+    assert np.array_equal(got[0], adeno["lcs"][9, :50])
+
+
+def test_carry_quirk_vector(engine):
+    """The reference's dropped-carry corner is reproduced bit for bit."""
+    codes, offsets, lens = seqio.pack([seqio.encode(s) for s in QUIRK_SEQS])
+    engine.upload(codes, offsets, lens)
+    assert np.array_equal(engine.rows(np.arange(4)), QUIRK_LCS)
+    tri = engine.triangle(dtype=np.uint32)
+    i, j = np.tril_indices(4, -1)
+    assert np.array_equal(tri, QUIRK_LCS[i, j])
+
+
+@pytest.mark.parametrize("seed,n,lo,hi", [(1, 150, 0, 90), (2, 97, 30, 700), (3, 40, 1000, 2300), (4, 33, 1, 1)])
+def test_random_ragged_sets(engine, seed, n, lo, hi):
+    """Ragged lengths incl. empty sequences, non-matching symbols (B Z X *), low-complexity runs,
+    sequences beyond the register-resident kernel's 2048 residues."""
+    rng = np.random.default_rng(seed)
+    code_list = random_set(rng, n, lo, hi)
+    code_list += random_set(rng, 6, max(lo, 1), max(hi // 2, 1), alphabet=2)
+    code_list.append(np.zeros(min(hi, 200) + 1, np.int8))
+    rng.shuffle(code_list)
+    codes, offsets, lens = seqio.pack(code_list)
+    m = len(code_list)
+    engine.upload(codes, offsets, lens)
+    assert np.array_equal(engine.triangle(dtype=np.uint32), pyoracle.lcs_triangle(codes, offsets, lens))
+    refs = rng.permutation(m)[:9]
+    cols = rng.permutation(m)[:31]
+    assert np.array_equal(engine.rows(refs, cols), pyoracle.lcs_rows(codes, offsets, lens, refs, cols))
+    assert np.array_equal(engine.rows(refs[:2]), pyoracle.lcs_rows(codes, offsets, lens, refs[:2]))
+
+
+def test_sorted_set_partial_rows(engine):
+    """Length-descending input (FAMSA's own order): identity permutation, row-range sharding."""
+    codes, offsets, lens = seqio.synth_family(300, 120, seed=9)
+    engine.upload(codes, offsets, lens)
+    full = pyoracle.lcs_triangle(codes, offsets, lens)
+    got = np.concatenate([engine.triangle(a, b, dtype=np.uint32) for a, b in [(0, 64), (64, 65), (65, 201), (201, 300)]])
+    assert np.array_equal(got, full)
+
+
+def test_edge_cases(engine):
+    codes, offsets, lens = seqio.pack([seqio.encode("ACDEFGHIK")])
+    engine.upload(codes, offsets, lens)
+    assert engine.triangle().size == 0
+    assert np.array_equal(engine.rows([0]), [[9]])
+    codes, offsets, lens = seqio.pack([seqio.encode("ACD"), seqio.encode(""), seqio.encode("XXBZ*"), seqio.encode("DCA")])
+    engine.upload(codes, offsets, lens)
+    assert np.array_equal(engine.rows(np.arange(4)), pyoracle.lcs_rows(codes, offsets, lens, np.arange(4)))
+    with pytest.raises(Exception):
+        engine.rows([4])
+    with pytest.raises(Exception):
+        engine.triangle(0, 5)
+
+
+def test_full_size_properties(engine):
+    """BASELINE config 2 shape (10k x 400 aa): size-independent properties + oracle spot checks."""
+    codes, offsets, lens = seqio.synth_family(10000, 400, seed=1)
+    n = len(lens)
+    engine.upload(codes, offsets, lens)
+    tri = engine.triangle(dtype=np.uint16)
+    assert tri.size == n * (n - 1) // 2
+    rng = np.random.default_rng(0)
+    # (1) bounded by the shorter sequence, and > 0 for related sequences
+    i, j = np.tril_indices(n, -1)
+    sel = rng.integers(0, tri.size, size=200000)
+    assert np.all(tri[sel] <= np.minimum(lens[i[sel]], lens[j[sel]]))
+    # (2) symmetry of the true LCS: row mode (roles swapped) agrees with the triangle
+    refs = rng.integers(0, n, size=8)
+    rows = engine.rows(refs, dtype=np.uint16)
+    for r, ref in enumerate(refs):
+        below = tri[ref * (ref - 1) // 2: ref * (ref - 1) // 2 + ref]
+        assert np.array_equal(rows[r, :ref], below)
+        assert rows[r, ref] == lens[ref]
+        above = np.arange(ref + 1, n)
+        assert np.array_equal(rows[r, ref + 1:], tri[above * (above - 1) // 2 + ref])
+    # (3) oracle on random rows
+    for ref in rng.integers(1, n, size=3):
+        cols = rng.integers(0, ref, size=300)
+        want = pyoracle.lcs_rows(codes, offsets, lens, [ref], cols)[0]
+        assert np.array_equal(tri[ref * (ref - 1) // 2 + cols], want)
+    # (4) checksum of checksums is reproducible across a second run
+    assert int(tri.astype(np.uint64).sum()) == int(engine.triangle(dtype=np.uint16).astype(np.uint64).sum())
