@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's configuration.
+
+A "step" is one pass of the hot path over one batch: the all-pairs LCS triangle of a synthetic
+protein family (SURVEY.md section 8(d) generator).
+  N = 1 : configs[1] -- 10 000 proteins x 400 aa, 49 995 000 LCS lengths on one B200.
+  N > 1 : the same per-GPU work ("weak"): 10 000*sqrt(N) proteins, triangle rows sharded so that every
+          rank owns the same number of pairs, then ONE NCCL all-gather of the uint16 row blocks
+          (the north star's "final all-gather of the distance row blocks").
+value   = LCS pairs / s, inputs (residue codes + bit-mask tables) resident in HBM, results left in HBM.
+e2e     = the same metric through the host-buffer C ABI call a FAMSA guide-tree builder would make
+          (famsa_lcs_upload + famsa_lcs_triangle): H2D of the residues, mask build, kernel, D2H of
+          the triangle -- all inside the timed region, every step.
+--impl reference : the UNMODIFIED reference (oracle/_ref: CLCSBP AVX2 path driven by the reference's
+          own calculateDistanceVector, UPGMA's row-parallel shape) on all host threads, same config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_BASE, LEN, SEED = 10000, 400, 1
+METRIC = "pairwise LCS distances/sec"
+UNIT = "pairs/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload(n_gpus: int):
+    from famsa_b200 import seqio
+    n = int(round(N_BASE * math.sqrt(n_gpus)))
+    return seqio.synth_family(n, LEN, SEED), n
+
+
+def row_shards(n: int, parts: int):
+    """Row boundaries giving every rank the same number of pairs (rows i has i pairs)."""
+    total = n * (n - 1) // 2
+    bounds = [0]
+    for r in range(1, parts):
+        target = total * r / parts
+        b = int(round((1 + math.sqrt(1 + 8 * target)) / 2))
+        bounds.append(min(max(b, bounds[-1]), n))
+    bounds.append(n)
+    return bounds
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.kill()
+        inside = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        sm = sorted(float(r[0]) for r in inside if r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in inside:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(inside[0][1]) if inside else None,
+                "power_w_max": max((float(r[2]) for r in inside), default=None),
+                "samples": len(inside), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(codes, offsets, lens, n, threads, row_begin=0):
+    """Times the reference's own CPU path (oracle/_ref) on rows [row_begin, n) of the triangle."""
+    from famsa_b200 import seqio
+    from oracle import pyoracle
+    letters = []
+    for i in range(n):
+        o = int(offsets[i])
+        letters.append(seqio.decode(codes[o:o + int(lens[i])]))
+    rs = pyoracle.RefSeqSet(letters)
+    sec, pairs, _ = rs.triangle_mt(row_begin, n, threads, 2)
+    rs.close()
+    return sec, pairs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle
+    (codes, offsets, lens), n = workload(args.gpus)
+    threads = os.cpu_count() or 1
+    if not pyoracle.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libfamsa_ref.so not built"}))
+        return
+    # bounded sample: the last rows of the triangle holding ~1/4 of the pairs when the set is large
+    row_begin = 0 if n <= 12000 else int(n * math.sqrt(0.75))
+    for _ in range(args.warmup):
+        cpu_reference_run(codes, offsets, lens, n, threads, max(row_begin, n - 800))
+    secs, pairs = 0.0, 0
+    for _ in range(args.steps):
+        s, p = cpu_reference_run(codes, offsets, lens, n, threads, row_begin)
+        secs += s
+        pairs = p
+    value = pairs * args.steps / secs
+    sample = f"triangle rows [{row_begin},{n}) of {n} x {LEN} aa = {pairs} pairs/step"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": {"workload": f"LCS triangle, {n} x {LEN} aa synthetic family (seed {SEED})",
+                                           "n_seqs": n, "len": LEN},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+                             "sample": sample + "; CLCSBP AVX2 via calculateDistanceVector, one row per task"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import famsa_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    (codes, offsets, lens), n = workload(world)
+    bounds = row_shards(n, world)
+    rb, re = bounds[rank], bounds[rank + 1]
+    tri = lambda r: r * (r - 1) // 2 if r else 0
+    my_pairs = tri(re) - tri(rb)
+    total_pairs = tri(n)
+    shard_sizes = [tri(bounds[r + 1]) - tri(bounds[r]) for r in range(world)]
+    max_shard = max(shard_sizes)
+
+    eng = famsa_b200.Engine(local)
+    eng.upload(codes, offsets, lens)                       # resident inputs for the `value` leg
+    d_block = torch.empty(max(max_shard, 1), dtype=torch.int16, device="cuda")
+    d_all = torch.empty(max_shard * world, dtype=torch.int16, device="cuda") if world > 1 else None
+    side = torch.cuda.Stream()                             # non-default stream shared by our kernels and NCCL
+    torch.cuda.set_stream(side)
+    stream = side.cuda_stream
+    l2_flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def step_device():
+        eng.triangle_device(rb, re, d_block.data_ptr(), 2, stream)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_block)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- value: device-resident
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = eng.kernel_launches()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.time()
+    for s in range(args.steps):
+        l2_flush.fill_(s)                                  # L2 flush between timed iterations (untimed)
+        ev[s][0].record()
+        step_device()
+        ev[s][1].record()
+    barrier()
+    wall1 = time.time()
+    launches = eng.kernel_launches() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    value = total_pairs * args.steps / (dev_ms / 1e3)
+
+    # dominant kernel, timed live with CUDA events on its launch stream (single launch class at this config)
+    kern_ms = []
+    for _ in range(3):
+        l2_flush.fill_(1)
+        eng.triangle_device(rb, re, d_block.data_ptr(), 2, 0)   # ctx stream: synchronises + records timing
+        kern_ms.append(eng.last_timing()[1])
+    kern_ms = sorted(kern_ms)[1]
+
+    # ---------------- e2e: host buffers through the C ABI, copies inside the timed region
+    h_out = torch.empty(max(my_pairs, 1), dtype=torch.int16).pin_memory()
+    h_np = h_out.numpy().view(np.uint16)
+    codes_p = torch.from_numpy(codes).pin_memory().numpy()
+
+    def step_e2e():
+        eng.upload(codes_p, offsets, lens)
+        eng.triangle(rb, re, out=h_np)
+        if world > 1:
+            # the gathered triangle is what a host-side tree builder consumes
+            d_block[:my_pairs].copy_(h_out[:my_pairs].cuda(non_blocking=True))
+            dist.all_gather_into_tensor(d_all, d_block)
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.time() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = total_pairs * args.steps / e2e_s
+    h2d = int(codes.nbytes + offsets.nbytes + lens.nbytes)
+    d2h = int(my_pairs * 2)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        mean_len = float(lens.mean())
+        b_pair = mean_len + 4.0                           # streamed residues (u8) + u32 result
+        achieved = my_pairs * b_pair / (kern_ms / 1e3) / 1e9
+        prof = os.path.join(ROOT, "profiles", "lcs_tile_traffic.json")
+        traffic = json.load(open(prof)).get("dram_bytes_per_launch") if os.path.exists(prof) else None
+        word_steps = my_pairs * mean_len * math.ceil(mean_len / 32)        # 32-bit limb updates
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"LCS triangle, {n} x {LEN} aa synthetic family (seed {SEED})",
+                       "n_seqs": n, "len": LEN, "pairs_per_step": total_pairs, "rows_per_rank": [rb, re],
+                       "out": "uint16 packed lower triangle", "l2": "flushed between timed iterations (192 MiB write)",
+                       "multi_gpu": "row shards with equal pairs + one NCCL all-gather of row blocks" if world > 1 else "none"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "fb::k_lcs_tile<NL>",
+                         "kernel_ms": kern_ms, "bytes_per_pair": b_pair,
+                         "note": "integer-ALU bound, not HBM bound: see alu_model"},
+            "alu_model": {"limb_steps_per_s": word_steps / (kern_ms / 1e3),
+                          "int_ops_per_limb_step": 3,
+                          "alu_pipe_peak_lane_ops_per_s": 148 * 64 * (clocks["sm_mhz"] or 0) * 1e6 if clocks else None},
+        }
+        if clocks and clocks.get("sm_mhz"):
+            line["alu_model"]["frac_of_alu_pipe"] = (3 * word_steps / (kern_ms / 1e3)) / (148 * 64 * clocks["sm_mhz"] * 1e6)
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import pyoracle
+            if pyoracle.have_ref():
+                threads = os.cpu_count() or 1
+                sec, pairs = cpu_reference_run(codes, offsets, lens, n, threads, 0)
+                line["cpu_baseline"] = {"value": pairs / sec, "unit": UNIT, "cores": threads, "kind": "reference",
+                                        "sample": f"whole {n} x {LEN} aa triangle ({pairs} pairs, {sec:.2f} s), "
+                                                  "oracle/_ref AVX2 path, one row per task"}
+            else:
+                n_s = 600
+                t0 = time.time()
+                pyoracle.lcs_triangle(codes, offsets, lens, n - n_s, n)
+                sec = time.time() - t0
+                pairs = tri(n) - tri(n - n_s)
+                line["cpu_baseline"] = {"value": pairs / sec, "unit": UNIT, "cores": 1, "kind": "port",
+                                        "sample": f"last {n_s} rows ({pairs} pairs)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
