@@ -12,8 +12,22 @@ EXPORTED_SYMBOLS = [
     "famsa_abi_version", "famsa_create", "famsa_destroy", "famsa_last_error", "famsa_kernel_launches",
     "famsa_lcs_upload", "famsa_lcs_n_seqs", "famsa_lcs_triangle", "famsa_lcs_triangle_device",
     "famsa_lcs_rows", "famsa_lcs_rows_device", "famsa_transform_f64", "famsa_transform_f32",
-    "famsa_lcs_last_timing",
+    "famsa_lcs_last_timing", "famsa_dp_align_batch", "famsa_dp_align_batch_device", "famsa_dp_last_timing",
 ]
+
+
+class DpProfile(C.Structure):
+    _fields_ = [("scores", C.c_void_p), ("counters", C.c_void_p), ("width", C.c_uint32), ("card", C.c_uint32)]
+
+
+class DpJob(C.Structure):
+    _fields_ = [("p1", DpProfile), ("p2", DpProfile)]
+
+
+class DpResult(C.Structure):
+    _fields_ = [("total_score", C.c_int64), ("last", C.c_int64 * 3), ("path_offset", C.c_uint64),
+                ("dirs_offset", C.c_uint64), ("path_len", C.c_uint32), ("rows_width", C.c_uint32),
+                ("cols_width", C.c_uint32), ("swapped", C.c_uint8), ("variant", C.c_uint8), ("pad", C.c_uint8 * 2)]
 
 
 class FamsaError(RuntimeError):
@@ -57,6 +71,9 @@ def load_library() -> C.CDLL:
     lib.famsa_transform_f32.argtypes = [i32, u32, u32, u32]
     lib.famsa_transform_f32.restype = C.c_float
     lib.famsa_lcs_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(u64)]
+    lib.famsa_dp_align_batch.argtypes = [vp, vp, u32, vp, vp, vp, vp]
+    lib.famsa_dp_align_batch_device.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp]
+    lib.famsa_dp_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(u64)]
     _lib = lib
     return lib
 
@@ -135,6 +152,45 @@ class Engine:
                                                    C.c_void_p(d_col_ptr) if d_col_ptr else None, n_col,
                                                    C.c_void_p(d_out_ptr), elem_bytes,
                                                    C.c_void_p(stream) if stream else None))
+
+    # ---------------------------------------------------------------- HP-2
+    def dp_align_batch(self, jobs, gaps, want_dirs: bool = False):
+        """jobs: list of (scores1, counters1, card1, scores2, counters2, card2) with scores (W+1,32) int64 and
+        counters (W+1,32) int32 -- the two arguments of CProfile::Align.  Returns a list of dicts
+        (path, total, last, swapped, variant[, dirs]) in job order."""
+        n = len(jobs)
+        arr = (DpJob * max(n, 1))()
+        keep = []
+        path_total = dirs_total = 0
+        for k, (s1, c1, k1, s2, c2, k2) in enumerate(jobs):
+            s1 = np.ascontiguousarray(s1, dtype=np.int64); c1 = np.ascontiguousarray(c1, dtype=np.int32)
+            s2 = np.ascontiguousarray(s2, dtype=np.int64); c2 = np.ascontiguousarray(c2, dtype=np.int32)
+            keep += [s1, c1, s2, c2]
+            w1, w2 = s1.shape[0] - 1, s2.shape[0] - 1
+            arr[k].p1 = DpProfile(s1.ctypes.data, c1.ctypes.data, w1, k1)
+            arr[k].p2 = DpProfile(s2.ctypes.data, c2.ctypes.data, w2, k2)
+            path_total += w1 + w2
+            dirs_total += (w1 + 1) * (w2 + 1)
+        g = np.ascontiguousarray(gaps, dtype=np.int64)
+        res = (DpResult * max(n, 1))()
+        path = np.zeros(max(path_total, 1), dtype=np.uint8)
+        dirs = np.zeros(max(dirs_total, 1), dtype=np.uint8) if want_dirs else None
+        self._check(self.lib.famsa_dp_align_batch(self.h, C.byref(arr), n, _ptr(g), C.byref(res), _ptr(path), _ptr(dirs)))
+        out = []
+        for k in range(n):
+            r = res[k]
+            d = dict(path=path[r.path_offset:r.path_offset + r.path_len].copy(), total=int(r.total_score),
+                     last=np.array(list(r.last), dtype=np.int64), swapped=bool(r.swapped), variant=int(r.variant))
+            if want_dirs:
+                d["dirs"] = dirs[r.dirs_offset:r.dirs_offset + (r.rows_width + 1) * (r.cols_width + 1)].reshape(
+                    r.rows_width + 1, r.cols_width + 1).copy()
+            out.append(d)
+        return out
+
+    def dp_last_timing(self) -> tuple[float, float, int]:
+        t, m, p = C.c_float(), C.c_float(), C.c_uint64()
+        self._check(self.lib.famsa_dp_last_timing(self.h, C.byref(t), C.byref(m), C.byref(p)))
+        return t.value, m.value, p.value
 
     def last_timing(self) -> tuple[float, float, int]:
         t, m, p = C.c_float(), C.c_float(), C.c_uint64()

@@ -66,6 +66,9 @@ void famsa_destroy(famsa_ctx* ctx)
                           &S.d_group_blob, &S.d_raw_codes, &S.d_raw_off, &S.d_raw_len, &S.d_flags, &S.d_tiles,
                           &S.d_res, &S.d_refpos, &S.d_ids_a, &S.d_ids_b, &S.d_out_stage, &S.d_masks64, &S.d_x64})
         b->release();
+    fb::DpState& D = ctx->dp;
+    for (fb::DevBuf* b : {&D.d_jobs, &D.d_order, &D.d_scratch, &D.d_dirs, &D.d_tables, &D.d_results, &D.d_path})
+        b->release();
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -221,6 +224,54 @@ int famsa_lcs_last_timing(const famsa_ctx* ctx, float* total_ms, float* main_ker
     if (total_ms) *total_ms = ctx->lcs.last_total_ms;
     if (main_kernel_ms) *main_kernel_ms = ctx->lcs.last_main_ms;
     if (n_pairs) *n_pairs = ctx->lcs.last_pairs;
+    return FAMSA_OK;
+}
+
+// ------------------------------------------------------------------ HP-2
+
+static int dp_finish_timing(famsa_ctx* ctx)
+{
+    float total = 0.f, k = 0.f;
+    FB_CUDA(cudaEventSynchronize(ctx->ev[3]));
+    FB_CUDA(cudaEventElapsedTime(&total, ctx->ev[0], ctx->ev[3]));
+    FB_CUDA(cudaEventElapsedTime(&k, ctx->ev[1], ctx->ev[2]));
+    ctx->dp.last_total_ms = total;
+    ctx->dp.last_kernel_ms = k;
+    return FAMSA_OK;
+}
+
+int famsa_dp_align_batch(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n_jobs, const int64_t gaps[4],
+                         famsa_dp_result* results, uint8_t* path_buf, uint8_t* dirs_buf)
+{
+    FB_CHECK_CTX(ctx);
+    if (n_jobs && (!jobs || !gaps || !results || !path_buf)) { set_error("NULL argument"); return FAMSA_E_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    FB_CUDA(cudaSetDevice(ctx->device));
+    int rc = fb::dp_run_host(ctx, jobs, n_jobs, gaps, results, path_buf, dirs_buf);
+    if (rc) return rc;
+    return dp_finish_timing(ctx);
+}
+
+int famsa_dp_align_batch_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n_jobs, const int64_t gaps[4],
+                                famsa_dp_result* d_results, uint8_t* d_path_buf, uint8_t* d_dirs_buf, void* stream)
+{
+    FB_CHECK_CTX(ctx);
+    if (n_jobs && (!jobs || !gaps || !d_results || !d_path_buf)) { set_error("NULL argument"); return FAMSA_E_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    FB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    int rc = fb::dp_run_device(ctx, jobs, n_jobs, gaps, d_results, d_path_buf, d_dirs_buf, st);
+    if (rc) return rc;
+    if (!stream) { FB_CUDA(cudaStreamSynchronize(st)); return dp_finish_timing(ctx); }
+    return FAMSA_OK;
+}
+
+int famsa_dp_last_timing(const famsa_ctx* ctx, float* total_ms, float* kernel_ms, uint64_t* n_cells)
+{
+    FB_CHECK_CTX(ctx);
+    if (total_ms) *total_ms = ctx->dp.last_total_ms;
+    if (kernel_ms) *kernel_ms = ctx->dp.last_kernel_ms;
+    if (n_cells) *n_cells = ctx->dp.last_cells;
     return FAMSA_OK;
 }
 

@@ -59,6 +59,13 @@ struct LcsState {
     uint64_t last_pairs = 0;
 };
 
+struct DpState {
+    DevBuf d_jobs, d_order, d_scratch, d_dirs, d_tables, d_results, d_path;
+    std::vector<uint8_t> h_stage;
+    uint64_t last_cells = 0;
+    float last_total_ms = 0.f, last_kernel_ms = 0.f;
+};
+
 } // namespace fb
 
 struct famsa_ctx {
@@ -69,6 +76,7 @@ struct famsa_ctx {
     uint64_t launches = 0;
     int sm_count = 0;
     fb::LcsState lcs;
+    fb::DpState dp;
 };
 
 namespace fb {
@@ -80,4 +88,9 @@ int lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_o
 int lcs_rows(famsa_ctx* ctx, const uint32_t* d_ref_ids, const uint32_t* h_ref_ids, uint32_t n_ref,
              const uint32_t* d_col_ids, uint32_t n_col, void* d_out, int elem_bytes,
              cudaStream_t stream);
+// dp.cu
+int dp_run_host(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int64_t gaps[4], famsa_dp_result* results,
+                uint8_t* path_buf, uint8_t* dirs_buf);
+int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int64_t gaps[4],
+                  famsa_dp_result* d_results, uint8_t* d_path, uint8_t* d_dirs, cudaStream_t st);
 } // namespace fb

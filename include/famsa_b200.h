@@ -109,6 +109,69 @@ float famsa_transform_f32(int kind, uint32_t lcs, uint32_t len1, uint32_t len2);
 int famsa_lcs_last_timing(const famsa_ctx* ctx, float* total_ms, float* main_kernel_ms,
                           uint64_t* n_pairs);
 
+/* ------------------------------------------------------------------ HP-2: profile alignment DP
+ *
+ * Replaces the body of
+ *   void CProfile::Align(CProfile* profile1, CProfile* profile2, uint32_t no_threads,
+ *                        uint32_t no_rows_per_box, ...)            src/core/profile.cpp:244-305
+ * i.e. the variant/orientation choice and the six cell loops
+ *   AlignSeqSeq / AlignSeqProf / AlignProfProf                    src/core/profile_seq.cpp:24,165,495
+ *   ParAlignSeqProf / ParAlignProfProf                            src/core/profile_par.cpp:26,441
+ * with their helpers DP_SolveGapsProblemWhenStarting/Continuing    src/core/profile.cpp:1223-1315
+ * and the traceback at the top of ConstructProfile                 src/core/profile.cpp:727-782,
+ * for MANY independent merges per call (all ready nodes of the guide tree: what CProfileQueue,
+ * src/core/queues.cpp:127-187, hands to the worker threads one at a time).
+ * The merged-profile construction (rest of ConstructProfile, profile.cpp:784-1002) stays on the
+ * host and consumes `path`; the unbanded variants are implemented (what every no_threads > 1
+ * call and every progressive-alignment call uses; the banded refinement calls pass NULL
+ * column mappings only when unguided -- see INTEGRATION.md).
+ * Scores are int64 (score_t, src/core/defs.h:36-40): results are bit-exact, not "within 1 ulp".
+ */
+
+typedef struct {
+    const int64_t* scores;   /* CProfileValues<score_t,32>: (width+1) columns x 32 rows, column c at scores + 32*c */
+    const int32_t* counters; /* CProfileValues<counter_t,32>: same shape */
+    uint32_t width;          /* CProfile::width */
+    uint32_t card;           /* CProfile::data.size() */
+} famsa_dp_profile;
+
+typedef struct {
+    famsa_dp_profile p1, p2; /* the two arguments of CProfile::Align, in call order */
+} famsa_dp_job;
+
+typedef struct {
+    int64_t total_score;     /* CProfile::total_score of the merged profile */
+    int64_t last[3];         /* dp_row_elem_t {D,H,V} at (W_rows, W_cols), ConstructProfile's last_elem */
+    uint64_t path_offset;    /* this job's path starts at path_buf + path_offset */
+    uint64_t dirs_offset;    /* this job's CDPMatrix bytes start at dirs_buf + dirs_offset (if requested) */
+    uint32_t path_len;       /* = width of the merged profile */
+    uint32_t rows_width, cols_width; /* after orientation */
+    uint8_t swapped;         /* 1: rows of the DP matrix = p2 (Align called the cell loop as (p2, p1)) */
+    uint8_t variant;         /* 0 AlignSeqSeq, 1 AlignSeqProf, 2 AlignProfProf */
+    uint8_t pad[2];
+} famsa_dp_result;
+
+/* gaps[4] = {gap_open, gap_ext, gap_term_open, gap_term_ext} (CParams, already rescaled,
+ * src/msa.cpp:83-106).  path_buf receives, per job, path_len direction_t bytes in forward order
+ * (0 D: a row and a column are consumed, 1 H: column only, 2 V: row only) == ConstructProfile's
+ * path[1..width]; job k starts at offset sum_{m<k}(p1.width + p2.width) (also reported).
+ * dirs_buf may be NULL; otherwise it receives each job's (rows_width+1) x (cols_width+1)
+ * CDPMatrix bytes (dirD | dirH<<2 | dirV<<4, src/core/profile.h:93-142) at offset
+ * sum_{m<k}(p1.width+1)(p2.width+1).  All pointers are HOST memory. */
+int famsa_dp_align_batch(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n_jobs, const int64_t gaps[4],
+                         famsa_dp_result* results, uint8_t* path_buf, uint8_t* dirs_buf);
+
+/* Same, but with the profile tables already resident in HBM (famsa_dp_profile pointers are DEVICE
+ * pointers; results/path/dirs are DEVICE buffers); used to time the kernels without PCIe.
+ * Variant/orientation are then decided on the device too.  stream: cudaStream_t or NULL. */
+int famsa_dp_align_batch_device(famsa_ctx* ctx, const famsa_dp_job* h_jobs_with_device_ptrs, uint32_t n_jobs,
+                                const int64_t gaps[4], famsa_dp_result* d_results, uint8_t* d_path_buf,
+                                uint8_t* d_dirs_buf, void* stream);
+
+/* Timing of the most recent DP call: total device time and the DP kernel alone (CUDA events on the
+ * launch stream), and the number of DP cells (sum of rows_width * cols_width). */
+int famsa_dp_last_timing(const famsa_ctx* ctx, float* total_ms, float* kernel_ms, uint64_t* n_cells);
+
 #ifdef __cplusplus
 }
 #endif

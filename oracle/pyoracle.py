@@ -43,8 +43,35 @@ def oracle() -> C.CDLL:
         lib.lcs_oracle_transform_f64.restype = C.c_double
         lib.lcs_oracle_transform_f32.argtypes = [C.c_int, u32, u32, u32]
         lib.lcs_oracle_transform_f32.restype = C.c_float
+        lib.dp_oracle_align.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         _oracle = lib
     return _oracle
+
+
+class DpProfile(C.Structure):
+    _fields_ = [("scores", C.c_void_p), ("counters", C.c_void_p), ("width", C.c_uint32), ("card", C.c_uint32)]
+
+
+def dp_align(scores1, counters1, card1, scores2, counters2, card2, gaps, score_matrix=None):
+    """Oracle version of CProfile::Align + traceback.  scores: (W+1,32) int64, counters: (W+1,32) int32.
+    Returns dict(path uint8[], total, last(3), swapped, variant, dirs (WR+1, WC+1) uint8)."""
+    lib = oracle()
+    s1 = np.ascontiguousarray(scores1, dtype=np.int64); c1 = np.ascontiguousarray(counters1, dtype=np.int32)
+    s2 = np.ascontiguousarray(scores2, dtype=np.int64); c2 = np.ascontiguousarray(counters2, dtype=np.int32)
+    w1, w2 = s1.shape[0] - 1, s2.shape[0] - 1
+    p1 = DpProfile(s1.ctypes.data, c1.ctypes.data, w1, card1)
+    p2 = DpProfile(s2.ctypes.data, c2.ctypes.data, w2, card2)
+    g = np.ascontiguousarray(gaps, dtype=np.int64)
+    sm = None if score_matrix is None else np.ascontiguousarray(score_matrix, dtype=np.int64)
+    dirs = np.zeros((w1 + 1) * (w2 + 1), dtype=np.uint8)
+    path = np.zeros(w1 + w2 + 1, dtype=np.uint8)
+    plen = C.c_uint32(); total = C.c_int64(); sw = C.c_int(); var = C.c_int()
+    last = np.zeros(3, dtype=np.int64)
+    lib.dp_oracle_align(C.byref(p1), C.byref(p2), _p(g), _p(sm), _p(dirs), _p(path), C.byref(plen), _p(last),
+                        C.byref(total), C.byref(sw), C.byref(var))
+    wr, wc = (w2, w1) if sw.value else (w1, w2)
+    return dict(path=path[:plen.value].copy(), total=total.value, last=last, swapped=bool(sw.value),
+                variant=var.value, dirs=dirs.reshape(wr + 1, wc + 1))
 
 
 def lcs_rows(codes, offsets, lens, ref_ids, col_ids=None, n_col=None) -> np.ndarray:
@@ -99,8 +126,109 @@ def ref() -> C.CDLL:
         lib.ref_transform_f64.restype = C.c_double
         lib.ref_transform_f32.argtypes = [C.c_int, u32, u32, u32]
         lib.ref_transform_f32.restype = C.c_float
+        i64 = C.c_int64
+        lib.ref_dp_create.argtypes = [C.c_int, C.c_int, C.c_int]
+        lib.ref_dp_create.restype = vp
+        lib.ref_dp_destroy.argtypes = [vp]
+        lib.ref_dp_gaps.argtypes = [vp, vp]
+        lib.ref_dp_set_gaps.argtypes = [vp, vp]
+        lib.ref_dp_score_matrix.argtypes = [vp, vp]
+        lib.ref_profile_create.argtypes = [vp, vp, vp, u32]
+        lib.ref_profile_create.restype = vp
+        lib.ref_profile_leaf.argtypes = [vp, C.c_char_p, C.c_int]
+        lib.ref_profile_leaf.restype = vp
+        lib.ref_profile_destroy.argtypes = [vp]
+        lib.ref_profile_width.argtypes = [vp]
+        lib.ref_profile_width.restype = u32
+        lib.ref_profile_card.argtypes = [vp]
+        lib.ref_profile_card.restype = u32
+        lib.ref_profile_total_score.argtypes = [vp]
+        lib.ref_profile_total_score.restype = i64
+        lib.ref_profile_tables.argtypes = [vp, vp, vp]
+        lib.ref_profile_row.argtypes = [vp, u32, vp]
+        lib.ref_profile_row.restype = C.c_int
+        lib.ref_profile_align.argtypes = [vp, vp, vp, C.c_int]
+        lib.ref_profile_align.restype = vp
         _ref = lib
     return _ref
+
+
+class RefDp:
+    """The reference's CProfile machinery behind oracle/ref_harness.cpp."""
+
+    def __init__(self, n_seqs_for_rescale: int = 0, matrix_type: int = 2, pool_threads: int = 2):
+        self.lib = ref()
+        self.h = C.c_void_p(self.lib.ref_dp_create(n_seqs_for_rescale, matrix_type, pool_threads))
+
+    def close(self):
+        if self.h:
+            self.lib.ref_dp_destroy(self.h)
+            self.h = None
+
+    def gaps(self) -> np.ndarray:
+        g = np.zeros(4, dtype=np.int64)
+        self.lib.ref_dp_gaps(self.h, _p(g))
+        return g
+
+    def set_gaps(self, g):
+        g = np.ascontiguousarray(g, dtype=np.int64)
+        self.lib.ref_dp_set_gaps(self.h, _p(g))
+
+    def score_matrix(self) -> np.ndarray:
+        m = np.zeros((24, 24), dtype=np.int64)
+        self.lib.ref_dp_score_matrix(self.h, _p(m))
+        return m
+
+    def profile(self, gapped: list[str], seq_nos: list[int]):
+        arr = (C.c_char_p * len(gapped))(*[s.encode("ascii") for s in gapped])
+        nos = np.ascontiguousarray(seq_nos, dtype=np.int32)
+        return C.c_void_p(self.lib.ref_profile_create(self.h, arr, _p(nos), len(gapped)))
+
+    def leaf(self, letters: str, seq_no: int):
+        return C.c_void_p(self.lib.ref_profile_leaf(self.h, letters.encode("ascii"), seq_no))
+
+    def free(self, p):
+        self.lib.ref_profile_destroy(p)
+
+    def tables(self, p):
+        w = self.lib.ref_profile_width(p)
+        sc = np.zeros((w + 1, 32), dtype=np.int64)
+        cn = np.zeros((w + 1, 32), dtype=np.int32)
+        self.lib.ref_profile_tables(p, _p(sc), _p(cn))
+        return sc, cn, int(self.lib.ref_profile_card(p))
+
+    def rows(self, p) -> dict[int, str]:
+        w = self.lib.ref_profile_width(p)
+        out = {}
+        buf = C.create_string_buffer(w + 2)
+        for i in range(self.lib.ref_profile_card(p)):
+            no = self.lib.ref_profile_row(p, i, buf)
+            out[no] = buf.value.decode()
+        return out
+
+    def align(self, p1, p2, no_threads: int = 1):
+        """Returns (merged profile handle, total_score).  p1 and p2 are consumed and freed."""
+        m = C.c_void_p(self.lib.ref_profile_align(self.h, p1, p2, no_threads))
+        self.lib.ref_profile_destroy(p1)
+        self.lib.ref_profile_destroy(p2)
+        return m, int(self.lib.ref_profile_total_score(m))
+
+
+def path_from_rows(rows: dict[int, str], members1: set, members2: set, swapped: bool) -> np.ndarray:
+    """Reconstruct the traceback path (0 D, 1 H, 2 V in (row profile, column profile) terms) from
+    the merged alignment: every child column holds at least one residue."""
+    width = len(next(iter(rows.values())))
+    in1 = np.zeros(width, dtype=bool)
+    in2 = np.zeros(width, dtype=bool)
+    for no, s in rows.items():
+        a = np.frombuffer(s.encode(), dtype=np.uint8) != ord("-")
+        if no in members1:
+            in1 |= a
+        else:
+            in2 |= a
+    inr, inc = (in2, in1) if swapped else (in1, in2)
+    assert np.all(inr | inc)
+    return np.where(inr & inc, 0, np.where(inc, 1, 2)).astype(np.uint8)
 
 
 class RefSeqSet:

@@ -16,6 +16,7 @@
 //   CProfile(CProfile*, CProfile*, CParams*, ...) -> Align src/core/profile.cpp:69-75, 244-305
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -176,6 +177,131 @@ float ref_transform_f32(int kind, uint32_t lcs, uint32_t len1, uint32_t len2)
     if (kind == 0) { Transform<float, Distance::indel075_div_lcs> t; return t(lcs, len1, len2); }
     if (kind == 1) { Transform<float, Distance::indel_div_lcs> t; return t(lcs, len1, len2); }
     Transform<float, Distance::pairwise_identity> t; return t(lcs, len1, len2);
+}
+
+// ---------------------------------------------------------------- HP-2: profile alignment
+// A DP session owns a CParams prepared exactly as CFAMSA does before ComputeAlignment:
+//   score matrix  = round(matrix * cost_cast_factor)         (msa.cpp:59-80, initScoreMatrix)
+//   gap costs     = CParams defaults, rescaled by 1 + log2(n/45)/7 when n >= 45 (msa.cpp:83-106)
+// (those two small routines live in msa.cpp, which drags in the I/O libraries; their arithmetic is
+// restated here in the harness -- the DP itself is the reference's own object code).
+struct DpSession {
+    CParams params;
+    std::unique_ptr<refresh::active_thread_pool_v2> atp;
+};
+
+void* ref_dp_create(int n_seqs_for_rescale, int matrix_type, int pool_threads)
+{
+    auto* s = new DpSession();
+    CParams& P = s->params;
+    P.matrix_type = (ScoringMatrices::matrix_type_t)matrix_type;   // 0 MIQS, 1 PFASUM31, 2 PFASUM43 (default), 3 PFASUM60
+    auto& sm = ScoringMatrices::get_matrix(P.matrix_type);
+    P.score_matrix.assign(NO_AMINOACIDS, std::vector<score_t>());
+    P.score_vector.clear();
+    for (int i = 0; i < NO_AMINOACIDS; ++i) {
+        P.score_vector.emplace_back((score_t)round(sm[i][i] * cost_cast_factor));
+        for (int j = 0; j < NO_AMINOACIDS; ++j)
+            P.score_matrix[i].emplace_back((score_t)round(sm[i][j] * cost_cast_factor));
+    }
+    if (n_seqs_for_rescale > 0 && P.enable_gap_rescaling) {
+        double gap_scaler = log2(n_seqs_for_rescale / (double)P.scaler_log);
+        if (n_seqs_for_rescale < (int)P.scaler_log) gap_scaler = 1.0;
+        else gap_scaler = 1.0 + (gap_scaler / P.scaler_div);
+        P.gap_ext = (score_t)(P.gap_ext * gap_scaler);
+        P.gap_open = (score_t)(P.gap_open * gap_scaler);
+        P.gap_term_ext = (score_t)(P.gap_term_ext * gap_scaler);
+        P.gap_term_open = (score_t)(P.gap_term_open * gap_scaler);
+    }
+    P.instruction_set = instruction_set_t::avx2;
+    P.n_threads = pool_threads;
+    s->atp.reset(new refresh::active_thread_pool_v2(pool_threads, pool_threads));
+    return s;
+}
+void ref_dp_destroy(void* h) { delete static_cast<DpSession*>(h); }
+
+// out4 = {gap_open, gap_ext, gap_term_open, gap_term_ext}
+void ref_dp_gaps(void* h, int64_t* out4)
+{
+    CParams& P = static_cast<DpSession*>(h)->params;
+    out4[0] = P.gap_open; out4[1] = P.gap_ext; out4[2] = P.gap_term_open; out4[3] = P.gap_term_ext;
+}
+void ref_dp_set_gaps(void* h, const int64_t* in4)
+{
+    CParams& P = static_cast<DpSession*>(h)->params;
+    P.gap_open = in4[0]; P.gap_ext = in4[1]; P.gap_term_open = in4[2]; P.gap_term_ext = in4[3];
+}
+void ref_dp_score_matrix(void* h, int64_t* out24x24)
+{
+    CParams& P = static_cast<DpSession*>(h)->params;
+    for (int i = 0; i < 24; ++i)
+        for (int j = 0; j < 24; ++j) out24x24[i * 24 + j] = P.score_matrix[i][j];
+}
+
+// profile from already-aligned (gapped) strings: AppendRawSequence + CalculateCountersScores,
+// the way CFAMSA::alignProfiles does (msa.cpp:680-689); one ungapped string = a leaf profile.
+void* ref_profile_create(void* h, const char* const* gapped, const int* seq_nos, uint32_t n)
+{
+    auto* s = static_cast<DpSession*>(h);
+    auto* p = new CProfile(&s->params, s->atp.get());
+    for (uint32_t i = 0; i < n; ++i) {
+        CGappedSequence gs("s" + std::to_string(seq_nos[i]), std::string(gapped[i]), seq_nos[i], nullptr);
+        p->AppendRawSequence(gs);
+    }
+    p->CalculateCountersScores();
+    return p;
+}
+// leaf profile as the main flow builds it: CSequence -> CGappedSequence(CSequence&&) (msa.cpp:595)
+// -> new CProfile(*gs, &params) (msa.cpp:391).  `letters` is the ungapped residue string.
+void* ref_profile_leaf(void* h, const char* letters, int seq_no)
+{
+    auto* s = static_cast<DpSession*>(h);
+    CSequence seq("s" + std::to_string(seq_no), std::string(letters), seq_no, nullptr);
+    CGappedSequence gs(std::move(seq));
+    return new CProfile(gs, &s->params);
+}
+void ref_profile_destroy(void* p) { delete static_cast<CProfile*>(p); }
+uint32_t ref_profile_width(void* p) { return (uint32_t)static_cast<CProfile*>(p)->width; }
+uint32_t ref_profile_card(void* p) { return (uint32_t)static_cast<CProfile*>(p)->data.size(); }
+int64_t ref_profile_total_score(void* p) { return static_cast<CProfile*>(p)->total_score; }
+
+// scores: (width+1) x 32 int64, counters: (width+1) x 32 int32, column-major as in CProfileValues
+void ref_profile_tables(void* p, int64_t* scores, int32_t* counters)
+{
+    auto* q = static_cast<CProfile*>(p);
+    for (size_t c = 0; c <= q->width; ++c)
+        for (size_t r = 0; r < NO_SYMBOLS; ++r) {
+            scores[c * NO_SYMBOLS + r] = q->scores.get_value(c, r);
+            counters[c * NO_SYMBOLS + r] = q->counters.get_value(c, r);
+        }
+}
+
+// gapped row i of the profile (width characters + NUL) and its sequence number
+int ref_profile_row(void* p, uint32_t i, char* out)
+{
+    // CGappedSequence::Decode() rewrites symbols[] in place (sequence.cpp:430-437), so the row is
+    // rendered here without touching the object: n_gaps[0] gaps, then symbol k followed by n_gaps[k].
+    static const char* letters = "ARNDCQEGHILKMFPSTWYVBZX*";
+    auto* q = static_cast<CProfile*>(p);
+    CGappedSequence* gs = q->data[i];
+    size_t at = 0;
+    for (uint32_t g = 0; g < gs->n_gaps[0]; ++g) out[at++] = '-';
+    for (size_t k = 1; k <= gs->size; ++k) {
+        const int c = gs->symbols[k];
+        out[at++] = (c >= 0 && c < 24) ? letters[c] : '?';
+        for (uint32_t g = 0; g < gs->n_gaps[k]; ++g) out[at++] = '-';
+    }
+    out[at] = 0;
+    return gs->sequence_no;
+}
+
+// new CProfile(p1, p2, params, no_threads, 4, atp): CProfile::Align + ConstructProfile.  The children
+// are consumed (their rows move into the result) exactly as in ComputeAlignment (msa.cpp:404-407);
+// the caller still has to ref_profile_destroy() them.
+void* ref_profile_align(void* h, void* p1, void* p2, int no_threads)
+{
+    auto* s = static_cast<DpSession*>(h);
+    return new CProfile(static_cast<CProfile*>(p1), static_cast<CProfile*>(p2), &s->params,
+                        (uint32_t)no_threads, 4, s->atp.get());
 }
 
 } // extern "C"

@@ -44,5 +44,95 @@ def main():
     print("adeno_fiber_lcs.npz:", lcs.shape, "lcs range", lcs.min(), lcs.max())
 
 
+def make_dp():
+    """HP-2 fixtures.  Needs oracle/_ref (the compiled reference).
+    adeno_pp.npz            the reference's single profile-profile golden: test/adeno_fiber/
+                            upgma.no_refine.part{1,2}.fasta -> upgma.pp.fasta.  Holds the two profiles'
+                            score/counter tables exactly as CFAMSA::alignProfiles builds them, the rescaled gap
+                            costs, and the reference outcome (traceback path, total score); generation asserts that
+                            the reference run reproduces upgma.pp.fasta byte for byte.
+    adeno_upgma_merges.npz  all 241 merges of test/adeno_fiber/upgma.dnd (refinement off): sequences, merge list and
+                            per-merge reference outcome; generation asserts the final alignment equals
+                            upgma.no_refine.fasta.  Inputs of each merge are rebuilt by the tests with oracle/_ref.
+    """
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from oracle import pyoracle
+    from treeutil import parse_newick
+    T = os.path.join(REF, "adeno_fiber")
+    i1, s1 = seqio.read_fasta(os.path.join(T, "upgma.no_refine.part1.fasta"))
+    i2, s2 = seqio.read_fasta(os.path.join(T, "upgma.no_refine.part2.fasta"))
+    ig, sg = seqio.read_fasta(os.path.join(T, "upgma.pp.fasta"))
+    dp = pyoracle.RefDp(len(s1) + len(s2))            # famsa.cpp:94 adjustParams(sizes[0] + sizes[1])
+    gaps = dp.gaps()
+    m1, m2 = set(range(len(s1))), set(range(len(s1), len(s1) + len(s2)))
+    p1 = dp.profile([s.upper() for s in s1], sorted(m1))
+    p2 = dp.profile([s.upper() for s in s2], sorted(m2))
+    t1, c1, k1 = dp.tables(p1)
+    t2, c2, k2 = dp.tables(p2)
+    m, total = dp.align(p1, p2, 1)
+    rows = dp.rows(m)
+    gold = {n: s.upper() for n, s in zip(ig, sg)}
+    names = i1 + i2
+    assert all(rows[k] == gold[names[k]] for k in rows), "reference run does not reproduce upgma.pp.fasta"
+    o = pyoracle.dp_align(t1, c1, k1, t2, c2, k2, gaps)
+    path = pyoracle.path_from_rows(rows, m1, m2, o["swapped"])[:len(o["path"])]
+    np.savez_compressed(os.path.join(HERE, "adeno_pp.npz"), s1=t1, c1=c1, k1=k1, s2=t2, c2=c2, k2=k2, gaps=gaps,
+                        path=path, total=total, swapped=o["swapped"])
+    print("adeno_pp.npz: widths", t1.shape[0] - 1, t2.shape[0] - 1, "path", len(path), "total", total)
+    dp.free(m); dp.close()
+
+    ids, seqs = seqio.read_fasta(os.path.join(T, "adeno_fiber"))
+    name2seq = dict(zip(ids, seqs))
+    leaves, merges = parse_newick(open(os.path.join(T, "upgma.dnd")).read())
+    ig, sg = seqio.read_fasta(os.path.join(T, "upgma.no_refine.fasta"))
+    gold = dict(zip(ig, sg))
+    lseqs = [name2seq[n].upper() for n in leaves]
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from dp_cases import reference_merges
+    g, recs = reference_merges(lseqs, merges, threads=(1,))
+    final = recs[-1]["rows"]
+    assert all(final[i] == gold[leaves[i]].upper() for i in range(len(leaves))), "does not reproduce upgma.no_refine.fasta"
+    totals, paths, plen, swapped = [], [], [], []
+    for r in recs:
+        o = pyoracle.dp_align(*r["job"], g)
+        pth = pyoracle.path_from_rows(r["rows"], r["m1"], r["m2"], o["swapped"])
+        totals.append(r["total"]); paths.append(pth); plen.append(len(pth)); swapped.append(o["swapped"])
+    np.savez_compressed(os.path.join(HERE, "adeno_upgma_merges.npz"), seqs=np.array(lseqs), merges=np.array(merges),
+                        gaps=g, totals=np.array(totals, dtype=np.int64), path=np.concatenate(paths),
+                        path_len=np.array(plen), swapped=np.array(swapped))
+    print("adeno_upgma_merges.npz:", len(recs), "merges, sum path", sum(plen))
+
+
+def make_hemopexin():
+    """hemopexin_medoid_sl.npz -- BASELINE config 4: every merge of test/hemopexin/medoid-sl.dnd (4188 sequences,
+    4187 merges, refinement is off for N > 1000).  Sequences, merge list, per-merge reference total score and a
+    CRC of each traceback path; generation asserts the final alignment equals test/hemopexin/medoid-sl.fasta."""
+    import zlib
+    from oracle import pyoracle
+    from treeutil import parse_newick
+    from dp_cases import reference_merges
+    T = os.path.join(REF, "hemopexin")
+    ids, seqs = seqio.read_fasta(os.path.join(T, "hemopexin"))
+    name2seq = dict(zip(ids, seqs))
+    leaves, merges = parse_newick(open(os.path.join(T, "medoid-sl.dnd")).read())
+    lseqs = [name2seq[n].upper() for n in leaves]
+    g, recs = reference_merges(lseqs, merges, threads=(1,))
+    ig, sg = seqio.read_fasta(os.path.join(T, "medoid-sl.fasta"))
+    gold = dict(zip(ig, sg))
+    final = recs[-1]["rows"]
+    assert all(final[i] == gold[leaves[i]].upper() for i in range(len(leaves))), "does not reproduce medoid-sl.fasta"
+    totals, crcs = [], []
+    for r in recs:
+        o = pyoracle.dp_align(*r["job"], g)
+        pth = pyoracle.path_from_rows(r["rows"], r["m1"], r["m2"], o["swapped"])
+        assert np.array_equal(pth, o["path"]) and o["total"] == r["total"]
+        totals.append(r["total"]); crcs.append(zlib.crc32(pth.tobytes()))
+    np.savez_compressed(os.path.join(HERE, "hemopexin_medoid_sl.npz"), seqs=np.array(lseqs), merges=np.array(merges),
+                        gaps=g, totals=np.array(totals, dtype=np.int64), path_crc=np.array(crcs, dtype=np.uint32))
+    print("hemopexin_medoid_sl.npz:", len(recs), "merges")
+
+
 if __name__ == "__main__":
     main()
+    make_dp()
+    make_hemopexin()

@@ -1,0 +1,111 @@
+"""GPU parity tests for HP-2 (through the C ABI).  int64 scores -> bit-exact, paths byte-identical."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from dp_cases import check_against_reference, random_tree, reference_merges
+from famsa_b200 import seqio
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+needs_ref = pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref not built")
+
+
+def assert_same(got, want, dirs=True):
+    assert got["variant"] == want["variant"] and got["swapped"] == want["swapped"]
+    assert got["total"] == want["total"]
+    assert np.array_equal(got["last"], want["last"])
+    assert np.array_equal(got["path"], want["path"])
+    if dirs:
+        assert np.array_equal(got["dirs"], want["dirs"])
+
+
+def test_pp_golden(engine):
+    """The reference's profile-profile known answer (upgma.pp.fasta), incl. the whole direction matrix."""
+    z = np.load(os.path.join(GOLDEN, "adeno_pp.npz"))
+    job = (z["s1"], z["c1"], int(z["k1"]), z["s2"], z["c2"], int(z["k2"]))
+    got = engine.dp_align_batch([job], z["gaps"], want_dirs=True)[0]
+    assert got["total"] == int(z["total"]) and np.array_equal(got["path"], z["path"])
+    assert_same(got, pyoracle.dp_align(*job, z["gaps"]))
+
+
+@needs_ref
+def test_all_merges_of_golden_upgma_tree(engine):
+    """241 merges behind upgma.no_refine.fasta in ONE batch: every variant, oracle + reference + fixture."""
+    z = np.load(os.path.join(GOLDEN, "adeno_upgma_merges.npz"))
+    seqs = [str(s) for s in z["seqs"]]
+    merges = [tuple(int(x) for x in m) for m in z["merges"]]
+    g, recs = reference_merges(seqs, merges, threads=(1,))
+    got = engine.dp_align_batch([r["job"] for r in recs], g, want_dirs=True)
+    check_against_reference(got, recs)
+    assert [r["total"] for r in got] == [int(t) for t in z["totals"]]
+    assert np.array_equal(np.concatenate([r["path"] for r in got]), z["path"])
+    for r, rec in zip(got, recs):
+        assert_same(r, pyoracle.dp_align(*rec["job"], g))
+
+
+@needs_ref
+def test_hemopexin_all_merges(engine):
+    """BASELINE config 4: all 4187 guide-tree merges of test/hemopexin (medoid-sl tree) on one B200, level by
+    level the way a host scheduler would submit them; totals and path CRCs pinned by the fixture, which was
+    generated from a reference run that reproduces medoid-sl.fasta byte for byte."""
+    from treeutil import levels
+    z = np.load(os.path.join(GOLDEN, "hemopexin_medoid_sl.npz"))
+    seqs = [str(s) for s in z["seqs"]]
+    merges = [tuple(int(x) for x in m) for m in z["merges"]]
+    g, recs = reference_merges(seqs, merges, threads=(1,))
+    assert np.array_equal(g, z["gaps"])
+    n_checked = 0
+    for lvl in levels(len(seqs), merges):
+        got = engine.dp_align_batch([recs[k]["job"] for k in lvl], g)
+        for k, r in zip(lvl, got):
+            assert r["total"] == int(z["totals"][k]) == recs[k]["total"], f"merge {k}"
+            assert zlib.crc32(r["path"].tobytes()) == int(z["path_crc"][k]), f"merge {k}"
+            n_checked += 1
+    assert n_checked == 4187
+    check_against_reference(engine.dp_align_batch([recs[k]["job"] for k in range(4000, 4187)], g), recs[4000:])
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,n,length,gaps", [(11, 70, 60, None), (12, 24, 500, None), (13, 40, 33, (-9000, -700, -300, -100)),
+                                                (14, 12, 1300, None), (15, 30, 31, (-20000, -2000, -2500, -900))])
+def test_random_families(engine, seed, n, length, gaps):
+    """Ragged widths around the 32-row stripe size, > 1000 columns, non-default gap costs, X/B/Z residues."""
+    rng = np.random.default_rng(seed)
+    codes, off, lens = seqio.synth_family(n, length, seed, sort_desc=False)
+    seqs = [seqio.decode(codes[int(o):int(o) + int(l)]) for o, l in zip(off, lens)]
+    seqs[1] = seqs[1][:3] + "XBZ*" + seqs[1][7:]
+    merges = random_tree(n, rng)
+    g, recs = reference_merges(seqs, merges, threads=(1, 2), rng=rng, gaps=gaps)
+    got = engine.dp_align_batch([r["job"] for r in recs], g, want_dirs=True)
+    check_against_reference(got, recs)
+    for r, rec in zip(got, recs):
+        assert_same(r, pyoracle.dp_align(*rec["job"], g))
+
+
+def test_tiny_and_degenerate(engine):
+    """Width-1 profiles, 1 x many, without the reference (oracle only)."""
+    rng = np.random.default_rng(3)
+
+    def prof(width, card):
+        c = np.zeros((width + 1, 32), dtype=np.int32)
+        for j in range(1, width + 1):
+            for _ in range(card):
+                c[j, int(rng.integers(0, 24))] += 1
+        s = rng.integers(-5000, 5000, size=(width + 1, 32)).astype(np.int64) * card
+        return s, c, card
+
+    gaps = np.array([-14850, -1250, -660, -660], dtype=np.int64)
+    jobs = []
+    for w1, k1, w2, k2 in [(1, 1, 1, 1), (1, 1, 7, 1), (5, 1, 1, 3), (1, 4, 1, 2), (33, 2, 32, 5), (64, 3, 65, 3), (2, 1, 40, 9)]:
+        a, b = prof(w1, k1), prof(w2, k2)
+        jobs.append((a[0], a[1], a[2], b[0], b[1], b[2]))
+    got = engine.dp_align_batch(jobs, gaps, want_dirs=True)
+    for r, job in zip(got, jobs):
+        assert_same(r, pyoracle.dp_align(*job, gaps))
+    assert engine.dp_align_batch([], gaps) == []
+    with pytest.raises(Exception):
+        engine.dp_align_batch([(jobs[0][0][:1], jobs[0][1][:1], 1, jobs[0][3], jobs[0][4], 1)], gaps)
