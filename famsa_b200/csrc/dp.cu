@@ -24,6 +24,8 @@ namespace fb {
 constexpr int kGO = 25, kGE = 26, kTE = 27, kTO = 28;   // GAP_OPEN, GAP_EXT, GAP_TERM_EXT, GAP_TERM_OPEN (defs.h:62-66)
 constexpr long long kNeg = -(1ll << 62);
 constexpr int kDpWarps = 4;
+constexpr int kDpTeamWarps = 8;          // warps cooperating on one large merge
+constexpr uint32_t kDpTeamMinWidth = 96;  // min(w1, w2) above which a merge gets a team
 
 struct DpJobDev {
     const long long* s1; const int* c1;
@@ -107,21 +109,31 @@ struct DpParams {
     famsa_dp_result* results;
 };
 
-template <int VAR>
+// One team = NW warps working on one merge.  Stripe k (rows 32k+1 .. 32k+32) belongs to warp k % NW;
+// consecutive stripes run as a staircase: stripe k+1 may touch column j only after stripe k has parked
+// its last row's cell (., j) in `brow`.  prog[w] is warp w's monotonically increasing count of parked
+// columns ((round * (WC+1)) + columns of the current stripe), polled by the warp that owns the next stripe.
+template <int VAR, int NW>
 __device__ __forceinline__ void dp_stripes(const DpParams& P, const long long* __restrict__ SRs, const int* __restrict__ CR,
                                            const long long* __restrict__ SCs, uint32_t WR, uint32_t WC, int nR, int nC,
                                            const ColInfo* __restrict__ col, Cell* __restrict__ brow,
                                            unsigned char* __restrict__ dirs, int* __restrict__ nz_k, int* __restrict__ nz_c,
-                                           long long (&last)[3])
+                                           volatile unsigned* prog, uint32_t team_warp, long long* last_out)
 {
     const uint32_t lane = threadIdx.x & 31;
     const size_t ld = (size_t)WC + 1;
     const long long go = P.go, ge = P.ge, to = P.to, te = P.te;
+    const uint32_t n_stripes = (WR + 31) / 32;
 
-    for (uint32_t i0 = 1; i0 <= WR; i0 += 32) {
-        const uint32_t i = i0 + lane;
+    for (uint32_t k = team_warp; k < n_stripes; k += NW) {
+        const uint32_t i = k * 32 + 1 + lane;
         const bool valid = i <= WR;
         const bool last_row = i == WR;
+        // what the producer (stripe k-1, warp (k-1) % NW) must have published before column j may be read
+        const uint32_t prod_warp = (k + NW - 1) % NW;
+        const unsigned prod_base = k ? ((k - 1) / NW) * (WC + 1) : 0;
+        const unsigned my_base = (k / NW) * (WC + 1);
+        unsigned avail = k ? 0 : WC + 1;                 // columns of the producer known to be parked
         // ---- row-side constants
         int symR = 22, s_o = 0, s_e = 0, s_to = 0, s_te = 0, k_e = 0, k_te = 0, g1o = 0, g1t = 0, nzn = 0;
         long long nongap1 = 0, srgo = 0, srge = 0, srto = 0, srte = 0, col0cost = 0;
@@ -131,9 +143,9 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const long long* _
             if (VAR == 2) {
                 solve_gaps(CR, i, WR, nR, s_o, s_e, s_to, s_te, k_e, k_te);
                 g1o = rc[kGO]; g1t = rc[kTO];
-                for (int k = 0; k < 30; ++k) {
-                    const int c = rc[k];
-                    if (c) { nz_k[nzn * 32 + lane] = k; nz_c[nzn * 32 + lane] = c; ++nzn; if (k < 24) nongap1 += c; }
+                for (int q = 0; q < 30; ++q) {
+                    const int c = rc[q];
+                    if (c) { nz_k[nzn * 32 + lane] = q; nz_c[nzn * 32 + lane] = c; ++nzn; if (q < 24) nongap1 += c; }
                 }
                 const long long* sr = SRs + (size_t)i * 32;
                 srgo = sr[kGO]; srge = sr[kGE]; srto = sr[kTO]; srte = sr[kTE];
@@ -143,10 +155,19 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const long long* _
         }
         __syncwarp();
 
+        auto wait_for = [&](uint32_t j) {               // lane 0 only: producer has parked column j
+            if (NW > 1 && j >= avail) {
+                unsigned v;
+                do { v = prog[prod_warp] - prod_base; } while ((int)v < 0 || v <= j);
+                avail = v;
+                __threadfence_block();
+            }
+        };
+
         Cell cur = {kNeg, kNeg, kNeg};      // own cell of the previous step (left neighbour)
         Cell up = {kNeg, kNeg, kNeg};       // cell above of the previous step (becomes the diagonal)
         Cell nxt = {kNeg, kNeg, kNeg};      // lane 0: boundary-row cell for the next step (L2 prefetch)
-        if (lane == 0) nxt = load_cell(brow);
+        if (lane == 0) { wait_for(0); nxt = load_cell(brow); }
         unsigned char* drow = dirs + (size_t)i * ld;
         const uint32_t steps = WC + 1 + 31;
         for (uint32_t s = 0; s < steps; ++s) {
@@ -156,7 +177,7 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const long long* _
             U.D = shfl_up_ll(cur.D); U.H = shfl_up_ll(cur.H); U.V = shfl_up_ll(cur.V);
             if (lane == 0) {
                 U = nxt;
-                if (s + 1 <= WC) nxt = load_cell(brow + s + 1);
+                if (s + 1 <= WC) { wait_for(s + 1); nxt = load_cell(brow + s + 1); }
             }
             const Cell Pd = up;                              // (i-1, j-1)
             up = U;
@@ -220,25 +241,44 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const long long* _
             }
             drow[j] = db;
             cur = out;
-            // park the stripe's last row for the next stripe (read by lane 0 at least 31 steps later)
-            if (lane == 31 || last_row) {
-                if (!last_row) store_cell(brow + j, out);
-                else if (j == (int)WC) { last[0] = out.D; last[1] = out.H; last[2] = out.V; }
+            if (last_row) {
+                if (j == (int)WC) { last_out[0] = out.D; last_out[1] = out.H; last_out[2] = out.V; }
+            } else if (lane == 31) {
+                // park the stripe's last row for the next stripe; publish every 4th column
+                store_cell(brow + j, out);
+                if (NW > 1 && ((j & 3) == 3 || j == (int)WC)) {
+                    __threadfence_block();
+                    prog[team_warp] = my_base + (unsigned)j + 1;
+                }
             }
         }
         __syncwarp();
     }
 }
 
-__global__ void __launch_bounds__(kDpWarps * 32) k_dp_align(const DpParams P)
+// NW == 1: four independent merges per 128-thread block (one warp each).  NW > 1: one merge per block.
+template <int NW>
+__global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_align(const DpParams P)
 {
-    __shared__ int sm_nz_k[kDpWarps][30 * 32];
-    __shared__ int sm_nz_c[kDpWarps][30 * 32];
+    constexpr int kBlockWarps = NW == 1 ? kDpWarps : NW;
+    extern __shared__ int sm_dyn[];                         // [kBlockWarps][2][30*32]: nz symbol ids, nz counts
+    int (*sm_nz_k)[30 * 32] = reinterpret_cast<int (*)[30 * 32]>(sm_dyn);
+    int (*sm_nz_c)[30 * 32] = reinterpret_cast<int (*)[30 * 32]>(sm_dyn + kBlockWarps * 30 * 32);
+    __shared__ unsigned sm_prog[kBlockWarps];
+    __shared__ unsigned long long sm_nz[2];
+    __shared__ long long sm_last[kBlockWarps][3];
     const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const uint32_t slot = blockIdx.x * kDpWarps + warp;
+    const uint32_t team_warp = NW == 1 ? 0 : warp;
+    const uint32_t tid = NW == 1 ? lane : threadIdx.x;          // index inside the team
+    constexpr uint32_t kTeam = NW * 32;
+    const uint32_t slot = NW == 1 ? blockIdx.x * kDpWarps + warp : blockIdx.x;
     if (slot >= P.n_jobs) return;
+    auto team_sync = [&]() { if (NW == 1) __syncwarp(); else __syncthreads(); };
     const uint32_t jid = P.order[slot];
     const DpJobDev J = P.jobs[jid];
+    if (threadIdx.x < kBlockWarps) sm_prog[threadIdx.x] = 0;
+    if (threadIdx.x < 2) sm_nz[threadIdx.x] = 0;
+    if (NW > 1) __syncthreads();
 
     // ---- variant and orientation (CProfile::Align, profile.cpp:254-304)
     int var, sw = 0;
@@ -248,11 +288,16 @@ __global__ void __launch_bounds__(kDpWarps * 32) k_dp_align(const DpParams P)
     else {
         var = 2;
         unsigned long long nz1 = 0, nz2 = 0;
-        for (size_t k = lane; k < ((size_t)J.w1 + 1) * 32; k += 32) nz1 += J.c1[k] != 0;
-        for (size_t k = lane; k < ((size_t)J.w2 + 1) * 32; k += 32) nz2 += J.c2[k] != 0;
+        for (size_t k = tid; k < ((size_t)J.w1 + 1) * 32; k += kTeam) nz1 += J.c1[k] != 0;
+        for (size_t k = tid; k < ((size_t)J.w2 + 1) * 32; k += kTeam) nz2 += J.c2[k] != 0;
         for (int o = 16; o; o >>= 1) {
             nz1 += __shfl_xor_sync(0xffffffffu, nz1, o);
             nz2 += __shfl_xor_sync(0xffffffffu, nz2, o);
+        }
+        if (NW > 1) {
+            if (lane == 0) { atomicAdd(&sm_nz[0], nz1); atomicAdd(&sm_nz[1], nz2); }
+            __syncthreads();
+            nz1 = sm_nz[0]; nz2 = sm_nz[1];
         }
         if (!(nz1 * (unsigned long long)J.w2 < nz2 * (unsigned long long)J.w1)) sw = 1;
     }
@@ -271,7 +316,7 @@ __global__ void __launch_bounds__(kDpWarps * 32) k_dp_align(const DpParams P)
     const long long go = P.go, ge = P.ge, to = P.to, te = P.te;
 
     // ---- column-side constants and row 0
-    for (uint32_t j = lane; j <= WC; j += 32) {
+    for (uint32_t j = tid; j <= WC; j += kTeam) {
         ColInfo ci;
         ci.pad = 0; ci.pad2[0] = 0;
         if (j >= 1) {
@@ -287,7 +332,7 @@ __global__ void __launch_bounds__(kDpWarps * 32) k_dp_align(const DpParams P)
         col[j] = ci;
         dirs[j] = j == 0 ? 0 : (unsigned char)(1 | 1 << 2 | 1 << 4);
     }
-    if (lane == 0) {
+    if (tid == 0) {
         store_cell(brow, Cell{0, kNeg, kNeg});
         long long h = 0;
         for (uint32_t j = 1; j <= WC; ++j) {
@@ -298,21 +343,20 @@ __global__ void __launch_bounds__(kDpWarps * 32) k_dp_align(const DpParams P)
             store_cell(brow + j, Cell{kNeg, j == WC ? kNeg : h, kNeg});
         }
     }
-    __syncwarp();
+    __threadfence_block();
+    team_sync();
 
-    long long last[3] = {kNeg, kNeg, kNeg};
-    if (var == 0) dp_stripes<0>(P, SR, CR, SC, WR, WC, nR, nC, col, brow, dirs, sm_nz_k[warp], sm_nz_c[warp], last);
-    else if (var == 1) dp_stripes<1>(P, SR, CR, SC, WR, WC, nR, nC, col, brow, dirs, sm_nz_k[warp], sm_nz_c[warp], last);
-    else dp_stripes<2>(P, SR, CR, SC, WR, WC, nR, nC, col, brow, dirs, sm_nz_k[warp], sm_nz_c[warp], last);
+    long long* last_out = sm_last[warp];
+    if (var == 0) dp_stripes<0, NW>(P, SR, CR, SC, WR, WC, nR, nC, col, brow, dirs, sm_nz_k[warp], sm_nz_c[warp], sm_prog, team_warp, last_out);
+    else if (var == 1) dp_stripes<1, NW>(P, SR, CR, SC, WR, WC, nR, nC, col, brow, dirs, sm_nz_k[warp], sm_nz_c[warp], sm_prog, team_warp, last_out);
+    else dp_stripes<2, NW>(P, SR, CR, SC, WR, WC, nR, nC, col, brow, dirs, sm_nz_k[warp], sm_nz_c[warp], sm_prog, team_warp, last_out);
+    __threadfence_block();
+    team_sync();
+    if (team_warp != 0) return;
 
-    // the lane that owned cell (WR, WC) holds `last`; everyone gets it
-    const int owner = (int)((WR - 1) % 32);
-    for (int k = 0; k < 3; ++k) {
-        int lo = (int)(unsigned long long)last[k], hi = (int)((unsigned long long)last[k] >> 32);
-        lo = __shfl_sync(0xffffffffu, lo, owner); hi = __shfl_sync(0xffffffffu, hi, owner);
-        last[k] = (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo);
-    }
-    __syncwarp();
+    // the warp that owned the final stripe stored (D,H,V)(WR,WC)
+    const uint32_t owner_warp = NW == 1 ? warp : ((WR + 31) / 32 - 1) % NW;
+    long long last[3] = {sm_last[owner_warp][0], sm_last[owner_warp][1], sm_last[owner_warp][2]};
 
     // ---- traceback (ConstructProfile, profile.cpp:727-775), lane 0 walks, the warp reverses
     uint32_t n = 0;
@@ -325,7 +369,7 @@ __global__ void __launch_bounds__(kDpWarps * 32) k_dp_align(const DpParams P)
         size_t i = WR, j = WC;
         while (i || j) {
             tmp_path[n++] = (unsigned char)dir;
-            const unsigned char b = dirs[i * ld + j];
+            const unsigned char b = __ldcg(dirs + i * ld + j);
             if (dir == 0) { dir = b & 3; --i; --j; }
             else if (dir == 1) { dir = (b >> 2) & 3; --j; }
             else { dir = (b >> 4) & 3; --i; }
@@ -381,10 +425,16 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
         scratch_off += ((sizeof(ColInfo) + sizeof(Cell)) * (wmax + 1) + d.w1 + d.w2 + 63) / 64 * 64;
         cells += (unsigned long long)d.w1 * d.w2;
     }
+    // merges whose shorter side spans several 32-row stripes get a whole block (kDpTeamWarps warps pipelined
+    // over the stripes); the rest run one warp per merge.  Both groups cost-descending.
+    auto big = [&](uint32_t a) { return std::min(dev[a].w1, dev[a].w2) > kDpTeamMinWidth; };
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        if (big(a) != big(b)) return big(a);
         return (unsigned long long)dev[a].w1 * dev[a].w2 > (unsigned long long)dev[b].w1 * dev[b].w2;
     });
+    uint32_t n_big = 0;
+    while (n_big < n && big(order[n_big])) ++n_big;
     S.last_cells = cells;
     FB_TRY(S.d_jobs.reserve(sizeof(DpJobDev) * std::max(1u, n)));
     FB_TRY(S.d_order.reserve(sizeof(uint32_t) * std::max(1u, n)));
@@ -407,8 +457,25 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
     P.scratch = S.d_scratch.as<uint8_t>();
     P.results = d_results;
     FB_CUDA(cudaEventRecord(ctx->ev[1], st));
-    if (n) {
-        k_dp_align<<<(n + kDpWarps - 1) / kDpWarps, kDpWarps * 32, 0, st>>>(P);
+    // `order` is cost-descending with the team-kernel jobs first (see the sort above)
+    static bool configured = false;
+    constexpr size_t smem_big = (size_t)kDpTeamWarps * 2 * 30 * 32 * sizeof(int);
+    constexpr size_t smem_small = (size_t)kDpWarps * 2 * 30 * 32 * sizeof(int);
+    if (!configured) {
+        FB_CUDA(cudaFuncSetAttribute(k_dp_align<kDpTeamWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
+        FB_CUDA(cudaFuncSetAttribute(k_dp_align<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
+        configured = true;
+    }
+    if (n_big) {
+        k_dp_align<kDpTeamWarps><<<n_big, kDpTeamWarps * 32, smem_big, st>>>(P);
+        FB_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+    if (n > n_big) {
+        DpParams Q = P;
+        Q.order = P.order + n_big;
+        Q.n_jobs = n - n_big;
+        k_dp_align<1><<<(Q.n_jobs + kDpWarps - 1) / kDpWarps, kDpWarps * 32, smem_small, st>>>(Q);
         FB_CUDA(cudaGetLastError());
         ctx->launches++;
     }
