@@ -60,7 +60,7 @@ struct LcsState {
 };
 
 struct DpState {
-    DevBuf d_jobs, d_order, d_scratch, d_dirs, d_tables, d_results, d_path;
+    DevBuf d_jobs, d_order, d_scratch, d_dirs, d_tables, d_results, d_path, d_meta, d_tblock, d_T;
     std::vector<uint8_t> h_stage;
     uint64_t last_cells = 0;
     float last_total_ms = 0.f, last_kernel_ms = 0.f;

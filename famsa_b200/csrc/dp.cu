@@ -6,14 +6,23 @@
 // (profile.cpp:1223-1315) and the traceback of ConstructProfile (profile.cpp:727-782).
 // Semantics follow SURVEY.md Appendix B; arithmetic is int64 with NEG = -(1<<62) unsaturated.
 //
-// Design: one warp per merge.  The DP matrix is swept in stripes of 32 rows; inside a stripe
-// lane L owns row i0+L and at step s computes column s-L (an anti-diagonal wavefront), receiving
-// the (D,H,V) of the cell above through warp shuffles and keeping its left neighbour in registers.
-// The last row of a stripe is parked in a per-merge boundary row (global, L1/L2 resident) and
-// feeds lane 0 of the next stripe.  Column-side constants (gap-correction counts, the profile-2
-// score column) are read through L1; row-side constants live in registers / shared memory.
-// After the fill the same warp walks the direction matrix back and emits the path.
+// Design (three kernels per batch):
+//   k_dp_prep  one block per merge: variant + orientation (CProfile::Align), the column-side constant
+//              records (gap scores + gap-correction counts, 64 B per column), row 0 of the DP, the compact
+//              non-zero lists of the row profile's counters and a transposed copy of the column profile's
+//              scores (so the next kernel reads them coalesced).
+//   k_dp_t     embarrassingly parallel: T[i][j] = sum_k counters_row[i][k] * scores_col[j][k], the column-
+//              pair score that does not depend on the DP state (profile_par.cpp:695-711).  Taking this
+//              gather-heavy dot product out of the wavefront removes the dependent-load chain from the
+//              latency-critical loop.
+//   k_dp_fill  the recurrence itself: a team of warps per merge, 32-row stripes, lane L owns row i0+L and
+//              at step s computes column s-L (anti-diagonal wavefront); (D,H,V) of the cell above arrives
+//              by warp shuffle, the left neighbour stays in registers, T and the column record of the NEXT
+//              step are prefetched into registers.  Stripes of one merge run as a staircase over the warps
+//              of the block, handing the boundary row over through L2 with a shared-memory progress counter.
+//              The same kernel then walks the direction matrix back and emits the path.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -23,58 +32,108 @@ namespace fb {
 
 constexpr int kGO = 25, kGE = 26, kTE = 27, kTO = 28;   // GAP_OPEN, GAP_EXT, GAP_TERM_EXT, GAP_TERM_OPEN (defs.h:62-66)
 constexpr long long kNeg = -(1ll << 62);
-constexpr int kDpWarps = 4;
-constexpr int kDpTeamWarps = 8;          // warps cooperating on one large merge
+constexpr int kDpWarps = 4;               // block size of the one-warp-per-merge fill kernel
+constexpr int kDpTeamWarps = 8;           // warps cooperating on one large merge
 constexpr uint32_t kDpTeamMinWidth = 96;  // min(w1, w2) above which a merge gets a team
+constexpr int kTThreads = 256, kTCellsPerThread = 4;
 
 struct DpJobDev {
     const long long* s1; const int* c1;
     const long long* s2; const int* c2;
     uint32_t w1, card1, w2, card2;
-    unsigned long long path_off, dirs_off, scratch_off;
+    unsigned long long path_off, dirs_off, scratch_off, t_off;
 };
 
-struct ColInfo {           // per column j of the column profile (64 bytes)
-    int s_o, s_e, s_to, s_te, k_e, k_te;   // DP_SolveGapsProblemWhenStarting / Continuing
-    int sym;                               // residue if the column profile is a single sequence
-    int pad;
-    long long chg2;                        // cnt[GO]*(ge-go) + cnt[TO]*(te-to)
-    long long gcv1, contv1;                // SeqProf: scalar-gap V costs (profile_par.cpp:204-211)
-    long long pad2[1];
+struct DpMeta {            // written by k_dp_prep
+    const long long* SR; const int* CR;
+    const long long* SC; const int* CC;
+    uint32_t WR, WC;
+    int nR, nC, var, sw;
+};
+
+// per column j of the column profile, 64 bytes, meaning depends on the variant:
+//   ProfProf: gap scores {S[j][GO], S[j][GE], S[j][TO], S[j][TE]}, chg, b0 = (s_o, s_e), b1 = (s_to, s_te), b2 = (k_e, k_te)
+//   SeqProf : same gap scores, chg, b0 = gcv1, b1 = contv1 (profile_par.cpp:204-211)
+//   SeqSeq  : unused
+struct ColInfo {
+    long long cgo, cge, cto, cte;
+    long long chg;
+    long long b0, b1, b2;
 };
 static_assert(sizeof(ColInfo) == 64, "ColInfo layout");
 
-struct Cell { long long D, H, V; };
+struct RowNz {             // compact non-zero list of one counters column (rows 0..29), 160 bytes
+    int n;
+    int c[30];
+    unsigned char k[30];
+    unsigned char pad[6];
+};
+static_assert(sizeof(RowNz) == 160, "RowNz layout");
+
+struct Cell { long long D, H, V, pad; };   // 32 bytes: two 16-byte cp.async / st.cg.v2 transfers
+static_assert(sizeof(Cell) == 32, "Cell layout");
+constexpr int kChunk = 16;                  // boundary-row columns handed over per cp.async batch / progress publish
+
+__host__ __device__ inline unsigned long long align_up(unsigned long long v, unsigned long long a) { return (v + a - 1) / a * a; }
+
+// scratch layout of one job (all sections 128-byte aligned)
+struct Scratch {
+    unsigned long long col, brow, rownz, s2t, tmp, total;
+    __host__ __device__ Scratch(uint32_t w1, uint32_t w2)
+    {
+        const unsigned long long wm = (w1 > w2 ? w1 : w2) + 1ull;
+        col = 0;
+        brow = align_up(col + sizeof(ColInfo) * wm, 128);
+        rownz = align_up(brow + sizeof(Cell) * wm, 128);
+        s2t = align_up(rownz + sizeof(RowNz) * wm, 128);
+        tmp = align_up(s2t + 8ull * 30 * wm, 128);
+        total = align_up(tmp + w1 + w2, 128);
+    }
+};
+
+__device__ __forceinline__ long long pack2(int lo, int hi) { return (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo); }
+__device__ __forceinline__ int lo32(long long v) { return (int)(unsigned long long)v; }
+__device__ __forceinline__ int hi32(long long v) { return (int)((unsigned long long)v >> 32); }
 
 __device__ __forceinline__ long long shfl_up_ll(long long v)
 {
-    int lo = (int)(unsigned long long)v, hi = (int)((unsigned long long)v >> 32);
+    int lo = lo32(v), hi = hi32(v);
     lo = __shfl_up_sync(0xffffffffu, lo, 1);
     hi = __shfl_up_sync(0xffffffffu, hi, 1);
-    return (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo);
+    return pack2(lo, hi);
 }
 
 // boundary-row traffic goes through L2 (.cg): written by lane 31 of one stripe, read by lane 0 of the next
-__device__ __forceinline__ Cell load_cell(const Cell* p)
-{
-    const long long* q = reinterpret_cast<const long long*>(p);
-    Cell c; c.D = __ldcg(q); c.H = __ldcg(q + 1); c.V = __ldcg(q + 2);
-    return c;
-}
 __device__ __forceinline__ void store_cell(Cell* p, const Cell& c)
 {
-    long long* q = reinterpret_cast<long long*>(p);
-    __stcg(q, c.D); __stcg(q + 1, c.H); __stcg(q + 2, c.V);
+    longlong2* q = reinterpret_cast<longlong2*>(p);
+    __stcg(q, make_longlong2(c.D, c.H));
+    __stcg(q + 1, make_longlong2(c.V, 0));
 }
+// global (L2) -> shared without staging registers: the warp does not wait for the data
+__device__ __forceinline__ void cp_async_cell(Cell* smem_dst, const Cell* gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(reinterpret_cast<const char*>(gsrc) + 16) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // a if a>b && a>c; else b if b>c; else c  (strict comparisons, fixed priority)
 __device__ __forceinline__ int pick3(long long a, long long b, long long c, int da, int db, int dc, long long& out)
 {
-    if (a > b && a > c) { out = a; return da; }
-    if (b > c) { out = b; return db; }
-    out = c; return dc;
+    const bool aw = (a > b) & (a > c);
+    const bool bw = b > c;
+    const long long bc = bw ? b : c;
+    const int dbc = bw ? db : dc;
+    out = aw ? a : bc;
+    return aw ? da : dbc;
 }
+// a value that can never win a strict comparison: turns a 3-way pick into the reference's 2-way form
+constexpr long long kNever = (long long)0x8000000000000000ull;
 
+// DP_SolveGapsProblemWhenStarting / WhenContinuing (profile.cpp:1223-1315) for column c
 __device__ __forceinline__ void solve_gaps(const int* __restrict__ cnt, uint32_t c, uint32_t width, int card,
                                            int& s_o, int& s_e, int& s_to, int& s_te, int& k_e, int& k_te)
 {
@@ -100,27 +159,173 @@ __device__ __forceinline__ int seq_symbol(const int* __restrict__ cnt, uint32_t 
 
 struct DpParams {
     const DpJobDev* jobs;
-    const uint32_t* order;        // launch slot -> job index (cost-descending)
+    DpMeta* meta;
+    const uint32_t* order;        // launch slot -> job index
     uint32_t n_jobs;
     long long go, ge, to, te;
     unsigned char* dirs;          // all direction matrices
     unsigned char* path;          // all paths (forward order)
-    unsigned char* scratch;       // per job: ColInfo[wmax+1], Cell brow[wmax+1], tmp path[w1+w2]
+    unsigned char* scratch;
+    long long* T;                 // all T matrices
+    const unsigned long long* tblock;   // k_dp_t: first block of each job (n_jobs + 1 entries)
     famsa_dp_result* results;
 };
+
+// ------------------------------------------------------------------------------------------------
+// k_dp_prep: one block per job
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_dp_prep(const DpParams P)
+{
+    __shared__ unsigned long long sm_nz[2];
+    const uint32_t jid = blockIdx.x;
+    const DpJobDev J = P.jobs[jid];
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+    if (tid < 2) sm_nz[tid] = 0;
+    __syncthreads();
+
+    // variant and orientation (CProfile::Align, profile.cpp:254-304)
+    int var, sw = 0;
+    if (J.card1 == 1 && J.card2 == 1) var = 0;
+    else if (J.card1 == 1) var = 1;
+    else if (J.card2 == 1) { var = 1; sw = 1; }
+    else {
+        var = 2;
+        unsigned long long nz1 = 0, nz2 = 0;
+        for (size_t k = tid; k < ((size_t)J.w1 + 1) * 32; k += nthr) nz1 += J.c1[k] != 0;
+        for (size_t k = tid; k < ((size_t)J.w2 + 1) * 32; k += nthr) nz2 += J.c2[k] != 0;
+        for (int o = 16; o; o >>= 1) {
+            nz1 += __shfl_xor_sync(0xffffffffu, nz1, o);
+            nz2 += __shfl_xor_sync(0xffffffffu, nz2, o);
+        }
+        if ((tid & 31) == 0) { atomicAdd(&sm_nz[0], nz1); atomicAdd(&sm_nz[1], nz2); }
+        __syncthreads();
+        if (!(sm_nz[0] * (unsigned long long)J.w2 < sm_nz[1] * (unsigned long long)J.w1)) sw = 1;
+    }
+    const long long* SR = sw ? J.s2 : J.s1;  const int* CR = sw ? J.c2 : J.c1;
+    const long long* SC = sw ? J.s1 : J.s2;  const int* CC = sw ? J.c1 : J.c2;
+    const uint32_t WR = sw ? J.w2 : J.w1, WC = sw ? J.w1 : J.w2;
+    const int nR = (int)(sw ? J.card2 : J.card1), nC = (int)(sw ? J.card1 : J.card2);
+    if (tid == 0) {
+        DpMeta m;
+        m.SR = SR; m.CR = CR; m.SC = SC; m.CC = CC; m.WR = WR; m.WC = WC; m.nR = nR; m.nC = nC; m.var = var; m.sw = sw;
+        P.meta[jid] = m;
+    }
+    const Scratch L(J.w1, J.w2);
+    unsigned char* scratch = P.scratch + J.scratch_off;
+    ColInfo* col = reinterpret_cast<ColInfo*>(scratch + L.col);
+    Cell* brow = reinterpret_cast<Cell*>(scratch + L.brow);
+    RowNz* rownz = reinterpret_cast<RowNz*>(scratch + L.rownz);
+    long long* s2t = reinterpret_cast<long long*>(scratch + L.s2t);
+    unsigned char* dirs = P.dirs + J.dirs_off;
+    const long long go = P.go, ge = P.ge, to = P.to, te = P.te;
+    const size_t ldc = (size_t)WC + 1;
+
+    // column records + row 0 of the direction matrix
+    for (uint32_t j = tid; j <= WC; j += nthr) {
+        ColInfo ci = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (j >= 1 && var != 0) {
+            int s_o, s_e, s_to, s_te, k_e, k_te;
+            solve_gaps(CC, j, WC, nC, s_o, s_e, s_to, s_te, k_e, k_te);
+            const int* cc = CC + (size_t)j * 32;
+            const long long* sc = SC + (size_t)j * 32;
+            ci.cgo = sc[kGO]; ci.cge = sc[kGE]; ci.cto = sc[kTO]; ci.cte = sc[kTE];
+            ci.chg = (long long)cc[kGO] * (ge - go) + (long long)cc[kTO] * (te - to);
+            if (var == 2) { ci.b0 = pack2(s_o, s_e); ci.b1 = pack2(s_to, s_te); ci.b2 = pack2(k_e, k_te); }
+            else { ci.b0 = go * s_o + ge * s_e + to * s_to + te * s_te; ci.b1 = ge * k_e + te * k_te; }
+        }
+        col[j] = ci;
+        dirs[j] = j == 0 ? 0 : (unsigned char)(1 | 1 << 2 | 1 << 4);
+    }
+    // row 0 (profile_par.cpp:531-555; SeqSeq profile_seq.cpp:48-69)
+    if (tid == 0) {
+        store_cell(brow, Cell{0, kNeg, kNeg, 0});
+        long long h = 0;
+        for (uint32_t j = 1; j <= WC; ++j) {
+            const long long* sc = SC + (size_t)j * 32;
+            if (var == 0) h = j == 1 ? to : h + te;            // max(H, D = NEG) + te
+            else if (var == 1) h = j == 1 ? sc[kTO] : h + sc[kTE];
+            else h = j == 1 ? sc[kTO] * nR : h + sc[kTE] * nR;
+            store_cell(brow + j, Cell{kNeg, j == WC ? kNeg : h, kNeg, 0});
+        }
+    }
+    // non-zero lists of the row profile (ProfProf) or its residue (Seq*)
+    for (uint32_t i = tid; i <= WR; i += nthr) {
+        RowNz* dst = rownz + i;
+        int n = 0;
+        if (i >= 1) {
+            if (var == 2) {
+                const int* rc = CR + (size_t)i * 32;
+                for (int k = 0; k < 30; ++k) {
+                    const int c = rc[k];
+                    if (c) { dst->c[n] = c; dst->k[n] = (unsigned char)k; ++n; }
+                }
+            } else {
+                dst->c[0] = 1; dst->k[0] = (unsigned char)seq_symbol(CR, i); n = 1;
+            }
+        }
+        dst->n = n;
+    }
+    // transposed scores of the column profile: s2t[k][j], k < 30
+    for (size_t e = tid; e < ldc * 32; e += nthr) {
+        const uint32_t j = (uint32_t)(e / 32), k = (uint32_t)(e % 32);
+        if (k < 30) s2t[(size_t)k * ldc + j] = SC[e];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_dp_t: T[i][j] for every cell of every job
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTThreads) k_dp_t(const DpParams P)
+{
+    // which job does this block belong to?
+    uint32_t lo = 0, hi = P.n_jobs;
+    const unsigned long long b = blockIdx.x;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) / 2;
+        if (P.tblock[mid] <= b) lo = mid; else hi = mid;
+    }
+    const uint32_t jid = lo;
+    const DpJobDev J = P.jobs[jid];
+    const DpMeta M = P.meta[jid];
+    const Scratch L(J.w1, J.w2);
+    const unsigned char* scratch = P.scratch + J.scratch_off;
+    const RowNz* rownz = reinterpret_cast<const RowNz*>(scratch + L.rownz);
+    const long long* s2t = reinterpret_cast<const long long*>(scratch + L.s2t);
+    long long* T = P.T + J.t_off;
+    const size_t ldc = (size_t)M.WC + 1;
+    const size_t cells = ((size_t)M.WR + 1) * ldc;
+    const size_t base = (size_t)(b - P.tblock[jid]) * kTThreads * kTCellsPerThread;
+#pragma unroll
+    for (int u = 0; u < kTCellsPerThread; ++u) {
+        const size_t c = base + (size_t)u * kTThreads + threadIdx.x;
+        if (c >= cells) break;
+        const uint32_t i = (uint32_t)(c / ldc), j = (uint32_t)(c % ldc);
+        long long t = 0;
+        if (i >= 1 && j >= 1) {
+            const RowNz* r = rownz + i;
+            const int n = r->n;
+            for (int q = 0; q < n; ++q) t += (long long)r->c[q] * s2t[(size_t)r->k[q] * ldc + j];
+        }
+        T[c] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_dp_fill: the recurrence + traceback
+// ------------------------------------------------------------------------------------------------
 
 // One team = NW warps working on one merge.  Stripe k (rows 32k+1 .. 32k+32) belongs to warp k % NW;
 // consecutive stripes run as a staircase: stripe k+1 may touch column j only after stripe k has parked
 // its last row's cell (., j) in `brow`.  prog[w] is warp w's monotonically increasing count of parked
 // columns ((round * (WC+1)) + columns of the current stripe), polled by the warp that owns the next stripe.
 template <int VAR, int NW>
-__device__ __forceinline__ void dp_stripes(const DpParams& P, const long long* __restrict__ SRs, const int* __restrict__ CR,
-                                           const long long* __restrict__ SCs, uint32_t WR, uint32_t WC, int nR, int nC,
+__device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, const long long* __restrict__ T,
                                            const ColInfo* __restrict__ col, Cell* __restrict__ brow,
-                                           unsigned char* __restrict__ dirs, int* __restrict__ nz_k, int* __restrict__ nz_c,
-                                           volatile unsigned* prog, uint32_t team_warp, long long* last_out)
+                                           unsigned char* __restrict__ dirs, volatile unsigned* prog, uint32_t team_warp,
+                                           long long* last_out, Cell (*sb)[kChunk])
 {
     const uint32_t lane = threadIdx.x & 31;
+    const uint32_t WR = M.WR, WC = M.WC;
     const size_t ld = (size_t)WC + 1;
     const long long go = P.go, ge = P.ge, to = P.to, te = P.te;
     const uint32_t n_stripes = (WR + 31) / 32;
@@ -129,126 +334,147 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const long long* _
         const uint32_t i = k * 32 + 1 + lane;
         const bool valid = i <= WR;
         const bool last_row = i == WR;
-        // what the producer (stripe k-1, warp (k-1) % NW) must have published before column j may be read
         const uint32_t prod_warp = (k + NW - 1) % NW;
         const unsigned prod_base = k ? ((k - 1) / NW) * (WC + 1) : 0;
         const unsigned my_base = (k / NW) * (WC + 1);
-        unsigned avail = k ? 0 : WC + 1;                 // columns of the producer known to be parked
-        // ---- row-side constants
-        int symR = 22, s_o = 0, s_e = 0, s_to = 0, s_te = 0, k_e = 0, k_te = 0, g1o = 0, g1t = 0, nzn = 0;
+        unsigned avail = k ? 0 : WC + 1;                 // columns of the producer stripe known to be parked
+        // ---- row-side constants (registers)
+        int s_o = 0, s_e = 0, s_to = 0, s_te = 0, k_e = 0, k_te = 0, g1o = 0, g1t = 0;
         long long nongap1 = 0, srgo = 0, srge = 0, srto = 0, srte = 0, col0cost = 0;
         if (valid) {
-            const int* rc = CR + (size_t)i * 32;
-            if (VAR != 2) symR = seq_symbol(CR, i);
             if (VAR == 2) {
-                solve_gaps(CR, i, WR, nR, s_o, s_e, s_to, s_te, k_e, k_te);
+                const int* rc = M.CR + (size_t)i * 32;
+                solve_gaps(M.CR, i, WR, M.nR, s_o, s_e, s_to, s_te, k_e, k_te);
                 g1o = rc[kGO]; g1t = rc[kTO];
-                for (int q = 0; q < 30; ++q) {
-                    const int c = rc[q];
-                    if (c) { nz_k[nzn * 32 + lane] = q; nz_c[nzn * 32 + lane] = c; ++nzn; if (q < 24) nongap1 += c; }
-                }
-                const long long* sr = SRs + (size_t)i * 32;
+                for (int q = 0; q < 24; ++q) nongap1 += rc[q];
+                const long long* sr = M.SR + (size_t)i * 32;
                 srgo = sr[kGO]; srge = sr[kGE]; srto = sr[kTO]; srte = sr[kTE];
-                col0cost = (i == 1 ? srto : srte) * nC;
-            } else if (VAR == 1) col0cost = (i == 1 ? to : te) * nC;
+                col0cost = (i == 1 ? srto : srte) * M.nC;
+            } else if (VAR == 1) col0cost = (i == 1 ? to : te) * M.nC;
             else col0cost = i == 1 ? to : te;
         }
-        __syncwarp();
 
-        auto wait_for = [&](uint32_t j) {               // lane 0 only: producer has parked column j
+        auto wait_for = [&](uint32_t j) {               // lane 0 only: the producer has parked column j
             if (NW > 1 && j >= avail) {
                 unsigned v;
-                do { v = prog[prod_warp] - prod_base; } while ((int)v < 0 || v <= j);
+                for (;;) {
+                    v = prog[prod_warp] - prod_base;
+                    if ((int)v >= 0 && v > j) break;
+                    __nanosleep(128);       // do not flood the MIO queue the producer's shuffles go through
+                }
                 avail = v;
                 __threadfence_block();
             }
         };
 
-        Cell cur = {kNeg, kNeg, kNeg};      // own cell of the previous step (left neighbour)
-        Cell up = {kNeg, kNeg, kNeg};       // cell above of the previous step (becomes the diagonal)
-        Cell nxt = {kNeg, kNeg, kNeg};      // lane 0: boundary-row cell for the next step (L2 prefetch)
-        if (lane == 0) { wait_for(0); nxt = load_cell(brow); }
+        Cell cur = {kNeg, kNeg, kNeg, 0};   // own cell of the previous step (left neighbour)
+        Cell up = {kNeg, kNeg, kNeg, 0};    // cell above of the previous step (becomes the diagonal)
+        // the boundary row arrives in chunks of kChunk columns: L2 -> shared by cp.async, one chunk ahead
+        if (lane == 0) wait_for(min((uint32_t)kChunk - 1, WC));
+        __syncwarp();
+        if (lane < kChunk && lane <= WC) cp_async_cell(&sb[0][lane], brow + lane);
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncwarp();
         unsigned char* drow = dirs + (size_t)i * ld;
+        const long long* trow = T + (size_t)i * ld;
+        // software pipeline: T and the column record of the next step are already in flight
+        long long t_next = 0;
+        ColInfo c_next = {0, 0, 0, 0, 0, 0, 0, 0};
         const uint32_t steps = WC + 1 + 31;
         for (uint32_t s = 0; s < steps; ++s) {
+            // The whole body is executed by all 32 lanes (results are committed under `active`), so the warp
+            // never diverges around the shuffles.
             const int j = (int)s - (int)lane;               // column handled now
+            const bool active = valid && j >= 0 && j <= (int)WC;
+            const long long t = t_next;
+            const ColInfo ci = c_next;
+            if (valid && j + 1 >= 1 && j + 1 <= (int)WC) {
+                t_next = trow[j + 1];
+                if (VAR != 0) c_next = col[j + 1];
+            }
             // (i-1, j): lane above computed it one step ago; lane 0 reads the boundary row
             Cell U;
             U.D = shfl_up_ll(cur.D); U.H = shfl_up_ll(cur.H); U.V = shfl_up_ll(cur.V);
-            if (lane == 0) {
-                U = nxt;
-                if (s + 1 <= WC) { wait_for(s + 1); nxt = load_cell(brow + s + 1); }
+            if ((s % kChunk) == 0) {                          // warp-uniform: prefetch the next chunk
+                const uint32_t nb = s + kChunk;
+                if (nb <= WC) {
+                    if (lane == 0) wait_for(min(nb + kChunk - 1, WC));
+                    __syncwarp();
+                    if (lane < kChunk && nb + lane <= WC) cp_async_cell(&sb[((s / kChunk) + 1) & 1][lane], brow + nb + lane);
+                }
+                cp_async_commit();
+            }
+            {
+                const Cell B = sb[(s / kChunk) & 1][s % kChunk];      // broadcast read; only lane 0 keeps it
+                const bool take = lane == 0;
+                U.D = take ? B.D : U.D; U.H = take ? B.H : U.H; U.V = take ? B.V : U.V;
             }
             const Cell Pd = up;                              // (i-1, j-1)
             up = U;
-            if (!valid || j < 0 || j > (int)WC) continue;
+            if ((s % kChunk) == kChunk - 1) { cp_async_wait_all(); __syncwarp(); }   // next chunk has landed
+
+            const Cell L = cur;
+            const bool three = i > 1 && j > 1;
             Cell out;
-            unsigned char db;
-            if (j == 0) {
+            out.pad = 0;
+            int dD, dH, dV;
+            if (VAR == 0) {
+                // profile_seq.cpp:86-140 (note the >= in the second D test)
+                const bool dw = (Pd.D > Pd.H) & (Pd.D > Pd.V), hw = Pd.H >= Pd.V;
+                out.D = (dw ? Pd.D : (hw ? Pd.H : Pd.V)) + t;
+                dD = dw ? 0 : (hw ? 1 : 2);
+                long long tD = L.D + (!last_row ? go : to);
+                const long long tH = L.H + (!last_row ? ge : te);
+                out.H = tD > tH ? tD : tH; dH = tD > tH ? 0 : 1;
+                tD = U.D + (j < (int)WC ? go : to);
+                const long long tV = U.V + (j < (int)WC ? ge : te);
+                out.V = tD > tV ? tD : tV; dV = tD > tV ? 0 : 2;
+            } else if (VAR == 1) {
+                // profile_par.cpp:255-421
+                dD = pick3(Pd.D, Pd.H, Pd.V + ci.chg, 0, 1, 2, out.D);
+                out.D += t;
+                const long long gcH = !last_row ? ci.cgo : ci.cto;
+                long long tD = L.D + gcH;
+                const long long tH = L.H + (!last_row ? ci.cge : ci.cte);
+                dH = pick3(tD, three ? L.V + gcH : kNever, tH, 0, 2, 1, out.H);
+                tD = U.D + ci.b0;
+                const long long tV = U.V + ci.b1;
+                dV = pick3(tD, three ? U.H + ci.b0 : kNever, tV, 0, 1, 2, out.V);
+            } else {
+                // profile_par.cpp:679-886
+                long long tD = Pd.D + t;
+                long long tH = Pd.H + t;
+                tH += (long long)g1o * (ci.cge - ci.cgo) + (long long)g1t * (ci.cte - ci.cto);   // == 0 when both counts are 0
+                long long tV = Pd.V + t + ci.chg * nongap1;
+                dD = pick3(tD, tH, tV, 0, 1, 2, out.D);
+                const long long gcH = ci.cgo * s_o + ci.cge * s_e + ci.cto * s_to + ci.cte * s_te;
+                tD = L.D + gcH;
+                tH = L.H + ci.cge * k_e + ci.cte * k_te;
+                dH = pick3(tD, three ? L.V + gcH : kNever, tH, 0, 2, 1, out.H);
+                const long long gcV = srgo * lo32(ci.b0) + srge * hi32(ci.b0) + srto * lo32(ci.b1) + srte * hi32(ci.b1);
+                tD = U.D + gcV;
+                tV = U.V + srge * lo32(ci.b2) + srte * hi32(ci.b2);
+                dV = pick3(tD, three ? U.H + gcV : kNever, tV, 0, 1, 2, out.V);
+            }
+            unsigned char db = (unsigned char)(dD | dH << 2 | dV << 4);
+            if (j == 0) {                                   // column 0 (profile_par.cpp:625-640)
                 out.D = kNeg; out.H = kNeg;
                 out.V = last_row ? kNeg : (U.D > U.V ? U.D : U.V) + col0cost;
                 db = 2 | 2 << 2 | 2 << 4;
-            } else {
-                const Cell L = cur;
-                const bool three = i > 1 && j > 1;
-                const long long* sc = SCs + (size_t)j * 32;
-                const ColInfo ci = col[j];
-                int dD, dH, dV;
-                if (VAR == 0) {
-                    const long long sc_ = sc[symR];
-                    if (Pd.D > Pd.H && Pd.D > Pd.V) { out.D = Pd.D + sc_; dD = 0; }
-                    else if (Pd.H >= Pd.V) { out.D = Pd.H + sc_; dD = 1; }
-                    else { out.D = Pd.V + sc_; dD = 2; }
-                    long long tD = L.D + (!last_row ? go : to), tH = L.H + (!last_row ? ge : te);
-                    if (tD > tH) { out.H = tD; dH = 0; } else { out.H = tH; dH = 1; }
-                    tD = U.D + (j < (int)WC ? go : to);
-                    const long long tV = U.V + (j < (int)WC ? ge : te);
-                    if (tD > tV) { out.V = tD; dV = 0; } else { out.V = tV; dV = 2; }
-                } else if (VAR == 1) {
-                    const long long t = sc[symR];
-                    dD = pick3(Pd.D, Pd.H, Pd.V + ci.chg2, 0, 1, 2, out.D);
-                    out.D += t;
-                    const long long gcH = !last_row ? sc[kGO] : sc[kTO];
-                    long long tD = L.D + gcH;
-                    const long long tH = L.H + (!last_row ? sc[kGE] : sc[kTE]);
-                    if (three) dH = pick3(tD, L.V + gcH, tH, 0, 2, 1, out.H);
-                    else if (tD > tH) { out.H = tD; dH = 0; } else { out.H = tH; dH = 1; }
-                    tD = U.D + ci.gcv1;
-                    const long long tV = U.V + ci.contv1;
-                    if (three) dV = pick3(tD, U.H + ci.gcv1, tV, 0, 1, 2, out.V);
-                    else if (tD > tV) { out.V = tD; dV = 0; } else { out.V = tV; dV = 2; }
-                } else {
-                    long long t = 0;
-                    for (int q = 0; q < nzn; ++q) t += (long long)nz_c[q * 32 + lane] * sc[nz_k[q * 32 + lane]];
-                    const long long cgo = sc[kGO], cge = sc[kGE], cte = sc[kTE], cto = sc[kTO];
-                    long long tD = Pd.D + t;
-                    long long tH = Pd.H + t;
-                    if (g1o || g1t) tH += (long long)g1o * (cge - cgo) + (long long)g1t * (cte - cto);
-                    long long tV = Pd.V + t + ci.chg2 * nongap1;
-                    dD = pick3(tD, tH, tV, 0, 1, 2, out.D);
-                    const long long gcH = cgo * s_o + cge * s_e + cto * s_to + cte * s_te;
-                    tD = L.D + gcH;
-                    tH = L.H + cge * k_e + cte * k_te;
-                    if (three) dH = pick3(tD, L.V + gcH, tH, 0, 2, 1, out.H);
-                    else if (tD > tH) { out.H = tD; dH = 0; } else { out.H = tH; dH = 1; }
-                    const long long gcV = srgo * ci.s_o + srge * ci.s_e + srto * ci.s_to + srte * ci.s_te;
-                    tD = U.D + gcV;
-                    tV = U.V + srge * ci.k_e + srte * ci.k_te;
-                    if (three) dV = pick3(tD, U.H + gcV, tV, 0, 1, 2, out.V);
-                    else if (tD > tV) { out.V = tD; dV = 0; } else { out.V = tV; dV = 2; }
-                }
-                db = (unsigned char)(dD | dH << 2 | dV << 4);
             }
-            drow[j] = db;
-            cur = out;
-            if (last_row) {
-                if (j == (int)WC) { last_out[0] = out.D; last_out[1] = out.H; last_out[2] = out.V; }
-            } else if (lane == 31) {
-                // park the stripe's last row for the next stripe; publish every 4th column
-                store_cell(brow + j, out);
-                if (NW > 1 && ((j & 3) == 3 || j == (int)WC)) {
-                    __threadfence_block();
-                    prog[team_warp] = my_base + (unsigned)j + 1;
+            if (active) {
+                drow[j] = db;
+                cur = out;
+                if (last_row) {
+                    if (j == (int)WC) { last_out[0] = out.D; last_out[1] = out.H; last_out[2] = out.V; }
+                } else if (lane == 31) {
+                    // park the stripe's last row for the next stripe; publish once per chunk
+                    store_cell(brow + j, out);
+                    if (NW > 1 && ((j % kChunk) == kChunk - 1 || j == (int)WC)) {
+                        __threadfence_block();
+                        prog[team_warp] = my_base + (unsigned)j + 1;
+                    }
                 }
             }
         }
@@ -258,105 +484,44 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const long long* _
 
 // NW == 1: four independent merges per 128-thread block (one warp each).  NW > 1: one merge per block.
 template <int NW>
-__global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_align(const DpParams P)
+__global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_fill(const DpParams P)
 {
     constexpr int kBlockWarps = NW == 1 ? kDpWarps : NW;
-    extern __shared__ int sm_dyn[];                         // [kBlockWarps][2][30*32]: nz symbol ids, nz counts
-    int (*sm_nz_k)[30 * 32] = reinterpret_cast<int (*)[30 * 32]>(sm_dyn);
-    int (*sm_nz_c)[30 * 32] = reinterpret_cast<int (*)[30 * 32]>(sm_dyn + kBlockWarps * 30 * 32);
     __shared__ unsigned sm_prog[kBlockWarps];
-    __shared__ unsigned long long sm_nz[2];
     __shared__ long long sm_last[kBlockWarps][3];
+    __shared__ __align__(16) Cell sm_brow[kBlockWarps][2][kChunk];
     const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const uint32_t team_warp = NW == 1 ? 0 : warp;
-    const uint32_t tid = NW == 1 ? lane : threadIdx.x;          // index inside the team
-    constexpr uint32_t kTeam = NW * 32;
     const uint32_t slot = NW == 1 ? blockIdx.x * kDpWarps + warp : blockIdx.x;
     if (slot >= P.n_jobs) return;
     auto team_sync = [&]() { if (NW == 1) __syncwarp(); else __syncthreads(); };
     const uint32_t jid = P.order[slot];
     const DpJobDev J = P.jobs[jid];
+    const DpMeta M = P.meta[jid];
     if (threadIdx.x < kBlockWarps) sm_prog[threadIdx.x] = 0;
-    if (threadIdx.x < 2) sm_nz[threadIdx.x] = 0;
-    if (NW > 1) __syncthreads();
-
-    // ---- variant and orientation (CProfile::Align, profile.cpp:254-304)
-    int var, sw = 0;
-    if (J.card1 == 1 && J.card2 == 1) var = 0;
-    else if (J.card1 == 1) var = 1;
-    else if (J.card2 == 1) { var = 1; sw = 1; }
-    else {
-        var = 2;
-        unsigned long long nz1 = 0, nz2 = 0;
-        for (size_t k = tid; k < ((size_t)J.w1 + 1) * 32; k += kTeam) nz1 += J.c1[k] != 0;
-        for (size_t k = tid; k < ((size_t)J.w2 + 1) * 32; k += kTeam) nz2 += J.c2[k] != 0;
-        for (int o = 16; o; o >>= 1) {
-            nz1 += __shfl_xor_sync(0xffffffffu, nz1, o);
-            nz2 += __shfl_xor_sync(0xffffffffu, nz2, o);
-        }
-        if (NW > 1) {
-            if (lane == 0) { atomicAdd(&sm_nz[0], nz1); atomicAdd(&sm_nz[1], nz2); }
-            __syncthreads();
-            nz1 = sm_nz[0]; nz2 = sm_nz[1];
-        }
-        if (!(nz1 * (unsigned long long)J.w2 < nz2 * (unsigned long long)J.w1)) sw = 1;
-    }
-    const long long* SR = sw ? J.s2 : J.s1;  const int* CR = sw ? J.c2 : J.c1;
-    const long long* SC = sw ? J.s1 : J.s2;  const int* CC = sw ? J.c1 : J.c2;
-    const uint32_t WR = sw ? J.w2 : J.w1, WC = sw ? J.w1 : J.w2;
-    const int nR = (int)(sw ? J.card2 : J.card1), nC = (int)(sw ? J.card1 : J.card2);
-    const uint32_t wmax = J.w1 > J.w2 ? J.w1 : J.w2;
-
-    unsigned char* scratch = P.scratch + J.scratch_off;
-    ColInfo* col = reinterpret_cast<ColInfo*>(scratch);
-    Cell* brow = reinterpret_cast<Cell*>(scratch + sizeof(ColInfo) * ((size_t)wmax + 1));
-    unsigned char* tmp_path = scratch + (sizeof(ColInfo) + sizeof(Cell)) * ((size_t)wmax + 1);
-    unsigned char* dirs = P.dirs + J.dirs_off;
-    const size_t ld = (size_t)WC + 1;
-    const long long go = P.go, ge = P.ge, to = P.to, te = P.te;
-
-    // ---- column-side constants and row 0
-    for (uint32_t j = tid; j <= WC; j += kTeam) {
-        ColInfo ci;
-        ci.pad = 0; ci.pad2[0] = 0;
-        if (j >= 1) {
-            solve_gaps(CC, j, WC, nC, ci.s_o, ci.s_e, ci.s_to, ci.s_te, ci.k_e, ci.k_te);
-            const int* cc = CC + (size_t)j * 32;
-            ci.chg2 = (long long)cc[kGO] * (ge - go) + (long long)cc[kTO] * (te - to);
-            ci.sym = var == 0 ? seq_symbol(CC, j) : 22;
-            ci.gcv1 = go * ci.s_o + ge * ci.s_e + to * ci.s_to + te * ci.s_te;
-            ci.contv1 = ge * ci.k_e + te * ci.k_te;
-        } else {
-            ci.s_o = ci.s_e = ci.s_to = ci.s_te = ci.k_e = ci.k_te = 0; ci.sym = 22; ci.chg2 = 0; ci.gcv1 = 0; ci.contv1 = 0;
-        }
-        col[j] = ci;
-        dirs[j] = j == 0 ? 0 : (unsigned char)(1 | 1 << 2 | 1 << 4);
-    }
-    if (tid == 0) {
-        store_cell(brow, Cell{0, kNeg, kNeg});
-        long long h = 0;
-        for (uint32_t j = 1; j <= WC; ++j) {
-            const long long* sc = SC + (size_t)j * 32;
-            if (var == 0) h = j == 1 ? to : h + te;            // max(H, D=NEG) + te
-            else if (var == 1) h = j == 1 ? sc[kTO] : h + sc[kTE];
-            else h = j == 1 ? sc[kTO] * nR : h + sc[kTE] * nR;
-            store_cell(brow + j, Cell{kNeg, j == WC ? kNeg : h, kNeg});
-        }
-    }
-    __threadfence_block();
     team_sync();
 
+    const Scratch L(J.w1, J.w2);
+    unsigned char* scratch = P.scratch + J.scratch_off;
+    const ColInfo* col = reinterpret_cast<const ColInfo*>(scratch + L.col);
+    Cell* brow = reinterpret_cast<Cell*>(scratch + L.brow);
+    unsigned char* tmp_path = scratch + L.tmp;
+    unsigned char* dirs = P.dirs + J.dirs_off;
+    const long long* T = P.T + J.t_off;
+    const uint32_t WR = M.WR, WC = M.WC;
+    const size_t ld = (size_t)WC + 1;
+
     long long* last_out = sm_last[warp];
-    if (var == 0) dp_stripes<0, NW>(P, SR, CR, SC, WR, WC, nR, nC, col, brow, dirs, sm_nz_k[warp], sm_nz_c[warp], sm_prog, team_warp, last_out);
-    else if (var == 1) dp_stripes<1, NW>(P, SR, CR, SC, WR, WC, nR, nC, col, brow, dirs, sm_nz_k[warp], sm_nz_c[warp], sm_prog, team_warp, last_out);
-    else dp_stripes<2, NW>(P, SR, CR, SC, WR, WC, nR, nC, col, brow, dirs, sm_nz_k[warp], sm_nz_c[warp], sm_prog, team_warp, last_out);
+    if (M.var == 0) dp_stripes<0, NW>(P, M, T, col, brow, dirs, sm_prog, team_warp, last_out, sm_brow[warp]);
+    else if (M.var == 1) dp_stripes<1, NW>(P, M, T, col, brow, dirs, sm_prog, team_warp, last_out, sm_brow[warp]);
+    else dp_stripes<2, NW>(P, M, T, col, brow, dirs, sm_prog, team_warp, last_out, sm_brow[warp]);
     __threadfence_block();
     team_sync();
     if (team_warp != 0) return;
 
     // the warp that owned the final stripe stored (D,H,V)(WR,WC)
     const uint32_t owner_warp = NW == 1 ? warp : ((WR + 31) / 32 - 1) % NW;
-    long long last[3] = {sm_last[owner_warp][0], sm_last[owner_warp][1], sm_last[owner_warp][2]};
+    const long long last[3] = {sm_last[owner_warp][0], sm_last[owner_warp][1], sm_last[owner_warp][2]};
 
     // ---- traceback (ConstructProfile, profile.cpp:727-775), lane 0 walks, the warp reverses
     uint32_t n = 0;
@@ -385,7 +550,7 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_align(con
         r.last[0] = last[0]; r.last[1] = last[1]; r.last[2] = last[2];
         r.path_offset = J.path_off; r.dirs_offset = J.dirs_off;
         r.path_len = n; r.rows_width = WR; r.cols_width = WC;
-        r.swapped = (uint8_t)sw; r.variant = (uint8_t)var; r.pad[0] = r.pad[1] = 0;
+        r.swapped = (uint8_t)M.sw; r.variant = (uint8_t)M.var; r.pad[0] = r.pad[1] = 0;
         P.results[jid] = r;
     }
 }
@@ -407,6 +572,7 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
     DpState& S = ctx->dp;
     std::vector<DpJobDev> dev(n);
     std::vector<uint32_t> order(n);
+    std::vector<unsigned long long> tblock(n + 1, 0);
     unsigned long long path_off = 0, dirs_off = 0, scratch_off = 0, cells = 0;
     for (uint32_t k = 0; k < n; ++k) {
         const famsa_dp_job& j = jobs[k];
@@ -418,16 +584,20 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
         d.s1 = reinterpret_cast<const long long*>(j.p1.scores); d.c1 = j.p1.counters;
         d.s2 = reinterpret_cast<const long long*>(j.p2.scores); d.c2 = j.p2.counters;
         d.w1 = j.p1.width; d.card1 = j.p1.card; d.w2 = j.p2.width; d.card2 = j.p2.card;
-        d.path_off = path_off; d.dirs_off = dirs_off; d.scratch_off = scratch_off;
+        d.path_off = path_off; d.dirs_off = dirs_off; d.scratch_off = scratch_off; d.t_off = dirs_off;
+        const unsigned long long mat = ((unsigned long long)d.w1 + 1) * (d.w2 + 1);
         path_off += (unsigned long long)d.w1 + d.w2;
-        dirs_off += ((unsigned long long)d.w1 + 1) * (d.w2 + 1);
-        const unsigned long long wmax = std::max(d.w1, d.w2);
-        scratch_off += ((sizeof(ColInfo) + sizeof(Cell)) * (wmax + 1) + d.w1 + d.w2 + 63) / 64 * 64;
+        dirs_off += mat;
+        scratch_off += Scratch(d.w1, d.w2).total;
+        tblock[k + 1] = tblock[k] + (mat + kTThreads * kTCellsPerThread - 1) / (kTThreads * kTCellsPerThread);
         cells += (unsigned long long)d.w1 * d.w2;
     }
+    if (tblock[n] > 0x7fffffffull) { set_error("dp batch too large for one launch; split it"); return FAMSA_E_INVALID; }
     // merges whose shorter side spans several 32-row stripes get a whole block (kDpTeamWarps warps pipelined
     // over the stripes); the rest run one warp per merge.  Both groups cost-descending.
-    auto big = [&](uint32_t a) { return std::min(dev[a].w1, dev[a].w2) > kDpTeamMinWidth; };
+    uint32_t team_min = kDpTeamMinWidth;
+    if (const char* e = getenv("FAMSA_DP_TEAM_MIN")) team_min = (uint32_t)atoi(e);   // development knob
+    auto big = [&](uint32_t a) { return std::min(dev[a].w1, dev[a].w2) > team_min; };
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
         if (big(a) != big(b)) return big(a);
@@ -437,8 +607,11 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
     while (n_big < n && big(order[n_big])) ++n_big;
     S.last_cells = cells;
     FB_TRY(S.d_jobs.reserve(sizeof(DpJobDev) * std::max(1u, n)));
+    FB_TRY(S.d_meta.reserve(sizeof(DpMeta) * std::max(1u, n)));
     FB_TRY(S.d_order.reserve(sizeof(uint32_t) * std::max(1u, n)));
+    FB_TRY(S.d_tblock.reserve(sizeof(unsigned long long) * (n + 1)));
     FB_TRY(S.d_scratch.reserve(std::max<unsigned long long>(scratch_off, 64)));
+    FB_TRY(S.d_T.reserve(std::max<unsigned long long>(dirs_off * 8, 64)));
     uint8_t* dirs = d_dirs;
     if (!dirs) {
         FB_TRY(S.d_dirs.reserve(std::max<unsigned long long>(dirs_off, 64)));
@@ -447,27 +620,30 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
     FB_CUDA(cudaEventRecord(ctx->ev[0], st));
     FB_CUDA(cudaMemcpyAsync(S.d_jobs.p, dev.data(), sizeof(DpJobDev) * n, cudaMemcpyHostToDevice, st));
     FB_CUDA(cudaMemcpyAsync(S.d_order.p, order.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    FB_CUDA(cudaMemcpyAsync(S.d_tblock.p, tblock.data(), sizeof(unsigned long long) * (n + 1), cudaMemcpyHostToDevice, st));
     DpParams P{};
     P.jobs = S.d_jobs.as<DpJobDev>();
+    P.meta = S.d_meta.as<DpMeta>();
     P.order = S.d_order.as<uint32_t>();
     P.n_jobs = n;
     P.go = gaps[0]; P.ge = gaps[1]; P.to = gaps[2]; P.te = gaps[3];
     P.dirs = dirs;
     P.path = d_path;
     P.scratch = S.d_scratch.as<uint8_t>();
+    P.T = S.d_T.as<long long>();
+    P.tblock = S.d_tblock.as<unsigned long long>();
     P.results = d_results;
     FB_CUDA(cudaEventRecord(ctx->ev[1], st));
-    // `order` is cost-descending with the team-kernel jobs first (see the sort above)
-    static bool configured = false;
-    constexpr size_t smem_big = (size_t)kDpTeamWarps * 2 * 30 * 32 * sizeof(int);
-    constexpr size_t smem_small = (size_t)kDpWarps * 2 * 30 * 32 * sizeof(int);
-    if (!configured) {
-        FB_CUDA(cudaFuncSetAttribute(k_dp_align<kDpTeamWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
-        FB_CUDA(cudaFuncSetAttribute(k_dp_align<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
-        configured = true;
+    if (n) {
+        k_dp_prep<<<n, 128, 0, st>>>(P);
+        FB_CUDA(cudaGetLastError());
+        k_dp_t<<<(unsigned)tblock[n], kTThreads, 0, st>>>(P);
+        FB_CUDA(cudaGetLastError());
+        ctx->launches += 2;
     }
+    // `order` has the team-kernel jobs first (see the sort above)
     if (n_big) {
-        k_dp_align<kDpTeamWarps><<<n_big, kDpTeamWarps * 32, smem_big, st>>>(P);
+        k_dp_fill<kDpTeamWarps><<<n_big, kDpTeamWarps * 32, 0, st>>>(P);
         FB_CUDA(cudaGetLastError());
         ctx->launches++;
     }
@@ -475,7 +651,7 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
         DpParams Q = P;
         Q.order = P.order + n_big;
         Q.n_jobs = n - n_big;
-        k_dp_align<1><<<(Q.n_jobs + kDpWarps - 1) / kDpWarps, kDpWarps * 32, smem_small, st>>>(Q);
+        k_dp_fill<1><<<(Q.n_jobs + kDpWarps - 1) / kDpWarps, kDpWarps * 32, 0, st>>>(Q);
         FB_CUDA(cudaGetLastError());
         ctx->launches++;
     }
@@ -508,7 +684,7 @@ int dp_run_host(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int6
     uint8_t* hb = S.h_stage.data();
     uint8_t* db = S.d_tables.as<uint8_t>();
     auto put = [&](const void* src, size_t sz) { memcpy(hb + at, src, sz); void* d = db + at; at += sz; return d; };
-    for (uint32_t k = 0; k < n; ++k) {      // all int64 tables first keeps 8-byte alignment trivially: sizes are multiples of 128
+    for (uint32_t k = 0; k < n; ++k) {      // every table size is a multiple of 128 bytes, so alignment is kept
         famsa_dp_job& j = dj[k];
         j.p1.scores = static_cast<const int64_t*>(put(jobs[k].p1.scores, ((size_t)jobs[k].p1.width + 1) * 32 * 8));
         j.p2.scores = static_cast<const int64_t*>(put(jobs[k].p2.scores, ((size_t)jobs[k].p2.width + 1) * 32 * 8));
