@@ -49,16 +49,7 @@ def workload(n_gpus: int):
     return seqio.synth_family(n, LEN, SEED), n
 
 
-def row_shards(n: int, parts: int):
-    """Row boundaries giving every rank the same number of pairs (rows i has i pairs)."""
-    total = n * (n - 1) // 2
-    bounds = [0]
-    for r in range(1, parts):
-        target = total * r / parts
-        b = int(round((1 + math.sqrt(1 + 8 * target)) / 2))
-        bounds.append(min(max(b, bounds[-1]), n))
-    bounds.append(n)
-    return bounds
+from famsa_b200.sharding import row_shards, shard_sizes, tri, all_gather_blocks  # noqa: E402
 
 
 class ClockSampler:
@@ -114,13 +105,160 @@ def cpu_reference_run(codes, offsets, lens, n, threads, row_begin=0):
     return sec, pairs
 
 
+# ---------------------------------------------------------------------------------------------- HP-2 leg
+DP_MERGES, DP_CARD, DP_WIDTH, DP_SEED = 296, (24, 64), (380, 520), 11
+DP_GAPS = (-14850, -1250, -660, -660)            # CParams defaults x1000 (src/core/params.cpp:26-29)
+
+
+def dp_workload(rank: int):
+    """A batch of independent profile-profile merges of the size the upper levels of a 10k x 400 aa guide tree
+    produce: 296 (= 2 x 148 SMs) pairs of aligned blocks, 24-64 sequences x 380-520 columns each.  The tables
+    are built on the host by famsa_b200.profiles (mirror of CProfile::CalculateCounters/Scores)."""
+    from famsa_b200 import profiles
+    rng = np.random.default_rng(DP_SEED + rank)
+    sm = profiles.synth_score_matrix(rng)
+    rows, jobs = [], []
+    for _ in range(DP_MERGES):
+        pair = []
+        for _ in range(2):
+            r = profiles.synth_alignment(int(rng.integers(*DP_CARD)), int(rng.integers(*DP_WIDTH)), rng)
+            pair.append(r)
+        rows.append(pair)
+        a = profiles.tables_from_rows(pair[0], sm, DP_GAPS)
+        b = profiles.tables_from_rows(pair[1], sm, DP_GAPS)
+        jobs.append((a[0], a[1], a[2], b[0], b[1], b[2]))
+    return rows, jobs
+
+
+def dp_cpu_reference(rows, threads):
+    """The reference's CProfile::Align (+ ConstructProfile, inseparable without patching it) over the same
+    aligned blocks, one merge per task on `threads` host threads (ComputeAlignment's shape, msa.cpp:375-426)."""
+    from famsa_b200 import seqio
+    from oracle import pyoracle
+    dp = pyoracle.RefDp(0)
+    dp.set_gaps(DP_GAPS)
+    to_str = lambda r: ["".join("-" if c < 0 else seqio.ALPHABET[c] for c in row) + "A" for row in r]
+    p1 = [dp.profile(to_str(a), list(range(len(a)))) for a, _ in rows]
+    p2 = [dp.profile(to_str(b), list(range(1000, 1000 + len(b)))) for _, b in rows]
+    sec, cells = dp.align_pairs_mt(p1, p2, threads)
+    dp.close()
+    return sec, cells
+
+
+def bench_dp(eng, torch, dist, world, rank, steps, warmup, l2_flush, stream, want_cpu):
+    import ctypes as C
+    from famsa_b200.binding import DpJob, DpProfile
+    rows, jobs = dp_workload(rank)
+    n = len(jobs)
+    cells = sum((j[0].shape[0] - 1) * (j[3].shape[0] - 1) for j in jobs)
+    gaps = np.array(DP_GAPS, dtype=np.int64)
+    # device-resident copies of every table
+    sc = torch.from_numpy(np.concatenate([np.concatenate([j[0].ravel(), j[3].ravel()]) for j in jobs])).cuda()
+    cn = torch.from_numpy(np.concatenate([np.concatenate([j[1].ravel(), j[4].ravel()]) for j in jobs])).cuda()
+    arr = (DpJob * n)()
+    so = co = 0
+    path_total = 0
+    for k, j in enumerate(jobs):
+        w1, w2 = j[0].shape[0] - 1, j[3].shape[0] - 1
+        arr[k].p1 = DpProfile(sc.data_ptr() + 8 * so, cn.data_ptr() + 4 * co, w1, j[2])
+        so += (w1 + 1) * 32; co += (w1 + 1) * 32
+        arr[k].p2 = DpProfile(sc.data_ptr() + 8 * so, cn.data_ptr() + 4 * co, w2, j[5])
+        so += (w2 + 1) * 32; co += (w2 + 1) * 32
+        path_total += w1 + w2
+    d_res = torch.empty(n * 64, dtype=torch.uint8, device="cuda")
+    d_path = torch.empty(path_total, dtype=torch.uint8, device="cuda")
+
+    def step_device():
+        eng.dp_align_batch_device(arr, n, gaps, d_res.data_ptr(), d_path.data_ptr(), 0, stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step_device()
+    barrier()
+    l0 = eng.kernel_launches()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s in range(steps):
+        l2_flush.fill_(s)
+        ev[s][0].record()
+        step_device()
+        ev[s][1].record()
+    barrier()
+    launches = eng.kernel_launches() - l0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    # kernel-only time (prep + T + fill) from the library's own events on the context stream
+    eng.dp_align_batch_device(arr, n, gaps, d_res.data_ptr(), d_path.data_ptr(), 0, 0)
+    kern_ms = eng.dp_last_timing()[1]
+    # e2e through the host-buffer C ABI
+    for _ in range(max(1, warmup // 2)):
+        eng.dp_align_batch(jobs, gaps)
+    barrier()
+    t0 = time.time()
+    for _ in range(steps):
+        res = eng.dp_align_batch(jobs, gaps)
+    barrier()
+    e2e_s = time.time() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    h2d = int(sum(j[0].nbytes + j[1].nbytes + j[3].nbytes + j[4].nbytes for j in jobs))
+    d2h = int(path_total + 64 * n)
+    out = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        # SURVEY 8(d): per merge (W1+1)(W2+1) direction bytes + traceback + tables + path
+        alg = sum((j[0].shape[0]) * (j[3].shape[0]) + 2 * (j[0].shape[0] + j[3].shape[0] - 2)
+                  + 160 * j[0].shape[0] + 384 * j[3].shape[0] for j in jobs)
+        achieved = alg / (kern_ms / 1e3) / 1e9
+        out = {"metric": "profile DP cells/sec", "unit": "cells/s", "value": cells * world * steps / (dev_ms / 1e3),
+               "ms_per_step": dev_ms / steps,
+               "config": {"workload": f"{n} independent profile-profile merges per GPU, {DP_CARD[0]}-{DP_CARD[1]} sequences x "
+                                      f"{DP_WIDTH[0]}-{DP_WIDTH[1]} columns each (seed {DP_SEED}), unbanded AlignProfProf + traceback",
+                          "cells_per_step_per_gpu": cells, "multi_gpu": "merges sharded across ranks, no collective (replicas per merge)"},
+               "e2e": {"value": cells * world * steps / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / steps},
+               "gpu_launches": int(launches),
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                            "traffic": None, "peak_source": peak_src, "kernel": "fb::k_dp_prep + k_dp_t + k_dp_fill<8>",
+                            "kernel_ms": kern_ms,
+                            "note": "latency-bound wavefront (int64 recurrence), not HBM-bound: see DESIGN.md section 4"}}
+        if want_cpu:
+            from oracle import pyoracle
+            if pyoracle.have_ref():
+                threads = usable_cpus()
+                sec, c = dp_cpu_reference(rows, threads)
+                out["cpu_baseline"] = {"value": c / sec, "unit": "cells/s", "cores": threads, "kind": "reference",
+                                       "sample": f"the same {n} merges, CProfile::Align incl. ConstructProfile, one merge per thread task ({sec:.2f} s)"}
+    return out
+
+
+def usable_cpus() -> int:
+    """Host threads this process may really use: min(affinity, cgroup cpu quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(p))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import pyoracle
     (codes, offsets, lens), n = workload(args.gpus)
-    threads = os.cpu_count() or 1
+    threads = usable_cpus()
     if not pyoracle.have_ref():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libfamsa_ref.so not built"}))
         return
@@ -144,6 +282,10 @@ def run_reference(args):
                              "sample": sample + "; CLCSBP AVX2 via calculateDistanceVector, one row per task"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    rows, _ = dp_workload(0)
+    sec, cells = dp_cpu_reference(rows, threads)
+    line["dp"] = {"metric": "profile DP cells/sec", "unit": "cells/s", "value": cells / sec, "cores": threads,
+                  "sample": f"{len(rows)} merges of the b200 arm's DP workload, CProfile::Align incl. ConstructProfile ({sec:.2f} s)"}
     print(json.dumps(line))
 
 
@@ -175,11 +317,9 @@ def main():
     (codes, offsets, lens), n = workload(world)
     bounds = row_shards(n, world)
     rb, re = bounds[rank], bounds[rank + 1]
-    tri = lambda r: r * (r - 1) // 2 if r else 0
     my_pairs = tri(re) - tri(rb)
     total_pairs = tri(n)
-    shard_sizes = [tri(bounds[r + 1]) - tri(bounds[r]) for r in range(world)]
-    max_shard = max(shard_sizes)
+    max_shard = max(shard_sizes(bounds))
 
     eng = famsa_b200.Engine(local)
     eng.upload(codes, offsets, lens)                       # resident inputs for the `value` leg
@@ -193,7 +333,7 @@ def main():
     def step_device():
         eng.triangle_device(rb, re, d_block.data_ptr(), 2, stream)
         if world > 1:
-            dist.all_gather_into_tensor(d_all, d_block)
+            all_gather_blocks(d_block, bounds, dist, out=d_all)
 
     def barrier():
         if world > 1:
@@ -298,7 +438,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             from oracle import pyoracle
             if pyoracle.have_ref():
-                threads = os.cpu_count() or 1
+                threads = usable_cpus()
                 sec, pairs = cpu_reference_run(codes, offsets, lens, n, threads, 0)
                 line["cpu_baseline"] = {"value": pairs / sec, "unit": UNIT, "cores": threads, "kind": "reference",
                                         "sample": f"whole {n} x {LEN} aa triangle ({pairs} pairs, {sec:.2f} s), "
@@ -311,6 +451,11 @@ def main():
                 pairs = tri(n) - tri(n - n_s)
                 line["cpu_baseline"] = {"value": pairs / sec, "unit": UNIT, "cores": 1, "kind": "port",
                                         "sample": f"last {n_s} rows ({pairs} pairs)"}
+    dp = bench_dp(eng, torch, dist, world, rank, max(2, args.steps // 2), args.warmup, l2_flush, stream,
+                  want_cpu=(world == 1 and not args.no_cpu_baseline))
+    if rank == 0:
+        line["dp"] = dp
+        line["gpu_launches"] = int(launches) + (dp["gpu_launches"] if dp else 0)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -187,6 +187,13 @@ class Engine:
             out.append(d)
         return out
 
+    def dp_align_batch_device(self, job_array, n: int, gaps, d_results: int, d_path: int, d_dirs: int = 0, stream: int = 0):
+        """job_array: ctypes (DpJob * n) whose table pointers are DEVICE pointers; d_* are device pointers."""
+        g = np.ascontiguousarray(gaps, dtype=np.int64)
+        self._check(self.lib.famsa_dp_align_batch_device(self.h, C.byref(job_array), n, _ptr(g), C.c_void_p(d_results),
+                                                         C.c_void_p(d_path), C.c_void_p(d_dirs) if d_dirs else None,
+                                                         C.c_void_p(stream) if stream else None))
+
     def dp_last_timing(self) -> tuple[float, float, int]:
         t, m, p = C.c_float(), C.c_float(), C.c_uint64()
         self._check(self.lib.famsa_dp_last_timing(self.h, C.byref(t), C.byref(m), C.byref(p)))

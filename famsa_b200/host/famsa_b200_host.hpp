@@ -1,0 +1,164 @@
+// famsa_b200_host.hpp -- C++ host side above the C ABI, shaped like the reference's own interfaces so
+// that FAMSA's guide-tree builders and CProfile can be pointed at the GPU with one-line changes
+// (INTEGRATION.md shows the exact seams).  Header-only; link with -lfamsa_b200.
+//
+//   reference                                                     here
+//   ------------------------------------------------------------  -----------------------------------------
+//   CLCSBP lcsbp(instruction_set)            src/lcs/lcsbp.h:15   famsa_b200::CLCSBP lcsbp(ctx, sequences)
+//   lcsbp.GetLCSBP(seq0, s1..s8, dist)       lcsbp.h:38-46        lcsbp.GetLCSBP(seq0, ids, n, dist)
+//   calculateDistanceVector/Range/Matrix     AbstractTreeGenerator.hpp:131,191,379   same names, same transforms
+//   Transform<T, Distance::*>                AbstractTreeGenerator.hpp:28-82         famsa_b200::Transform<T, D>
+//   CProfile::Align(p1, p2, ...)             src/core/profile.cpp:244                famsa_b200::AlignBatch(...)
+// Errors: the reference throws std::runtime_error and catches it in main() (src/famsa.cpp:160-165);
+// every non-zero C-ABI status is rethrown here the same way.  There is no CPU fallback.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/famsa_b200.h"
+
+namespace famsa_b200 {
+
+inline void check(int rc)
+{
+    if (rc != FAMSA_OK) throw std::runtime_error(std::string("famsa_b200: ") + famsa_last_error());
+}
+
+class Context {
+    famsa_ctx* h_ = nullptr;
+public:
+    explicit Context(int device = -1) { check(famsa_create(device, &h_)); }
+    ~Context() { famsa_destroy(h_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    famsa_ctx* get() const { return h_; }
+};
+
+// ---- LCS -> distance, on the host, bit-identical to the reference (AbstractTreeGenerator.hpp:28-82)
+enum class Distance { indel_div_lcs, indel075_div_lcs, pairwise_identity };
+
+template <class T, Distance measure> struct Transform;
+
+template <class T> struct Transform<T, Distance::indel075_div_lcs> {
+    std::vector<T> pp_pow075_rec;           // lazily grown table of (T) pow(i, 0.75), like the reference's
+    T operator()(uint32_t lcs, uint32_t len1, uint32_t len2)
+    {
+        const T indel = (T)(len1 + len2 - 2 * lcs);
+        const T l = (T)lcs;
+        if (indel >= (T)pp_pow075_rec.size()) {
+            const uint32_t upto = (uint32_t)indel;
+            for (uint32_t v = (uint32_t)pp_pow075_rec.size(); v <= upto; ++v) pp_pow075_rec.push_back((T)std::pow(v, 0.75));
+        }
+        if (l) return pp_pow075_rec[(size_t)indel] / l;
+        return (T)std::nextafter(std::numeric_limits<T>::max(), 0);
+    }
+};
+template <class T> struct Transform<T, Distance::indel_div_lcs> {
+    T operator()(uint32_t lcs, uint32_t len1, uint32_t len2)
+    {
+        const T indel = (T)(len1 + len2 - 2 * lcs);
+        if (lcs) return (T)indel / lcs;
+        return (T)std::nextafter(std::numeric_limits<T>::max(), 0);
+    }
+};
+template <class T> struct Transform<T, Distance::pairwise_identity> {
+    T operator()(uint32_t lcs, uint32_t len1, uint32_t len2) { return (T)lcs / std::min(len1, len2); }
+};
+
+// what the batch drivers need to know about a sequence (CSequence::data / CSequence::length)
+struct SequenceView {
+    const int8_t* data;
+    uint32_t length;
+};
+
+// One instance serves every worker thread (the C ABI serialises calls on a context); in the reference each
+// worker owns a CLCSBP because the CPU implementation keeps per-thread scratch (lcsbp_avx2_intr.h:27-36).
+class CLCSBP {
+    Context& ctx_;
+    std::vector<uint32_t> lens_;
+public:
+    // uploads the set = ComputeBitMasks for every sequence (sequence.cpp:190-201), once
+    CLCSBP(Context& ctx, const SequenceView* seqs, uint32_t n) : ctx_(ctx), lens_(n)
+    {
+        std::vector<uint64_t> off(n);
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < n; ++i) { off[i] = total; lens_[i] = seqs[i].length; total += seqs[i].length; }
+        std::vector<int8_t> codes(std::max<uint64_t>(total, 1));
+        for (uint32_t i = 0; i < n; ++i) std::copy(seqs[i].data, seqs[i].data + seqs[i].length, codes.begin() + off[i]);
+        check(famsa_lcs_upload(ctx_.get(), codes.data(), off.data(), lens_.data(), n));
+    }
+    uint32_t length(uint32_t i) const { return lens_[i]; }
+
+    // the raw seam: LCS lengths of row `seq0` against n others (GetLCSBP's 4- and 8-way calls, any n)
+    void GetLCSBP(uint32_t seq0, const uint32_t* ids, uint32_t n, uint32_t* dist)
+    {
+        check(famsa_lcs_rows(ctx_.get(), &seq0, 1, ids, n, dist, 4));
+    }
+
+    // AbstractTreeGenerator::calculateDistanceVector: ref against sequences[0 .. n_seqs)
+    template <class distance_type, class Tr>
+    void calculateDistanceVector(Tr& transform, uint32_t ref, uint32_t n_seqs, distance_type* out_vector)
+    {
+        std::vector<uint32_t> lcs(std::max(1u, n_seqs));
+        check(famsa_lcs_rows(ctx_.get(), &ref, 1, nullptr, n_seqs, lcs.data(), 4));
+        for (uint32_t k = 0; k < n_seqs; ++k) out_vector[k] = transform(lcs[k], lens_[ref], lens_[k]);
+    }
+
+    // AbstractTreeGenerator::calculateDistanceRange / RangeSV: ref against an id range
+    template <class distance_type, class Iter, class Tr>
+    void calculateDistanceRange(Tr& transform, uint32_t ref, Iter first, Iter last, distance_type* out_vector)
+    {
+        std::vector<uint32_t> ids(first, last), lcs(std::max<size_t>(1, ids.size()));
+        check(famsa_lcs_rows(ctx_.get(), &ref, 1, ids.data(), (uint32_t)ids.size(), lcs.data(), 4));
+        for (size_t k = 0; k < ids.size(); ++k) out_vector[k] = transform(lcs[k], lens_[ref], lens_[ids[k]]);
+    }
+
+    // AbstractTreeGenerator::calculateDistanceMatrix: packed lower triangle (TriangleMatrix::access)
+    template <class distance_type, class Tr>
+    void calculateDistanceMatrix(Tr& transform, uint32_t n_seq, distance_type* out_matrix)
+    {
+        const size_t pairs = (size_t)n_seq * (n_seq ? n_seq - 1 : 0) / 2;
+        std::vector<uint32_t> lcs(std::max<size_t>(1, pairs));
+        check(famsa_lcs_triangle(ctx_.get(), 0, n_seq, lcs.data(), 4));
+        size_t at = 0;
+        for (uint32_t i = 1; i < n_seq; ++i)
+            for (uint32_t j = 0; j < i; ++j, ++at) out_matrix[at] = transform(lcs[at], lens_[i], lens_[j]);
+    }
+};
+
+// ---- profile alignment: what CProfile::Align hands to ConstructProfile
+struct AlignResult {
+    std::vector<uint8_t> path;     // direction_t per merged column, forward order (ConstructProfile's path[1..width])
+    int64_t total_score;
+    int64_t last[3];               // dp_row_elem_t {D,H,V} at the corner
+    bool swapped;                  // true: the DP's row profile is the second argument (Align called the loop as (p2,p1))
+    int variant;                   // 0 AlignSeqSeq, 1 AlignSeqProf, 2 AlignProfProf
+};
+
+// All ready merges of the guide tree in one call (the level-synchronous replacement for CProfileQueue's
+// one-at-a-time hand-out, queues.cpp:127-187).
+inline std::vector<AlignResult> AlignBatch(Context& ctx, const std::vector<famsa_dp_job>& jobs, const int64_t gaps[4])
+{
+    std::vector<famsa_dp_result> res(std::max<size_t>(1, jobs.size()));
+    size_t path_total = 0;
+    for (auto& j : jobs) path_total += (size_t)j.p1.width + j.p2.width;
+    std::vector<uint8_t> path(std::max<size_t>(1, path_total));
+    check(famsa_dp_align_batch(ctx.get(), jobs.data(), (uint32_t)jobs.size(), gaps, res.data(), path.data(), nullptr));
+    std::vector<AlignResult> out(jobs.size());
+    for (size_t k = 0; k < jobs.size(); ++k) {
+        const famsa_dp_result& r = res[k];
+        out[k].path.assign(path.begin() + r.path_offset, path.begin() + r.path_offset + r.path_len);
+        out[k].total_score = r.total_score;
+        std::copy(r.last, r.last + 3, out[k].last);
+        out[k].swapped = r.swapped != 0;
+        out[k].variant = r.variant;
+    }
+    return out;
+}
+
+} // namespace famsa_b200

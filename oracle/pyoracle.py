@@ -149,6 +149,8 @@ def ref() -> C.CDLL:
         lib.ref_profile_row.restype = C.c_int
         lib.ref_profile_align.argtypes = [vp, vp, vp, C.c_int]
         lib.ref_profile_align.restype = vp
+        lib.ref_dp_align_pairs_mt.argtypes = [vp, vp, vp, u32, C.c_int, vp]
+        lib.ref_dp_align_pairs_mt.restype = C.c_double
         _ref = lib
     return _ref
 
@@ -205,6 +207,15 @@ class RefDp:
             no = self.lib.ref_profile_row(p, i, buf)
             out[no] = buf.value.decode()
         return out
+
+    def align_pairs_mt(self, p1s, p2s, n_threads: int):
+        """Times len(p1s) independent merges on n_threads threads; consumes the profiles."""
+        n = len(p1s)
+        a = (C.c_void_p * n)(*[p.value for p in p1s])
+        b = (C.c_void_p * n)(*[p.value for p in p2s])
+        cells = C.c_uint64()
+        sec = self.lib.ref_dp_align_pairs_mt(self.h, a, b, n, n_threads, C.byref(cells))
+        return sec, cells.value
 
     def align(self, p1, p2, no_threads: int = 1):
         """Returns (merged profile handle, total_score).  p1 and p2 are consumed and freed."""

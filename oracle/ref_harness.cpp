@@ -304,4 +304,33 @@ void* ref_profile_align(void* h, void* p1, void* p2, int no_threads)
                         (uint32_t)no_threads, 4, s->atp.get());
 }
 
+// Times n independent merges on n_threads host threads (one merge per task, each merge sequential:
+// CProfile::Align with no_threads = 1 + ConstructProfile, as ComputeAlignment's workers run them,
+// msa.cpp:375-426).  The children are consumed and freed.  Returns wall seconds; *cells = sum W1*W2.
+double ref_dp_align_pairs_mt(void* h, void** p1s, void** p2s, uint32_t n, int n_threads, uint64_t* cells)
+{
+    auto* s = static_cast<DpSession*>(h);
+    uint64_t c = 0;
+    for (uint32_t k = 0; k < n; ++k)
+        c += (uint64_t)static_cast<CProfile*>(p1s[k])->width * static_cast<CProfile*>(p2s[k])->width;
+    if (cells) *cells = c;
+    std::atomic<uint32_t> next(0);
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> workers;
+    for (int t = 0; t < n_threads; ++t)
+        workers.emplace_back([&] {
+            refresh::active_thread_pool_v2 atp(1, 1);
+            for (;;) {
+                uint32_t k = next.fetch_add(1);
+                if (k >= n) break;
+                auto* a = static_cast<CProfile*>(p1s[k]);
+                auto* b = static_cast<CProfile*>(p2s[k]);
+                CProfile* m = new CProfile(a, b, &s->params, 1, 4, &atp);
+                delete a; delete b; delete m;
+            }
+        });
+    for (auto& w : workers) w.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
 } // extern "C"
