@@ -260,7 +260,7 @@ def run_reference(args):
     (codes, offsets, lens), n = workload(args.gpus)
     threads = usable_cpus()
     if not pyoracle.have_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libfamsa_ref.so not built"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libfamsa_ref.so not built"})
         return
     # bounded sample: the last rows of the triangle holding ~1/4 of the pairs when the set is large
     row_begin = 0 if n <= 12000 else int(n * math.sqrt(0.75))
@@ -286,10 +286,24 @@ def run_reference(args):
     sec, cells = dp_cpu_reference(rows, threads)
     line["dp"] = {"metric": "profile DP cells/sec", "unit": "cells/s", "value": cells / sec, "cores": threads,
                   "sample": f"{len(rows)} merges of the b200 arm's DP workload, CProfile::Align incl. ConstructProfile ({sec:.2f} s)"}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line goes to the real stdout; everything else any library prints (NCCL's version banner,
+    warnings) was redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -387,7 +401,7 @@ def main():
         if world > 1:
             # the gathered triangle is what a host-side tree builder consumes
             d_block[:my_pairs].copy_(h_out[:my_pairs].cuda(non_blocking=True))
-            dist.all_gather_into_tensor(d_all, d_block)
+            all_gather_blocks(d_block, bounds, dist, out=d_all)
 
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
@@ -456,7 +470,7 @@ def main():
     if rank == 0:
         line["dp"] = dp
         line["gpu_launches"] = int(launches) + (dp["gpu_launches"] if dp else 0)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
