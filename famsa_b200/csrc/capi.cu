@@ -67,6 +67,7 @@ void famsa_destroy(famsa_ctx* ctx)
                           &S.d_res, &S.d_refpos, &S.d_ids_a, &S.d_ids_b, &S.d_out_stage, &S.d_masks64, &S.d_x64})
         b->release();
     fb::DpState& D = ctx->dp;
+    if (D.h_pinned) cudaFreeHost(D.h_pinned);
     for (fb::DevBuf* b : {&D.d_jobs, &D.d_order, &D.d_scratch, &D.d_dirs, &D.d_tables, &D.d_results, &D.d_path, &D.d_meta, &D.d_tblock, &D.d_T})
         b->release();
     for (auto& ev : ctx->ev)

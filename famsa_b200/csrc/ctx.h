@@ -61,7 +61,8 @@ struct LcsState {
 
 struct DpState {
     DevBuf d_jobs, d_order, d_scratch, d_dirs, d_tables, d_results, d_path, d_meta, d_tblock, d_T;
-    std::vector<uint8_t> h_stage;
+    void* h_pinned = nullptr;          // pinned staging buffer of the host entry point
+    size_t h_pinned_cap = 0;
     uint64_t last_cells = 0;
     float last_total_ms = 0.f, last_kernel_ms = 0.f;
 };

@@ -117,6 +117,8 @@ __device__ __forceinline__ void cp_async_cell(Cell* smem_dst, const Cell* gsrc)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(reinterpret_cast<const char*>(gsrc) + 16) : "memory");
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+constexpr int kPrefetch = 8;                 // columns of look-ahead for the L1 prefetches
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -314,14 +316,17 @@ __global__ void __launch_bounds__(kTThreads) k_dp_t(const DpParams P)
 // k_dp_fill: the recurrence + traceback
 // ------------------------------------------------------------------------------------------------
 
-// One team = NW warps working on one merge.  Stripe k (rows 32k+1 .. 32k+32) belongs to warp k % NW;
-// consecutive stripes run as a staircase: stripe k+1 may touch column j only after stripe k has parked
-// its last row's cell (., j) in `brow`.  prog[w] is warp w's monotonically increasing count of parked
-// columns ((round * (WC+1)) + columns of the current stripe), polled by the warp that owns the next stripe.
+// One team = NW warps working on one merge.  Stripe k (rows 32k+1 .. 32k+32) belongs to warp k % NW.  The
+// stripes of a team run as a lock-step staircase over MACRO STEPS of kChunk wavefront steps: stripe k starts
+// kLag macro steps after stripe k-1, which is exactly late enough for every boundary-row column it is about
+// to read (and the chunk it prefetches for the next macro step) to have been parked by lane 31 of stripe k-1.
+// Because the schedule is a closed form, nobody polls: one __syncthreads per macro step orders the hand-over.
+constexpr int kLag = 4;      // macro steps between consecutive stripes: (31 + 2*kChunk) / kChunk rounded up
+
 template <int VAR, int NW>
 __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, const long long* __restrict__ T,
                                            const ColInfo* __restrict__ col, Cell* __restrict__ brow,
-                                           unsigned char* __restrict__ dirs, volatile unsigned* prog, uint32_t team_warp,
+                                           unsigned char* __restrict__ dirs, uint32_t team_warp,
                                            long long* last_out, Cell (*sb)[kChunk])
 {
     const uint32_t lane = threadIdx.x & 31;
@@ -329,156 +334,162 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
     const size_t ld = (size_t)WC + 1;
     const long long go = P.go, ge = P.ge, to = P.to, te = P.te;
     const uint32_t n_stripes = (WR + 31) / 32;
+    const uint32_t steps = WC + 1 + 31;                              // wavefront steps per stripe
+    const uint32_t S = (steps + kChunk - 1) / kChunk;                // macro steps per stripe
+    const uint32_t period = NW == 1 ? S : (S > (uint32_t)NW * kLag ? S : (uint32_t)NW * kLag);
+    const uint32_t rounds = (n_stripes + NW - 1) / NW;
+    // stripe k = r*NW + w starts at macro step r*period + w*kLag; the last stripe ends at m_end
+    const uint32_t last_k = n_stripes - 1;
+    const uint32_t m_end = (last_k / NW) * period + (last_k % NW) * kLag + S;
 
-    for (uint32_t k = team_warp; k < n_stripes; k += NW) {
-        const uint32_t i = k * 32 + 1 + lane;
-        const bool valid = i <= WR;
-        const bool last_row = i == WR;
-        const uint32_t prod_warp = (k + NW - 1) % NW;
-        const unsigned prod_base = k ? ((k - 1) / NW) * (WC + 1) : 0;
-        const unsigned my_base = (k / NW) * (WC + 1);
-        unsigned avail = k ? 0 : WC + 1;                 // columns of the producer stripe known to be parked
-        // ---- row-side constants (registers)
-        int s_o = 0, s_e = 0, s_to = 0, s_te = 0, k_e = 0, k_te = 0, g1o = 0, g1t = 0;
-        long long nongap1 = 0, srgo = 0, srge = 0, srto = 0, srte = 0, col0cost = 0;
-        if (valid) {
-            if (VAR == 2) {
-                const int* rc = M.CR + (size_t)i * 32;
-                solve_gaps(M.CR, i, WR, M.nR, s_o, s_e, s_to, s_te, k_e, k_te);
-                g1o = rc[kGO]; g1t = rc[kTO];
-                for (int q = 0; q < 24; ++q) nongap1 += rc[q];
-                const long long* sr = M.SR + (size_t)i * 32;
-                srgo = sr[kGO]; srge = sr[kGE]; srto = sr[kTO]; srte = sr[kTE];
-                col0cost = (i == 1 ? srto : srte) * M.nC;
-            } else if (VAR == 1) col0cost = (i == 1 ? to : te) * M.nC;
-            else col0cost = i == 1 ? to : te;
-        }
+    // per-stripe state, live across macro steps
+    uint32_t i = 0;
+    bool valid = false, last_row = false;
+    int s_o = 0, s_e = 0, s_to = 0, s_te = 0, k_e = 0, k_te = 0, g1o = 0, g1t = 0;
+    long long nongap1 = 0, srgo = 0, srge = 0, srto = 0, srte = 0, col0cost = 0;
+    Cell cur = {kNeg, kNeg, kNeg, 0}, up = {kNeg, kNeg, kNeg, 0};
+    long long t_next = 0;
+    ColInfo c_next = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned char* drow = dirs;
+    const long long* trow = T;
 
-        auto wait_for = [&](uint32_t j) {               // lane 0 only: the producer has parked column j
-            if (NW > 1 && j >= avail) {
-                unsigned v;
-                for (;;) {
-                    v = prog[prod_warp] - prod_base;
-                    if ((int)v >= 0 && v > j) break;
-                    __nanosleep(128);       // do not flood the MIO queue the producer's shuffles go through
+    for (uint32_t m = 0; m < (NW == 1 ? rounds * S : m_end); ++m) {
+        // my stripes start at r*period + team_warp*kLag, r = 0, 1, ...; `off` = local macro step inside the stripe
+        const int rel = (int)m - (int)(team_warp * kLag);
+        const uint32_t r = rel >= 0 ? (uint32_t)rel / period : 0;
+        const int off = rel >= 0 ? (int)((uint32_t)rel - r * period) : -1;
+        const uint32_t k = r * NW + team_warp;
+        const bool mine = off >= 0 && off < (int)S && k < n_stripes;        // warp-uniform
+        if (mine) {
+            if (off == 0) {
+                // ---- new stripe: row-side constants into registers
+                i = k * 32 + 1 + lane;
+                valid = i <= WR;
+                last_row = i == WR;
+                s_o = s_e = s_to = s_te = k_e = k_te = g1o = g1t = 0;
+                nongap1 = srgo = srge = srto = srte = col0cost = 0;
+                if (valid) {
+                    if (VAR == 2) {
+                        const int* rc = M.CR + (size_t)i * 32;
+                        solve_gaps(M.CR, i, WR, M.nR, s_o, s_e, s_to, s_te, k_e, k_te);
+                        g1o = rc[kGO]; g1t = rc[kTO];
+                        for (int q = 0; q < 24; ++q) nongap1 += rc[q];
+                        const long long* sr = M.SR + (size_t)i * 32;
+                        srgo = sr[kGO]; srge = sr[kGE]; srto = sr[kTO]; srte = sr[kTE];
+                        col0cost = (i == 1 ? srto : srte) * M.nC;
+                    } else if (VAR == 1) col0cost = (i == 1 ? to : te) * M.nC;
+                    else col0cost = i == 1 ? to : te;
                 }
-                avail = v;
-                __threadfence_block();
-            }
-        };
-
-        Cell cur = {kNeg, kNeg, kNeg, 0};   // own cell of the previous step (left neighbour)
-        Cell up = {kNeg, kNeg, kNeg, 0};    // cell above of the previous step (becomes the diagonal)
-        // the boundary row arrives in chunks of kChunk columns: L2 -> shared by cp.async, one chunk ahead
-        if (lane == 0) wait_for(min((uint32_t)kChunk - 1, WC));
-        __syncwarp();
-        if (lane < kChunk && lane <= WC) cp_async_cell(&sb[0][lane], brow + lane);
-        cp_async_commit();
-        cp_async_wait_all();
-        __syncwarp();
-        unsigned char* drow = dirs + (size_t)i * ld;
-        const long long* trow = T + (size_t)i * ld;
-        // software pipeline: T and the column record of the next step are already in flight
-        long long t_next = 0;
-        ColInfo c_next = {0, 0, 0, 0, 0, 0, 0, 0};
-        const uint32_t steps = WC + 1 + 31;
-        for (uint32_t s = 0; s < steps; ++s) {
-            // The whole body is executed by all 32 lanes (results are committed under `active`), so the warp
-            // never diverges around the shuffles.
-            const int j = (int)s - (int)lane;               // column handled now
-            const bool active = valid && j >= 0 && j <= (int)WC;
-            const long long t = t_next;
-            const ColInfo ci = c_next;
-            if (valid && j + 1 >= 1 && j + 1 <= (int)WC) {
-                t_next = trow[j + 1];
-                if (VAR != 0) c_next = col[j + 1];
-            }
-            // (i-1, j): lane above computed it one step ago; lane 0 reads the boundary row
-            Cell U;
-            U.D = shfl_up_ll(cur.D); U.H = shfl_up_ll(cur.H); U.V = shfl_up_ll(cur.V);
-            if ((s % kChunk) == 0) {                          // warp-uniform: prefetch the next chunk
-                const uint32_t nb = s + kChunk;
-                if (nb <= WC) {
-                    if (lane == 0) wait_for(min(nb + kChunk - 1, WC));
-                    __syncwarp();
-                    if (lane < kChunk && nb + lane <= WC) cp_async_cell(&sb[((s / kChunk) + 1) & 1][lane], brow + nb + lane);
-                }
+                cur = Cell{kNeg, kNeg, kNeg, 0};
+                up = Cell{kNeg, kNeg, kNeg, 0};
+                t_next = 0;
+                drow = dirs + (size_t)i * ld;
+                trow = T + (size_t)i * ld;
+                // first boundary chunk (columns 0..kChunk-1): nobody could prefetch it for us
+                if (lane < kChunk && lane <= WC) cp_async_cell(&sb[0][lane], brow + lane);
                 cp_async_commit();
             }
-            {
-                const Cell B = sb[(s / kChunk) & 1][s % kChunk];      // broadcast read; only lane 0 keeps it
-                const bool take = lane == 0;
-                U.D = take ? B.D : U.D; U.H = take ? B.H : U.H; U.V = take ? B.V : U.V;
+            // the chunk of this macro step was requested one macro step ago (or just above)
+            cp_async_wait_all();
+            __syncwarp();
+            {   // request the next one: columns (off+1)*kChunk ... have been parked (see kLag)
+                const uint32_t nb = (uint32_t)(off + 1) * kChunk;
+                if (lane < kChunk && nb + lane <= WC) cp_async_cell(&sb[(off + 1) & 1][lane], brow + nb + lane);
+                cp_async_commit();
             }
-            const Cell Pd = up;                              // (i-1, j-1)
-            up = U;
-            if ((s % kChunk) == kChunk - 1) { cp_async_wait_all(); __syncwarp(); }   // next chunk has landed
+            const Cell* chunk = sb[off & 1];
+            const uint32_t s_begin = (uint32_t)off * kChunk;
+#pragma unroll 1
+            for (uint32_t u = 0; u < (uint32_t)kChunk; ++u) {
+                const uint32_t s = s_begin + u;
+                if (s >= steps) break;                                   // warp-uniform
+                // The whole body is executed by all 32 lanes (results are committed under `active`), so the warp
+                // never diverges around the shuffles.
+                const int j = (int)s - (int)lane;                        // column handled now
+                const bool active = valid && j >= 0 && j <= (int)WC;
+                const long long t = t_next;
+                const ColInfo ci = c_next;
+                if (valid && j + 1 >= 1 && j + 1 <= (int)WC) {
+                    t_next = trow[j + 1];
+                    if (VAR != 0) c_next = col[j + 1];
+                }
+                // pull what the next few steps will read into L1 now: every lane streams its own T row (a new
+                // 32-byte sector every 4 steps), lane 0 is the first to touch each column record
+                if (valid && (j & 3) == 0 && j + kPrefetch <= (int)WC) prefetch_l1(trow + j + kPrefetch);
+                if (VAR != 0 && lane == 0 && s + kPrefetch <= WC) prefetch_l1(col + s + kPrefetch);
+                // (i-1, j): the lane above computed it one step ago; lane 0 takes it from the boundary row
+                Cell U;
+                U.D = shfl_up_ll(cur.D); U.H = shfl_up_ll(cur.H); U.V = shfl_up_ll(cur.V);
+                {
+                    const Cell B = chunk[u];                             // broadcast read; only lane 0 keeps it
+                    const bool take = lane == 0;
+                    U.D = take ? B.D : U.D; U.H = take ? B.H : U.H; U.V = take ? B.V : U.V;
+                }
+                const Cell Pd = up;                                      // (i-1, j-1)
+                up = U;
 
-            const Cell L = cur;
-            const bool three = i > 1 && j > 1;
-            Cell out;
-            out.pad = 0;
-            int dD, dH, dV;
-            if (VAR == 0) {
-                // profile_seq.cpp:86-140 (note the >= in the second D test)
-                const bool dw = (Pd.D > Pd.H) & (Pd.D > Pd.V), hw = Pd.H >= Pd.V;
-                out.D = (dw ? Pd.D : (hw ? Pd.H : Pd.V)) + t;
-                dD = dw ? 0 : (hw ? 1 : 2);
-                long long tD = L.D + (!last_row ? go : to);
-                const long long tH = L.H + (!last_row ? ge : te);
-                out.H = tD > tH ? tD : tH; dH = tD > tH ? 0 : 1;
-                tD = U.D + (j < (int)WC ? go : to);
-                const long long tV = U.V + (j < (int)WC ? ge : te);
-                out.V = tD > tV ? tD : tV; dV = tD > tV ? 0 : 2;
-            } else if (VAR == 1) {
-                // profile_par.cpp:255-421
-                dD = pick3(Pd.D, Pd.H, Pd.V + ci.chg, 0, 1, 2, out.D);
-                out.D += t;
-                const long long gcH = !last_row ? ci.cgo : ci.cto;
-                long long tD = L.D + gcH;
-                const long long tH = L.H + (!last_row ? ci.cge : ci.cte);
-                dH = pick3(tD, three ? L.V + gcH : kNever, tH, 0, 2, 1, out.H);
-                tD = U.D + ci.b0;
-                const long long tV = U.V + ci.b1;
-                dV = pick3(tD, three ? U.H + ci.b0 : kNever, tV, 0, 1, 2, out.V);
-            } else {
-                // profile_par.cpp:679-886
-                long long tD = Pd.D + t;
-                long long tH = Pd.H + t;
-                tH += (long long)g1o * (ci.cge - ci.cgo) + (long long)g1t * (ci.cte - ci.cto);   // == 0 when both counts are 0
-                long long tV = Pd.V + t + ci.chg * nongap1;
-                dD = pick3(tD, tH, tV, 0, 1, 2, out.D);
-                const long long gcH = ci.cgo * s_o + ci.cge * s_e + ci.cto * s_to + ci.cte * s_te;
-                tD = L.D + gcH;
-                tH = L.H + ci.cge * k_e + ci.cte * k_te;
-                dH = pick3(tD, three ? L.V + gcH : kNever, tH, 0, 2, 1, out.H);
-                const long long gcV = srgo * lo32(ci.b0) + srge * hi32(ci.b0) + srto * lo32(ci.b1) + srte * hi32(ci.b1);
-                tD = U.D + gcV;
-                tV = U.V + srge * lo32(ci.b2) + srte * hi32(ci.b2);
-                dV = pick3(tD, three ? U.H + gcV : kNever, tV, 0, 1, 2, out.V);
-            }
-            unsigned char db = (unsigned char)(dD | dH << 2 | dV << 4);
-            if (j == 0) {                                   // column 0 (profile_par.cpp:625-640)
-                out.D = kNeg; out.H = kNeg;
-                out.V = last_row ? kNeg : (U.D > U.V ? U.D : U.V) + col0cost;
-                db = 2 | 2 << 2 | 2 << 4;
-            }
-            if (active) {
-                drow[j] = db;
-                cur = out;
-                if (last_row) {
-                    if (j == (int)WC) { last_out[0] = out.D; last_out[1] = out.H; last_out[2] = out.V; }
-                } else if (lane == 31) {
-                    // park the stripe's last row for the next stripe; publish once per chunk
-                    store_cell(brow + j, out);
-                    if (NW > 1 && ((j % kChunk) == kChunk - 1 || j == (int)WC)) {
-                        __threadfence_block();
-                        prog[team_warp] = my_base + (unsigned)j + 1;
+                const Cell L = cur;
+                const bool three = i > 1 && j > 1;
+                Cell out;
+                out.pad = 0;
+                int dD, dH, dV;
+                if (VAR == 0) {
+                    // profile_seq.cpp:86-140 (note the >= in the second D test)
+                    const bool dw = (Pd.D > Pd.H) & (Pd.D > Pd.V), hw = Pd.H >= Pd.V;
+                    out.D = (dw ? Pd.D : (hw ? Pd.H : Pd.V)) + t;
+                    dD = dw ? 0 : (hw ? 1 : 2);
+                    long long tD = L.D + (!last_row ? go : to);
+                    const long long tH = L.H + (!last_row ? ge : te);
+                    out.H = tD > tH ? tD : tH; dH = tD > tH ? 0 : 1;
+                    tD = U.D + (j < (int)WC ? go : to);
+                    const long long tV = U.V + (j < (int)WC ? ge : te);
+                    out.V = tD > tV ? tD : tV; dV = tD > tV ? 0 : 2;
+                } else if (VAR == 1) {
+                    // profile_par.cpp:255-421
+                    dD = pick3(Pd.D, Pd.H, Pd.V + ci.chg, 0, 1, 2, out.D);
+                    out.D += t;
+                    const long long gcH = !last_row ? ci.cgo : ci.cto;
+                    long long tD = L.D + gcH;
+                    const long long tH = L.H + (!last_row ? ci.cge : ci.cte);
+                    dH = pick3(tD, three ? L.V + gcH : kNever, tH, 0, 2, 1, out.H);
+                    tD = U.D + ci.b0;
+                    const long long tV = U.V + ci.b1;
+                    dV = pick3(tD, three ? U.H + ci.b0 : kNever, tV, 0, 1, 2, out.V);
+                } else {
+                    // profile_par.cpp:679-886
+                    long long tD = Pd.D + t;
+                    long long tH = Pd.H + t;
+                    tH += (long long)g1o * (ci.cge - ci.cgo) + (long long)g1t * (ci.cte - ci.cto);   // == 0 when both counts are 0
+                    long long tV = Pd.V + t + ci.chg * nongap1;
+                    dD = pick3(tD, tH, tV, 0, 1, 2, out.D);
+                    const long long gcH = ci.cgo * s_o + ci.cge * s_e + ci.cto * s_to + ci.cte * s_te;
+                    tD = L.D + gcH;
+                    tH = L.H + ci.cge * k_e + ci.cte * k_te;
+                    dH = pick3(tD, three ? L.V + gcH : kNever, tH, 0, 2, 1, out.H);
+                    const long long gcV = srgo * lo32(ci.b0) + srge * hi32(ci.b0) + srto * lo32(ci.b1) + srte * hi32(ci.b1);
+                    tD = U.D + gcV;
+                    tV = U.V + srge * lo32(ci.b2) + srte * hi32(ci.b2);
+                    dV = pick3(tD, three ? U.H + gcV : kNever, tV, 0, 1, 2, out.V);
+                }
+                unsigned char db = (unsigned char)(dD | dH << 2 | dV << 4);
+                if (j == 0) {                                            // column 0 (profile_par.cpp:625-640)
+                    out.D = kNeg; out.H = kNeg;
+                    out.V = last_row ? kNeg : (U.D > U.V ? U.D : U.V) + col0cost;
+                    db = 2 | 2 << 2 | 2 << 4;
+                }
+                if (active) {
+                    drow[j] = db;
+                    cur = out;
+                    if (last_row) {
+                        if (j == (int)WC) { last_out[0] = out.D; last_out[1] = out.H; last_out[2] = out.V; }
+                    } else if (lane == 31) {
+                        store_cell(brow + j, out);                       // park the stripe's last row (L2)
                     }
                 }
             }
         }
-        __syncwarp();
+        if (NW > 1) __syncthreads();        // hand-over point: parked columns become visible to the next stripe
+        else __syncwarp();
     }
 }
 
@@ -487,7 +498,6 @@ template <int NW>
 __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_fill(const DpParams P)
 {
     constexpr int kBlockWarps = NW == 1 ? kDpWarps : NW;
-    __shared__ unsigned sm_prog[kBlockWarps];
     __shared__ long long sm_last[kBlockWarps][3];
     __shared__ __align__(16) Cell sm_brow[kBlockWarps][2][kChunk];
     const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -498,8 +508,6 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_fill(cons
     const uint32_t jid = P.order[slot];
     const DpJobDev J = P.jobs[jid];
     const DpMeta M = P.meta[jid];
-    if (threadIdx.x < kBlockWarps) sm_prog[threadIdx.x] = 0;
-    team_sync();
 
     const Scratch L(J.w1, J.w2);
     unsigned char* scratch = P.scratch + J.scratch_off;
@@ -512,9 +520,9 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_fill(cons
     const size_t ld = (size_t)WC + 1;
 
     long long* last_out = sm_last[warp];
-    if (M.var == 0) dp_stripes<0, NW>(P, M, T, col, brow, dirs, sm_prog, team_warp, last_out, sm_brow[warp]);
-    else if (M.var == 1) dp_stripes<1, NW>(P, M, T, col, brow, dirs, sm_prog, team_warp, last_out, sm_brow[warp]);
-    else dp_stripes<2, NW>(P, M, T, col, brow, dirs, sm_prog, team_warp, last_out, sm_brow[warp]);
+    if (M.var == 0) dp_stripes<0, NW>(P, M, T, col, brow, dirs, team_warp, last_out, sm_brow[warp]);
+    else if (M.var == 1) dp_stripes<1, NW>(P, M, T, col, brow, dirs, team_warp, last_out, sm_brow[warp]);
+    else dp_stripes<2, NW>(P, M, T, col, brow, dirs, team_warp, last_out, sm_brow[warp]);
     __threadfence_block();
     team_sync();
     if (team_warp != 0) return;
@@ -643,7 +651,14 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
     }
     // `order` has the team-kernel jobs first (see the sort above)
     if (n_big) {
-        k_dp_fill<kDpTeamWarps><<<n_big, kDpTeamWarps * 32, 0, st>>>(P);
+        int nw = kDpTeamWarps;
+        if (const char* e = getenv("FAMSA_DP_TEAM_WARPS")) nw = atoi(e);           // development knob
+        switch (nw) {
+        case 2: k_dp_fill<2><<<n_big, 2 * 32, 0, st>>>(P); break;
+        case 4: k_dp_fill<4><<<n_big, 4 * 32, 0, st>>>(P); break;
+        case 16: k_dp_fill<16><<<n_big, 16 * 32, 0, st>>>(P); break;
+        default: k_dp_fill<kDpTeamWarps><<<n_big, kDpTeamWarps * 32, 0, st>>>(P); break;
+        }
         FB_CUDA(cudaGetLastError());
         ctx->launches++;
     }
@@ -677,11 +692,19 @@ int dp_run_host(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int6
         path_total += (unsigned long long)j.p1.width + j.p2.width;
         dirs_total += ((unsigned long long)j.p1.width + 1) * (j.p2.width + 1);
     }
-    S.h_stage.resize(bytes);
+    // pinned staging buffer; tables are packed and shipped in ~8 MB slices so that packing slice k+1 overlaps the
+    // H2D of slice k
+    if (bytes > S.h_pinned_cap) {
+        if (S.h_pinned) cudaFreeHost(S.h_pinned);
+        S.h_pinned = nullptr;
+        S.h_pinned_cap = 0;
+        FB_CUDA(cudaHostAlloc(&S.h_pinned, bytes + bytes / 4 + 4096, cudaHostAllocDefault));
+        S.h_pinned_cap = bytes + bytes / 4 + 4096;
+    }
     FB_TRY(S.d_tables.reserve(std::max<unsigned long long>(bytes, 64)));
     std::vector<famsa_dp_job> dj(jobs, jobs + n);
-    unsigned long long at = 0;
-    uint8_t* hb = S.h_stage.data();
+    unsigned long long at = 0, shipped = 0;
+    uint8_t* hb = static_cast<uint8_t*>(S.h_pinned);
     uint8_t* db = S.d_tables.as<uint8_t>();
     auto put = [&](const void* src, size_t sz) { memcpy(hb + at, src, sz); void* d = db + at; at += sz; return d; };
     for (uint32_t k = 0; k < n; ++k) {      // every table size is a multiple of 128 bytes, so alignment is kept
@@ -690,6 +713,10 @@ int dp_run_host(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int6
         j.p2.scores = static_cast<const int64_t*>(put(jobs[k].p2.scores, ((size_t)jobs[k].p2.width + 1) * 32 * 8));
         j.p1.counters = static_cast<const int32_t*>(put(jobs[k].p1.counters, ((size_t)jobs[k].p1.width + 1) * 32 * 4));
         j.p2.counters = static_cast<const int32_t*>(put(jobs[k].p2.counters, ((size_t)jobs[k].p2.width + 1) * 32 * 4));
+        if (at - shipped >= (8u << 20) || k + 1 == n) {
+            FB_CUDA(cudaMemcpyAsync(db + shipped, hb + shipped, at - shipped, cudaMemcpyHostToDevice, st));
+            shipped = at;
+        }
     }
     FB_TRY(S.d_results.reserve(sizeof(famsa_dp_result) * std::max(1u, n)));
     FB_TRY(S.d_path.reserve(std::max<unsigned long long>(path_total, 64)));
@@ -698,7 +725,6 @@ int dp_run_host(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int6
         FB_TRY(S.d_dirs.reserve(std::max<unsigned long long>(dirs_total, 64)));
         d_dirs = S.d_dirs.as<uint8_t>();
     }
-    if (bytes) FB_CUDA(cudaMemcpyAsync(db, hb, bytes, cudaMemcpyHostToDevice, st));
     FB_TRY(dp_run_device(ctx, dj.data(), n, gaps, S.d_results.as<famsa_dp_result>(), S.d_path.as<uint8_t>(), d_dirs, st));
     if (n) FB_CUDA(cudaMemcpyAsync(results, S.d_results.p, sizeof(famsa_dp_result) * n, cudaMemcpyDeviceToHost, st));
     if (path_total) FB_CUDA(cudaMemcpyAsync(path_buf, S.d_path.p, path_total, cudaMemcpyDeviceToHost, st));

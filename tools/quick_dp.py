@@ -16,8 +16,7 @@ def bench(name, seqs, merges, rescale=None):
         t = time.time(); res = eng.dp_align_batch(jobs, g); wall = time.time() - t
         tot, kern, c = eng.dp_last_timing()
     ok = all(r["total"] == rec["total"] for r, rec in zip(res, recs))
-    print(f"{name}: {len(jobs)} merges, {cells/1e6:.1f} Mcells; ref CPU 1 thread (incl ConstructProfile + harness) {tref:.2f}s = {cells/tref/1e6:.1f} Mcells/s; "
-          f"GPU kernel {kern:.2f} ms = {cells/kern/1e3:.1f} Mcells/s, e2e wall {wall*1e3:.1f} ms = {cells/wall/1e6:.1f} Mcells/s, totals ok={ok}")
+    print(f"{name}: {len(jobs)} merges {cells/1e6:.1f} Mcells | kernel {kern:.2f} ms = {cells/kern/1e3:.0f} Mc/s | e2e {wall*1e3:.1f} ms = {cells/wall/1e6:.0f} Mc/s | ok={ok}")
 
 z = np.load(os.path.join(ROOT, "tests/golden/hemopexin_medoid_sl.npz"))
 bench("hemopexin C4 (one batch)", [str(s) for s in z["seqs"]], [tuple(int(x) for x in m) for m in z["merges"]])
