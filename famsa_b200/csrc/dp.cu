@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include "ctx.h"
 
@@ -163,7 +164,8 @@ struct DpParams {
     const DpJobDev* jobs;
     DpMeta* meta;
     const uint32_t* order;        // launch slot -> job index
-    uint32_t n_jobs;
+    uint32_t n_jobs;              // jobs of this launch (a sub-batch, or one fill class of it)
+    uint32_t job_base;            // first job id of the sub-batch (k_dp_prep / k_dp_t index jobs as job_base + x)
     long long go, ge, to, te;
     unsigned char* dirs;          // all direction matrices
     unsigned char* path;          // all paths (forward order)
@@ -179,7 +181,7 @@ struct DpParams {
 __global__ void __launch_bounds__(128) k_dp_prep(const DpParams P)
 {
     __shared__ unsigned long long sm_nz[2];
-    const uint32_t jid = blockIdx.x;
+    const uint32_t jid = P.job_base + blockIdx.x;
     const DpJobDev J = P.jobs[jid];
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
     if (tid < 2) sm_nz[tid] = 0;
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(kTThreads) k_dp_t(const DpParams P)
         const uint32_t mid = (lo + hi) / 2;
         if (P.tblock[mid] <= b) lo = mid; else hi = mid;
     }
-    const uint32_t jid = lo;
+    const uint32_t jid = P.job_base + lo;
     const DpJobDev J = P.jobs[jid];
     const DpMeta M = P.meta[jid];
     const Scratch L(J.w1, J.w2);
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(kTThreads) k_dp_t(const DpParams P)
     long long* T = P.T + J.t_off;
     const size_t ldc = (size_t)M.WC + 1;
     const size_t cells = ((size_t)M.WR + 1) * ldc;
-    const size_t base = (size_t)(b - P.tblock[jid]) * kTThreads * kTCellsPerThread;
+    const size_t base = (size_t)(b - P.tblock[lo]) * kTThreads * kTCellsPerThread;
 #pragma unroll
     for (int u = 0; u < kTCellsPerThread; ++u) {
         const size_t c = base + (size_t)u * kTThreads + threadIdx.x;
@@ -579,9 +581,7 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
 {
     DpState& S = ctx->dp;
     std::vector<DpJobDev> dev(n);
-    std::vector<uint32_t> order(n);
-    std::vector<unsigned long long> tblock(n + 1, 0);
-    unsigned long long path_off = 0, dirs_off = 0, scratch_off = 0, cells = 0;
+    unsigned long long path_off = 0, dirs_off = 0, cells = 0;
     for (uint32_t k = 0; k < n; ++k) {
         const famsa_dp_job& j = jobs[k];
         if (j.p1.width == 0 || j.p2.width == 0 || j.p1.card == 0 || j.p2.card == 0) {
@@ -592,83 +592,109 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
         d.s1 = reinterpret_cast<const long long*>(j.p1.scores); d.c1 = j.p1.counters;
         d.s2 = reinterpret_cast<const long long*>(j.p2.scores); d.c2 = j.p2.counters;
         d.w1 = j.p1.width; d.card1 = j.p1.card; d.w2 = j.p2.width; d.card2 = j.p2.card;
-        d.path_off = path_off; d.dirs_off = dirs_off; d.scratch_off = scratch_off; d.t_off = dirs_off;
-        const unsigned long long mat = ((unsigned long long)d.w1 + 1) * (d.w2 + 1);
+        d.path_off = path_off; d.dirs_off = dirs_off;           // caller-visible layout: global prefix sums
         path_off += (unsigned long long)d.w1 + d.w2;
-        dirs_off += mat;
-        scratch_off += Scratch(d.w1, d.w2).total;
-        tblock[k + 1] = tblock[k] + (mat + kTThreads * kTCellsPerThread - 1) / (kTThreads * kTCellsPerThread);
+        dirs_off += ((unsigned long long)d.w1 + 1) * (d.w2 + 1);
         cells += (unsigned long long)d.w1 * d.w2;
     }
-    if (tblock[n] > 0x7fffffffull) { set_error("dp batch too large for one launch; split it"); return FAMSA_E_INVALID; }
-    // merges whose shorter side spans several 32-row stripes get a whole block (kDpTeamWarps warps pipelined
-    // over the stripes); the rest run one warp per merge.  Both groups cost-descending.
-    uint32_t team_min = kDpTeamMinWidth;
-    if (const char* e = getenv("FAMSA_DP_TEAM_MIN")) team_min = (uint32_t)atoi(e);   // development knob
-    auto big = [&](uint32_t a) { return std::min(dev[a].w1, dev[a].w2) > team_min; };
-    std::iota(order.begin(), order.end(), 0u);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-        if (big(a) != big(b)) return big(a);
-        return (unsigned long long)dev[a].w1 * dev[a].w2 > (unsigned long long)dev[b].w1 * dev[b].w2;
-    });
-    uint32_t n_big = 0;
-    while (n_big < n && big(order[n_big])) ++n_big;
     S.last_cells = cells;
-    FB_TRY(S.d_jobs.reserve(sizeof(DpJobDev) * std::max(1u, n)));
-    FB_TRY(S.d_meta.reserve(sizeof(DpMeta) * std::max(1u, n)));
-    FB_TRY(S.d_order.reserve(sizeof(uint32_t) * std::max(1u, n)));
-    FB_TRY(S.d_tblock.reserve(sizeof(unsigned long long) * (n + 1)));
-    FB_TRY(S.d_scratch.reserve(std::max<unsigned long long>(scratch_off, 64)));
-    FB_TRY(S.d_T.reserve(std::max<unsigned long long>(dirs_off * 8, 64)));
-    uint8_t* dirs = d_dirs;
-    if (!dirs) {
-        FB_TRY(S.d_dirs.reserve(std::max<unsigned long long>(dirs_off, 64)));
-        dirs = S.d_dirs.as<uint8_t>();
-    }
+    // Sub-batches of consecutive jobs bound the device scratch (T is 8 bytes per cell): ~1 Gi cells each.
+    unsigned long long max_cells = 1ull << 30;
+    if (const char* e = getenv("FAMSA_DP_MAX_CELLS")) max_cells = strtoull(e, nullptr, 10);     // development knob
+    uint32_t team_min = kDpTeamMinWidth;
+    if (const char* e = getenv("FAMSA_DP_TEAM_MIN")) team_min = (uint32_t)atoi(e);               // development knob
+    int nw = kDpTeamWarps;
+    if (const char* e = getenv("FAMSA_DP_TEAM_WARPS")) nw = atoi(e);                             // development knob
+
     FB_CUDA(cudaEventRecord(ctx->ev[0], st));
-    FB_CUDA(cudaMemcpyAsync(S.d_jobs.p, dev.data(), sizeof(DpJobDev) * n, cudaMemcpyHostToDevice, st));
-    FB_CUDA(cudaMemcpyAsync(S.d_order.p, order.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
-    FB_CUDA(cudaMemcpyAsync(S.d_tblock.p, tblock.data(), sizeof(unsigned long long) * (n + 1), cudaMemcpyHostToDevice, st));
-    DpParams P{};
-    P.jobs = S.d_jobs.as<DpJobDev>();
-    P.meta = S.d_meta.as<DpMeta>();
-    P.order = S.d_order.as<uint32_t>();
-    P.n_jobs = n;
-    P.go = gaps[0]; P.ge = gaps[1]; P.to = gaps[2]; P.te = gaps[3];
-    P.dirs = dirs;
-    P.path = d_path;
-    P.scratch = S.d_scratch.as<uint8_t>();
-    P.T = S.d_T.as<long long>();
-    P.tblock = S.d_tblock.as<unsigned long long>();
-    P.results = d_results;
     FB_CUDA(cudaEventRecord(ctx->ev[1], st));
-    if (n) {
-        k_dp_prep<<<n, 128, 0, st>>>(P);
+    for (uint32_t j0 = 0; j0 < n;) {
+        // [j0, j1): as many consecutive jobs as fit
+        uint32_t j1 = j0;
+        unsigned long long mat_sum = 0, scratch_off = 0, t_off = 0;
+        std::vector<unsigned long long> tblock(1, 0);
+        while (j1 < n) {
+            const unsigned long long mat = ((unsigned long long)dev[j1].w1 + 1) * (dev[j1].w2 + 1);
+            if (j1 > j0 && mat_sum + mat > max_cells) break;
+            dev[j1].scratch_off = scratch_off;
+            dev[j1].t_off = t_off;
+            if (!d_dirs) dev[j1].dirs_off = t_off;              // internal direction matrices are per sub-batch
+            scratch_off += Scratch(dev[j1].w1, dev[j1].w2).total;
+            t_off += mat;
+            mat_sum += mat;
+            tblock.push_back(tblock.back() + (mat + kTThreads * kTCellsPerThread - 1) / (kTThreads * kTCellsPerThread));
+            ++j1;
+        }
+        const uint32_t m = j1 - j0;
+        if (tblock[m] > 0x7fffffffull) { set_error("dp sub-batch too large for one launch"); return FAMSA_E_INVALID; }
+        // merges whose shorter side spans several 32-row stripes get a whole block (a team of warps pipelined over
+        // the stripes); the rest run one warp per merge.  Both groups cost-descending.
+        auto big = [&](uint32_t a) { return std::min(dev[a].w1, dev[a].w2) > team_min; };
+        std::vector<uint32_t> order(m);
+        std::iota(order.begin(), order.end(), j0);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            if (big(a) != big(b)) return big(a);
+            return (unsigned long long)dev[a].w1 * dev[a].w2 > (unsigned long long)dev[b].w1 * dev[b].w2;
+        });
+        uint32_t n_big = 0;
+        while (n_big < m && big(order[n_big])) ++n_big;
+
+        FB_TRY(S.d_jobs.reserve(sizeof(DpJobDev) * n));
+        FB_TRY(S.d_meta.reserve(sizeof(DpMeta) * n));
+        FB_TRY(S.d_order.reserve(sizeof(uint32_t) * m));
+        FB_TRY(S.d_tblock.reserve(sizeof(unsigned long long) * (m + 1)));
+        FB_TRY(S.d_scratch.reserve(std::max<unsigned long long>(scratch_off, 64)));
+        FB_TRY(S.d_T.reserve(std::max<unsigned long long>(t_off * 8, 64)));
+        uint8_t* dirs = d_dirs;
+        if (!dirs) {
+            FB_TRY(S.d_dirs.reserve(std::max<unsigned long long>(t_off, 64)));
+            dirs = S.d_dirs.as<uint8_t>();
+        }
+        FB_CUDA(cudaMemcpyAsync(S.d_jobs.as<DpJobDev>() + j0, dev.data() + j0, sizeof(DpJobDev) * m, cudaMemcpyHostToDevice, st));
+        FB_CUDA(cudaMemcpyAsync(S.d_order.p, order.data(), sizeof(uint32_t) * m, cudaMemcpyHostToDevice, st));
+        FB_CUDA(cudaMemcpyAsync(S.d_tblock.p, tblock.data(), sizeof(unsigned long long) * (m + 1), cudaMemcpyHostToDevice, st));
+        DpParams P{};
+        P.jobs = S.d_jobs.as<DpJobDev>();
+        P.meta = S.d_meta.as<DpMeta>();
+        P.order = S.d_order.as<uint32_t>();
+        P.n_jobs = m;
+        P.job_base = j0;
+        P.go = gaps[0]; P.ge = gaps[1]; P.to = gaps[2]; P.te = gaps[3];
+        P.dirs = dirs;
+        P.path = d_path;
+        P.scratch = S.d_scratch.as<uint8_t>();
+        P.T = S.d_T.as<long long>();
+        P.tblock = S.d_tblock.as<unsigned long long>();
+        P.results = d_results;
+        k_dp_prep<<<m, 128, 0, st>>>(P);
         FB_CUDA(cudaGetLastError());
-        k_dp_t<<<(unsigned)tblock[n], kTThreads, 0, st>>>(P);
+        k_dp_t<<<(unsigned)tblock[m], kTThreads, 0, st>>>(P);
         FB_CUDA(cudaGetLastError());
         ctx->launches += 2;
-    }
-    // `order` has the team-kernel jobs first (see the sort above)
-    if (n_big) {
-        int nw = kDpTeamWarps;
-        if (const char* e = getenv("FAMSA_DP_TEAM_WARPS")) nw = atoi(e);           // development knob
-        switch (nw) {
-        case 2: k_dp_fill<2><<<n_big, 2 * 32, 0, st>>>(P); break;
-        case 4: k_dp_fill<4><<<n_big, 4 * 32, 0, st>>>(P); break;
-        case 16: k_dp_fill<16><<<n_big, 16 * 32, 0, st>>>(P); break;
-        default: k_dp_fill<kDpTeamWarps><<<n_big, kDpTeamWarps * 32, 0, st>>>(P); break;
+        // `order` has the team-kernel jobs first (see the sort above)
+        if (n_big) {
+            DpParams Q = P;
+            Q.n_jobs = n_big;
+            switch (nw) {
+            case 2: k_dp_fill<2><<<n_big, 2 * 32, 0, st>>>(Q); break;
+            case 4: k_dp_fill<4><<<n_big, 4 * 32, 0, st>>>(Q); break;
+            case 16: k_dp_fill<16><<<n_big, 16 * 32, 0, st>>>(Q); break;
+            default: k_dp_fill<kDpTeamWarps><<<n_big, kDpTeamWarps * 32, 0, st>>>(Q); break;
+            }
+            FB_CUDA(cudaGetLastError());
+            ctx->launches++;
         }
-        FB_CUDA(cudaGetLastError());
-        ctx->launches++;
-    }
-    if (n > n_big) {
-        DpParams Q = P;
-        Q.order = P.order + n_big;
-        Q.n_jobs = n - n_big;
-        k_dp_fill<1><<<(Q.n_jobs + kDpWarps - 1) / kDpWarps, kDpWarps * 32, 0, st>>>(Q);
-        FB_CUDA(cudaGetLastError());
-        ctx->launches++;
+        if (m > n_big) {
+            DpParams Q = P;
+            Q.order = P.order + n_big;
+            Q.n_jobs = m - n_big;
+            k_dp_fill<1><<<(Q.n_jobs + kDpWarps - 1) / kDpWarps, kDpWarps * 32, 0, st>>>(Q);
+            FB_CUDA(cudaGetLastError());
+            ctx->launches++;
+        }
+        // the next sub-batch reuses the scratch: the reserve() calls above may also free+reallocate, and
+        // cudaFree synchronises, so nothing is released while kernels still read it
+        j0 = j1;
     }
     FB_CUDA(cudaEventRecord(ctx->ev[2], st));
     FB_CUDA(cudaEventRecord(ctx->ev[3], st));
@@ -706,18 +732,46 @@ int dp_run_host(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int6
     unsigned long long at = 0, shipped = 0;
     uint8_t* hb = static_cast<uint8_t*>(S.h_pinned);
     uint8_t* db = S.d_tables.as<uint8_t>();
-    auto put = [&](const void* src, size_t sz) { memcpy(hb + at, src, sz); void* d = db + at; at += sz; return d; };
+    // device addresses first (cheap), then the copies: the staging buffer is filled by a few host threads, each
+    // shipping its own contiguous slice as soon as it is packed
+    std::vector<unsigned long long> job_at(n + 1, 0);
     for (uint32_t k = 0; k < n; ++k) {      // every table size is a multiple of 128 bytes, so alignment is kept
         famsa_dp_job& j = dj[k];
-        j.p1.scores = static_cast<const int64_t*>(put(jobs[k].p1.scores, ((size_t)jobs[k].p1.width + 1) * 32 * 8));
-        j.p2.scores = static_cast<const int64_t*>(put(jobs[k].p2.scores, ((size_t)jobs[k].p2.width + 1) * 32 * 8));
-        j.p1.counters = static_cast<const int32_t*>(put(jobs[k].p1.counters, ((size_t)jobs[k].p1.width + 1) * 32 * 4));
-        j.p2.counters = static_cast<const int32_t*>(put(jobs[k].p2.counters, ((size_t)jobs[k].p2.width + 1) * 32 * 4));
-        if (at - shipped >= (8u << 20) || k + 1 == n) {
-            FB_CUDA(cudaMemcpyAsync(db + shipped, hb + shipped, at - shipped, cudaMemcpyHostToDevice, st));
-            shipped = at;
-        }
+        const size_t s1 = ((size_t)jobs[k].p1.width + 1) * 32 * 8, s2 = ((size_t)jobs[k].p2.width + 1) * 32 * 8;
+        j.p1.scores = reinterpret_cast<const int64_t*>(db + at);
+        j.p2.scores = reinterpret_cast<const int64_t*>(db + at + s1);
+        j.p1.counters = reinterpret_cast<const int32_t*>(db + at + s1 + s2);
+        j.p2.counters = reinterpret_cast<const int32_t*>(db + at + s1 + s2 + s1 / 2);
+        at += (s1 + s2) * 3 / 2;
+        job_at[k + 1] = at;
     }
+    {
+        const unsigned n_thr = bytes > (16u << 20) ? 4 : 1;
+        std::vector<std::thread> workers;
+        std::vector<cudaError_t> errs(n_thr, cudaSuccess);
+        for (unsigned t = 0; t < n_thr; ++t)
+            workers.emplace_back([&, t] {
+                cudaSetDevice(ctx->device);
+                const uint32_t k0 = (uint32_t)((unsigned long long)n * t / n_thr), k1 = (uint32_t)((unsigned long long)n * (t + 1) / n_thr);
+                unsigned long long sent = job_at[k0];
+                for (uint32_t k = k0; k < k1; ++k) {
+                    const size_t s1 = ((size_t)jobs[k].p1.width + 1) * 32 * 8, s2 = ((size_t)jobs[k].p2.width + 1) * 32 * 8;
+                    uint8_t* h = hb + job_at[k];
+                    memcpy(h, jobs[k].p1.scores, s1);
+                    memcpy(h + s1, jobs[k].p2.scores, s2);
+                    memcpy(h + s1 + s2, jobs[k].p1.counters, s1 / 2);
+                    memcpy(h + s1 + s2 + s1 / 2, jobs[k].p2.counters, s2 / 2);
+                    if (job_at[k + 1] - sent >= (8u << 20) || k + 1 == k1) {
+                        cudaError_t e = cudaMemcpyAsync(db + sent, hb + sent, job_at[k + 1] - sent, cudaMemcpyHostToDevice, st);
+                        if (e != cudaSuccess) errs[t] = e;
+                        sent = job_at[k + 1];
+                    }
+                }
+            });
+        for (auto& w : workers) w.join();
+        for (cudaError_t e : errs) FB_CUDA(e);
+    }
+    (void)shipped;
     FB_TRY(S.d_results.reserve(sizeof(famsa_dp_result) * std::max(1u, n)));
     FB_TRY(S.d_path.reserve(std::max<unsigned long long>(path_total, 64)));
     uint8_t* d_dirs = nullptr;

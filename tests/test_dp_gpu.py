@@ -48,6 +48,22 @@ def test_all_merges_of_golden_upgma_tree(engine):
 
 
 @needs_ref
+@pytest.mark.parametrize("want_dirs", [False, True])
+def test_sub_batching(engine, monkeypatch, want_dirs):
+    """Large batches are cut into sub-batches that bound the device scratch; force tiny ones."""
+    z = np.load(os.path.join(GOLDEN, "adeno_upgma_merges.npz"))
+    seqs = [str(s) for s in z["seqs"]]
+    merges = [tuple(int(x) for x in m) for m in z["merges"]]
+    g, recs = reference_merges(seqs, merges, threads=(1,))
+    monkeypatch.setenv("FAMSA_DP_MAX_CELLS", "60000")
+    got = engine.dp_align_batch([r["job"] for r in recs], g, want_dirs=want_dirs)
+    check_against_reference(got, recs)
+    if want_dirs:
+        for r, rec in zip(got[::17], recs[::17]):
+            assert np.array_equal(r["dirs"], pyoracle.dp_align(*rec["job"], g)["dirs"])
+
+
+@needs_ref
 def test_hemopexin_all_merges(engine):
     """BASELINE config 4: all 4187 guide-tree merges of test/hemopexin (medoid-sl tree) on one B200, level by
     level the way a host scheduler would submit them; totals and path CRCs pinned by the fixture, which was
