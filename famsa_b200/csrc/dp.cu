@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kTThreads) k_dp_t(const DpParams P)
     for (int u = 0; u < kTCellsPerThread; ++u) {
         const size_t c = base + (size_t)u * kTThreads + threadIdx.x;
         if (c >= cells) break;
-        const uint32_t i = (uint32_t)(c / ldc), j = (uint32_t)(c % ldc);
+        const uint32_t i = (uint32_t)c / (uint32_t)ldc, j = (uint32_t)c - i * (uint32_t)ldc;   // cells < 2^32 per merge
         long long t = 0;
         if (i >= 1 && j >= 1) {
             const RowNz* r = rownz + i;
@@ -502,6 +502,7 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_fill(cons
     constexpr int kBlockWarps = NW == 1 ? kDpWarps : NW;
     __shared__ long long sm_last[kBlockWarps][3];
     __shared__ __align__(16) Cell sm_brow[kBlockWarps][2][kChunk];
+    __shared__ unsigned char sm_tile[NW == 1 ? kDpWarps : 1][32 * 32];
     const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const uint32_t team_warp = NW == 1 ? 0 : warp;
     const uint32_t slot = NW == 1 ? blockIdx.x * kDpWarps + warp : blockIdx.x;
@@ -533,21 +534,47 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_fill(cons
     const uint32_t owner_warp = NW == 1 ? warp : ((WR + 31) / 32 - 1) % NW;
     const long long last[3] = {sm_last[owner_warp][0], sm_last[owner_warp][1], sm_last[owner_warp][2]};
 
-    // ---- traceback (ConstructProfile, profile.cpp:727-775), lane 0 walks, the warp reverses
+    // ---- traceback (ConstructProfile, profile.cpp:727-775).  The warp fetches the 32 x 32 corner of the direction
+    // matrix that ends at the current cell into shared memory (32 independent byte loads per lane instead of one
+    // dependent L2 round trip per path step), lane 0 walks inside the tile, repeat.
     uint32_t n = 0;
     long long total = 0;
-    if (lane == 0) {
+    {
+        unsigned char* tile = sm_tile[NW == 1 ? warp : 0];
         int dir;
         if (last[0] >= last[1] && last[0] >= last[2]) { dir = 0; total = last[0]; }
         else if (last[1] > last[2]) { dir = 1; total = last[1]; }
         else { dir = 2; total = last[2]; }
-        size_t i = WR, j = WC;
-        while (i || j) {
-            tmp_path[n++] = (unsigned char)dir;
-            const unsigned char b = __ldcg(dirs + i * ld + j);
-            if (dir == 0) { dir = b & 3; --i; --j; }
-            else if (dir == 1) { dir = (b >> 2) & 3; --j; }
-            else { dir = (b >> 4) & 3; --i; }
+        uint32_t ti = WR, tj = WC;
+        while (ti || tj) {
+            const uint32_t i0 = ti >= 31 ? ti - 31 : 0, j0 = tj >= 31 ? tj - 31 : 0;
+            if (ti >= lane && ti - lane >= i0) {
+                const unsigned char* src = dirs + (size_t)(ti - lane) * ld + j0;
+                const uint32_t w = tj - j0 + 1;
+#pragma unroll
+                for (uint32_t c = 0; c < 32; ++c)
+                    if (c < w) tile[lane * 32 + c] = __ldcg(src + c);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                uint32_t ii = ti, jj = tj;
+                while ((ii || jj) && ii >= i0 && jj >= j0) {
+                    tmp_path[n++] = (unsigned char)dir;
+                    const unsigned char b = tile[(ti - ii) * 32 + (jj - j0)];
+                    if (dir == 0) {
+                        dir = b & 3;
+                        if (ii == 0 || jj == 0) { ii = jj = 0; break; }      // cannot happen for a valid matrix
+                        --ii; --jj;
+                    } else if (dir == 1) { dir = (b >> 2) & 3; --jj; }
+                    else { dir = (b >> 4) & 3; --ii; }
+                    if ((int)ii < (int)i0 || (int)jj < (int)j0) break;
+                }
+                ti = ii; tj = jj;
+            }
+            ti = __shfl_sync(0xffffffffu, ti, 0);
+            tj = __shfl_sync(0xffffffffu, tj, 0);
+            dir = __shfl_sync(0xffffffffu, dir, 0);
+            __syncwarp();
         }
     }
     n = __shfl_sync(0xffffffffu, n, 0);
@@ -586,6 +613,10 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
         const famsa_dp_job& j = jobs[k];
         if (j.p1.width == 0 || j.p2.width == 0 || j.p1.card == 0 || j.p2.card == 0) {
             set_error("dp job " + std::to_string(k) + ": empty profile");
+            return FAMSA_E_INVALID;
+        }
+        if (((unsigned long long)j.p1.width + 1) * (j.p2.width + 1) > 0xffffffffull) {
+            set_error("dp job " + std::to_string(k) + ": more than 2^32 matrix cells");
             return FAMSA_E_INVALID;
         }
         DpJobDev& d = dev[k];
