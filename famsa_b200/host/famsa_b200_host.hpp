@@ -161,4 +161,20 @@ inline std::vector<AlignResult> AlignBatch(Context& ctx, const std::vector<famsa
     return out;
 }
 
+// Level-synchronous order of the guide tree's merges (replaces CProfileQueue's one-at-a-time hand-out,
+// queues.cpp:17-187): tree = the reference's tree_structure, n leaves then internal nodes (left, right).
+// Returns, per level, the indices (into the internal-node part) of the merges whose children are finished.
+inline std::vector<std::vector<uint32_t>> ReadyLevels(const std::vector<std::pair<int, int>>& tree, uint32_t n_leaves)
+{
+    std::vector<uint32_t> depth(tree.size(), 0);
+    std::vector<std::vector<uint32_t>> levels;
+    for (uint32_t node = n_leaves; node < tree.size(); ++node) {
+        const uint32_t d = std::max(depth[tree[node].first], depth[tree[node].second]) + 1;
+        depth[node] = d;
+        if (levels.size() < d) levels.resize(d);
+        levels[d - 1].push_back(node - n_leaves);
+    }
+    return levels;
+}
+
 } // namespace famsa_b200

@@ -47,3 +47,12 @@ def test_row_shards_balance():
         assert sum(sizes) == n * (n - 1) // 2
         if n >= 1000:
             assert max(sizes) <= 1.01 * (sum(sizes) / parts)
+
+
+def test_schedule_levels_and_shards():
+    from famsa_b200.schedule import ready_levels, shard_level
+    merges = [(0, 1), (2, 3), (4, 5), (6, 7), (8, 9)]        # 6 leaves: (0,1)->6 (2,3)->7 (4,5)->8 (6,7)->9 (8,9)->10
+    lv = ready_levels(6, merges)
+    assert lv == [[0, 1, 2], [3], [4]]
+    parts = shard_level([0, 1, 2, 3], [10, 7, 5, 4], 2)
+    assert sorted(sum(parts, [])) == [0, 1, 2, 3] and abs(sum([10, 7, 5, 4][k] for k in parts[0]) - 13) <= 3

@@ -47,14 +47,6 @@ def parse_newick(text: str):
     return leaves, [(ident(a), ident(b)) for a, b in raw_merges]
 
 
-def levels(n_leaves: int, merges: list[tuple[int, int]]) -> list[list[int]]:
-    """Group merges (by index) into dependency levels: level 0 merges only leaves, ..."""
-    depth = [0] * (n_leaves + len(merges))
-    out: list[list[int]] = []
-    for k, (a, b) in enumerate(merges):
-        d = max(depth[a], depth[b]) + 1
-        depth[n_leaves + k] = d
-        while len(out) < d:
-            out.append([])
-        out[d - 1].append(k)
-    return out
+def levels(n_leaves: int, merges):
+    from famsa_b200.schedule import ready_levels
+    return ready_levels(n_leaves, merges)
