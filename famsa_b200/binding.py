@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 EXPORTED_SYMBOLS = [
     "famsa_abi_version", "famsa_create", "famsa_destroy", "famsa_last_error", "famsa_kernel_launches",
     "famsa_lcs_upload", "famsa_lcs_n_seqs", "famsa_lcs_triangle", "famsa_lcs_triangle_device",
-    "famsa_lcs_rows", "famsa_lcs_rows_device", "famsa_transform_f64", "famsa_transform_f32",
+    "famsa_lcs_rows", "famsa_lcs_rows_device", "famsa_lcs_assign", "famsa_transform_f64", "famsa_transform_f32",
     "famsa_lcs_last_timing", "famsa_dp_align_batch", "famsa_dp_align_batch_device", "famsa_dp_last_timing",
 ]
 
@@ -66,6 +66,7 @@ def load_library() -> C.CDLL:
     lib.famsa_lcs_triangle_device.argtypes = [vp, u32, u32, vp, i32, vp]
     lib.famsa_lcs_rows.argtypes = [vp, vp, u32, vp, u32, vp, i32]
     lib.famsa_lcs_rows_device.argtypes = [vp, vp, u32, vp, u32, vp, i32, vp]
+    lib.famsa_lcs_assign.argtypes = [vp, vp, u32, i32, vp, vp]
     lib.famsa_transform_f64.argtypes = [i32, u32, u32, u32]
     lib.famsa_transform_f64.restype = C.c_double
     lib.famsa_transform_f32.argtypes = [i32, u32, u32, u32]
@@ -145,6 +146,14 @@ class Engine:
         self._check(self.lib.famsa_lcs_rows(self.h, _ptr(ref), len(ref), _ptr(cols), n_col, _ptr(buf),
                                             buf.dtype.itemsize))
         return buf[:len(ref) * n_col].reshape(len(ref), n_col)
+
+    def assign(self, seed_ids, kind: int = 0) -> tuple[np.ndarray, np.ndarray]:
+        """FastTree<>::makeEvaluation's assignment loop: (assignments uint32[n], min_dist float32[n])."""
+        seeds = np.ascontiguousarray(seed_ids, dtype=np.uint32)
+        a = np.empty(self.n, dtype=np.uint32)
+        d = np.empty(self.n, dtype=np.float32)
+        self._check(self.lib.famsa_lcs_assign(self.h, _ptr(seeds), len(seeds), kind, _ptr(a), _ptr(d)))
+        return a, d
 
     def rows_device(self, d_ref_ptr: int, n_ref: int, d_col_ptr: int, n_col: int, d_out_ptr: int,
                     elem_bytes: int, stream: int = 0):

@@ -63,7 +63,8 @@ void famsa_destroy(famsa_ctx* ctx)
     cudaDeviceSynchronize();
     fb::LcsState& S = ctx->lcs;
     for (fb::DevBuf* b : {&S.d_perm, &S.d_invperm, &S.d_len_sorted, &S.d_code_off, &S.d_codes, &S.d_blob,
-                          &S.d_group_blob, &S.d_raw_codes, &S.d_raw_off, &S.d_raw_len, &S.d_flags, &S.d_tiles,
+                          &S.d_group_blob, &S.d_raw_codes, &S.d_raw_off, &S.d_raw_len, &S.d_flags, &S.d_pow075, &S.d_assign_lcs,
+                          &S.d_assign, &S.d_mind, &S.d_tiles,
                           &S.d_res, &S.d_refpos, &S.d_ids_a, &S.d_ids_b, &S.d_out_stage, &S.d_masks64, &S.d_x64})
         b->release();
     fb::DpState& D = ctx->dp;
@@ -217,6 +218,22 @@ int famsa_lcs_rows(famsa_ctx* ctx, const uint32_t* ref_ids, uint32_t n_ref, cons
     if (rc) return rc;
     if (cells) FB_CUDA(cudaMemcpy(out, S.d_out_stage.p, cells * elem_bytes, cudaMemcpyDeviceToHost));
     return FAMSA_OK;
+}
+
+int famsa_lcs_assign(famsa_ctx* ctx, const uint32_t* seed_ids, uint32_t n_seeds, int distance_kind, uint32_t* assignments,
+                     float* min_dist)
+{
+    FB_CHECK_CTX(ctx);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->lcs.n == 0) { set_error("famsa_lcs_upload has not been called"); return FAMSA_E_STATE; }
+    if (!seed_ids || !n_seeds || !assignments || !min_dist) { set_error("NULL argument / no seeds"); return FAMSA_E_INVALID; }
+    if (distance_kind < 0 || distance_kind > 2) { set_error("distance_kind must be 0, 1 or 2"); return FAMSA_E_INVALID; }
+    for (uint32_t k = 0; k < n_seeds; ++k)
+        if (seed_ids[k] >= ctx->lcs.n) { set_error("seed id out of range"); return FAMSA_E_INVALID; }
+    FB_CUDA(cudaSetDevice(ctx->device));
+    int rc = fb::lcs_assign(ctx, seed_ids, n_seeds, distance_kind, assignments, min_dist);
+    if (rc) return rc;
+    return finish_timing(ctx);
 }
 
 int famsa_lcs_last_timing(const famsa_ctx* ctx, float* total_ms, float* main_kernel_ms, uint64_t* n_pairs)

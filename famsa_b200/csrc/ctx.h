@@ -51,7 +51,7 @@ struct LcsState {
     std::vector<uint32_t> h_quirky;    // caller ids whose masks contain an all-ones 64-bit word
     std::vector<uint32_t> h_long;      // caller ids longer than the tile kernel handles as mask side
     DevBuf d_perm, d_invperm, d_len_sorted, d_code_off, d_codes, d_blob, d_group_blob;
-    DevBuf d_raw_codes, d_raw_off, d_raw_len, d_flags;
+    DevBuf d_raw_codes, d_raw_off, d_raw_len, d_flags, d_pow075, d_assign_lcs, d_assign, d_mind;
     // per-call scratch
     DevBuf d_tiles, d_res, d_refpos, d_ids_a, d_ids_b, d_out_stage, d_masks64, d_x64;
     // last-call timing
@@ -89,6 +89,8 @@ int lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_o
 int lcs_rows(famsa_ctx* ctx, const uint32_t* d_ref_ids, const uint32_t* h_ref_ids, uint32_t n_ref,
              const uint32_t* d_col_ids, uint32_t n_col, void* d_out, int elem_bytes,
              cudaStream_t stream);
+int lcs_assign(famsa_ctx* ctx, const uint32_t* h_seed_ids, uint32_t n_seeds, int kind, uint32_t* h_assign,
+               float* h_mind);
 // dp.cu
 int dp_run_host(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int64_t gaps[4], famsa_dp_result* results,
                 uint8_t* path_buf, uint8_t* dirs_buf);

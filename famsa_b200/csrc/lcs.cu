@@ -22,6 +22,8 @@
 //     those rows -- and rows too long for the register-resident kernel -- are recomputed by
 //     k_lcs_exact, which follows the reference recurrence word for word.
 #include <algorithm>
+#include <cfloat>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 
@@ -354,6 +356,42 @@ __global__ void k_lcs_exact(const uint8_t* __restrict__ codes, const uint32_t* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// medoid assignment: float Transform + running arg-min over the seed rows (FastTree.cpp:309-324)
+// ------------------------------------------------------------------------------------------------
+
+// Transform<float, Distance> (AbstractTreeGenerator.hpp:28-82) with the host-computed (float) pow(i, 0.75) table;
+// IEEE division, so the result is the host's bit for bit.
+__device__ __forceinline__ float transform_f32(int kind, uint32_t lcs, uint32_t len1, uint32_t len2,
+                                               const float* __restrict__ pow075, float never)
+{
+    if (kind == 2) return __fdiv_rn((float)lcs, (float)(len1 < len2 ? len1 : len2));
+    const uint32_t indel_i = len1 + len2 - 2 * lcs;
+    if (!lcs) return never;                                  // (float) nextafter((double) FLT_MAX, 0) == FLT_MAX
+    if (kind == 0) return __fdiv_rn(pow075[indel_i], (float)lcs);
+    return __fdiv_rn((float)indel_i, (float)lcs);
+}
+
+__global__ void k_assign(const void* __restrict__ lcs, int elem_bytes, uint32_t n, uint32_t n_seeds,
+                         const uint32_t* __restrict__ seed_ids, const uint32_t* __restrict__ lens,
+                         const float* __restrict__ pow075, int kind, float never,
+                         uint32_t* __restrict__ assign, float* __restrict__ mind)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t lj = lens[j];
+    float best = 0.f;
+    uint32_t a = 0;
+    for (uint32_t k = 0; k < n_seeds; ++k) {
+        const size_t at = (size_t)k * n + j;
+        const uint32_t l = elem_bytes == 2 ? static_cast<const uint16_t*>(lcs)[at] : static_cast<const uint32_t*>(lcs)[at];
+        const float d = transform_f32(kind, l, lens[seed_ids[k]], lj, pow075, never);
+        if (k == 0 || d < best) { best = d; a = k; }
+    }
+    assign[j] = a;
+    mind[j] = best;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 
@@ -497,6 +535,13 @@ int lcs_upload(famsa_ctx* ctx, const int8_t* codes, const uint64_t* offsets, con
     FB_CUDA(cudaMemcpyAsync(S.d_raw_len.p, lens, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
     FB_CUDA(cudaMemsetAsync(S.d_codes.p, kNoMatch, units * 16 + 64, st));
 
+    {   // (float) pow(i, 0.75) for every possible indel count, computed by the host libm like the reference's table
+        std::vector<float> pw((size_t)2 * S.max_len + 2);
+        for (size_t v = 0; v < pw.size(); ++v) pw[v] = (float)pow((double)v, 0.75);
+        FB_TRY(S.d_pow075.reserve(sizeof(float) * pw.size()));
+        FB_CUDA(cudaMemcpyAsync(S.d_pow075.p, pw.data(), sizeof(float) * pw.size(), cudaMemcpyHostToDevice, st));
+        FB_CUDA(cudaStreamSynchronize(st));          // pw goes out of scope
+    }
     k_repack<<<(n + 7) / 8, 256, 0, st>>>(S.d_raw_codes.as<int8_t>(), S.d_raw_off.as<uint64_t>(),
                                           S.d_raw_len.as<uint32_t>(), S.d_perm.as<uint32_t>(),
                                           S.d_code_off.as<uint32_t>(), S.d_codes.as<uint8_t>(), n);
@@ -686,6 +731,32 @@ int lcs_rows(famsa_ctx* ctx, const uint32_t* d_ref_ids, const uint32_t* h_ref_id
     (void)d_ref_ids;
     (void)n;
     FB_CUDA(cudaEventRecord(ctx->ev[3], st));
+    return FAMSA_OK;
+}
+
+int lcs_assign(famsa_ctx* ctx, const uint32_t* h_seed_ids, uint32_t n_seeds, int kind, uint32_t* h_assign, float* h_mind)
+{
+    LcsState& S = ctx->lcs;
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = S.n;
+    const int eb = S.max_len < 65536 ? 2 : 4;
+    FB_TRY(S.d_assign_lcs.reserve((size_t)eb * n * n_seeds));
+    FB_TRY(S.d_assign.reserve(sizeof(uint32_t) * n));
+    FB_TRY(S.d_mind.reserve(sizeof(float) * n));
+    FB_TRY(S.d_ids_a.reserve(sizeof(uint32_t) * n_seeds));
+    FB_CUDA(cudaMemcpyAsync(S.d_ids_a.p, h_seed_ids, sizeof(uint32_t) * n_seeds, cudaMemcpyHostToDevice, st));
+    // seed k is the row (seq0) of its distance vector, every sequence a column: exactly famsa_lcs_rows
+    FB_TRY(lcs_rows(ctx, S.d_ids_a.as<uint32_t>(), h_seed_ids, n_seeds, nullptr, n, S.d_assign_lcs.p, eb, st));
+    const float never = (float)nextafter((double)FLT_MAX, 0.0);
+    k_assign<<<(n + 255) / 256, 256, 0, st>>>(S.d_assign_lcs.p, eb, n, n_seeds, S.d_ids_a.as<uint32_t>(),
+                                             S.d_raw_len.as<uint32_t>(), S.d_pow075.as<float>(), kind, never,
+                                             S.d_assign.as<uint32_t>(), S.d_mind.as<float>());
+    FB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    FB_CUDA(cudaEventRecord(ctx->ev[3], st));
+    FB_CUDA(cudaMemcpyAsync(h_assign, S.d_assign.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaMemcpyAsync(h_mind, S.d_mind.p, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaStreamSynchronize(st));
     return FAMSA_OK;
 }
 

@@ -98,6 +98,19 @@ int famsa_lcs_rows_device(famsa_ctx* ctx, const uint32_t* d_ref_ids, uint32_t n_
                           const uint32_t* d_col_ids, uint32_t n_col, void* d_out, int elem_bytes,
                           void* stream);
 
+/* Medoid assignment, the inner loop of the -medoidtree / -parttree heuristic
+ * (FastTree<>::makeEvaluation, src/tree/FastTree.cpp:309-324): seed k's row of float distances
+ * (calculateDistanceVector with sequences[seed_ids[k]] as the row, Transform<float, distance>) is folded into a
+ * running minimum,   if (row_k[j] < best[j]) { best[j] = row_k[j]; assignments[j] = k; }   for k = 0..n_seeds-1
+ * (strict <, so the first seed wins ties; starting from seed 0 is what the reference's pre-filled dist_row
+ * amounts to).  Computed entirely on the device -- LCS rows, the float Transform (pow table shipped from the
+ * host so it is the host libm's), the arg-min -- and only assignments[n_seqs] / min_dist[n_seqs] come back
+ * instead of n_seeds x n_seqs distances.  The cost (std::accumulate over min_dist, float, left to right) is
+ * left to the caller so that its summation order stays the reference's.  distance_kind as in
+ * famsa_transform_f32.  HOST pointers. */
+int famsa_lcs_assign(famsa_ctx* ctx, const uint32_t* seed_ids, uint32_t n_seeds, int distance_kind,
+                     uint32_t* assignments, float* min_dist);
+
 /* Host-side Transform<T, Distance> (AbstractTreeGenerator.hpp:28-82), provided so bindings that
  * are not C++ get bit-identical distances.  kind: 0 indel075_div_lcs, 1 indel_div_lcs,
  * 2 pairwise_identity. */

@@ -123,3 +123,61 @@ def test_full_size_properties(engine):
         assert np.array_equal(tri[ref * (ref - 1) // 2 + cols], want)
     # (4) checksum of checksums is reproducible across a second run
     assert int(tri.astype(np.uint64).sum()) == int(engine.triangle(dtype=np.uint16).astype(np.uint64).sum())
+
+
+def _assign_reference(codes, offsets, lens, seeds, kind, lcs_rows):
+    """FastTree<>::makeEvaluation (src/tree/FastTree.cpp:309-324) restated with the oracle's float Transform."""
+    n = len(lens)
+    best = np.zeros(n, dtype=np.float32)
+    assign = np.zeros(n, dtype=np.uint32)
+    for k, s in enumerate(seeds):
+        row = np.array([pyoracle.transform(kind, int(lcs_rows[k, j]), int(lens[s]), int(lens[j]), double=False)
+                        for j in range(n)], dtype=np.float32)
+        if k == 0:
+            best[:] = row
+        else:
+            better = row < best
+            best[better] = row[better]
+            assign[better] = k
+    return assign, best
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2])
+def test_medoid_assignment(engine, adeno, kind):
+    """famsa_lcs_assign == seed rows -> float Transform -> strict-< running arg-min, bit for bit."""
+    rng = np.random.default_rng(kind)
+    codes, offsets, lens = adeno["codes"], adeno["offsets"], adeno["lens"]
+    engine.upload(codes, offsets, lens)
+    seeds = rng.permutation(len(lens))[:17]
+    want_a, want_d = _assign_reference(codes, offsets, lens, seeds, kind, adeno["lcs"][seeds])
+    got_a, got_d = engine.assign(seeds, kind)
+    assert np.array_equal(got_a, want_a)
+    assert np.array_equal(got_d.view(np.uint32), want_d.view(np.uint32))          # same float bits
+    if pyoracle.have_ref():
+        rs = pyoracle.RefSeqSet(adeno["seqs"])
+        lib = pyoracle.ref()
+        s = int(seeds[3])
+        row = rs.row_prefix(s, len(lens), 2)
+        d = np.array([lib.ref_transform_f32(kind, int(row[j]), int(lens[s]), int(lens[j])) for j in range(len(lens))], dtype=np.float32)
+        assert np.all(got_d <= d)
+        assert np.array_equal(got_d[got_a == 3], d[got_a == 3])
+
+
+def test_medoid_assignment_large(engine):
+    """Config-5 shape at reduced N: two-level family, 100 seeds, duplicates of a seed's sequence tie to the first."""
+    codes, offsets, lens = seqio.synth_family(20000, 250, seed=3, n_subroots=30)
+    engine.upload(codes, offsets, lens)
+    rng = np.random.default_rng(5)
+    seeds = np.sort(rng.choice(len(lens), size=100, replace=False))
+    a, d = engine.assign(seeds, 0)
+    rows = engine.rows(seeds[:3], dtype=np.uint32)
+    for j in rng.integers(0, len(lens), size=200):
+        ds = [pyoracle.transform(0, int(pyoracle.lcs_rows(codes, offsets, lens, [int(s)], [int(j)])[0, 0]), int(lens[s]), int(lens[j]), False)
+              for s in seeds]
+        ds = np.array(ds, dtype=np.float32)
+        assert a[j] == int(np.argmin(ds)) and d[j] == ds.min()
+    assert np.all(a[seeds] == np.arange(100)) or np.all(d[seeds] == 0)
+    cost = np.float32(0)
+    for x in d[:1000]:
+        cost = np.float32(cost + x)                     # the caller keeps std::accumulate's order
+    assert np.isfinite(cost)
