@@ -149,6 +149,8 @@ def ref() -> C.CDLL:
         lib.ref_profile_row.restype = C.c_int
         lib.ref_profile_align.argtypes = [vp, vp, vp, C.c_int]
         lib.ref_profile_align.restype = vp
+        lib.ref_profile_construct.argtypes = [vp, vp, vp, vp, vp, C.c_int]
+        lib.ref_profile_construct.restype = vp
         lib.ref_dp_align_pairs_mt.argtypes = [vp, vp, vp, u32, C.c_int, vp]
         lib.ref_dp_align_pairs_mt.restype = C.c_double
         _ref = lib
@@ -207,6 +209,15 @@ class RefDp:
             no = self.lib.ref_profile_row(p, i, buf)
             out[no] = buf.value.decode()
         return out
+
+    def construct(self, p1, p2, dirs: np.ndarray, last, swapped: bool):
+        """The reference's ConstructProfile on an externally produced direction matrix.  Consumes p1, p2."""
+        d = np.ascontiguousarray(dirs, dtype=np.uint8)
+        l = np.ascontiguousarray(last, dtype=np.int64)
+        m = C.c_void_p(self.lib.ref_profile_construct(self.h, p1, p2, _p(d), _p(l), int(swapped)))
+        self.lib.ref_profile_destroy(p1)
+        self.lib.ref_profile_destroy(p2)
+        return m
 
     def align_pairs_mt(self, p1s, p2s, n_threads: int):
         """Times len(p1s) independent merges on n_threads threads; consumes the profiles."""

@@ -22,6 +22,7 @@
 #include <memory>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #define private public      // harness TU only: read CProfile internals, nothing is modified
@@ -64,6 +65,20 @@ struct SeqSet {
 };
 
 } // namespace
+
+// CProfile::ConstructProfile and its dp_row_elem_t parameter sit in the class's default-private section (no
+// `private:` keyword for the macro above to catch).  An explicit template instantiation may name a private
+// member, which hands us the member-function pointer without touching the reference source.
+auto stolen_construct_profile();
+template <auto M> struct StealMember {
+    friend auto stolen_construct_profile() { return M; }
+};
+template struct StealMember<&CProfile::ConstructProfile>;
+template <class T> struct ConstructTraits;
+template <class C, class R, class A1, class A2, class A3, class A4, class A5>
+struct ConstructTraits<R (C::*)(A1, A2, A3, A4, A5)> {
+    using elem_t = std::remove_reference_t<A4>;      // CProfile::dp_row_elem_t
+};
 
 extern "C" {
 
@@ -302,6 +317,27 @@ void* ref_profile_align(void* h, void* p1, void* p2, int no_threads)
     auto* s = static_cast<DpSession*>(h);
     return new CProfile(static_cast<CProfile*>(p1), static_cast<CProfile*>(p2), &s->params,
                         (uint32_t)no_threads, 4, s->atp.get());
+}
+
+// The host half of a merge driven from OUTSIDE: the reference's own, unmodified ConstructProfile
+// (profile.cpp:694-1002) run on a CDPMatrix whose bytes were produced elsewhere (by the GPU in
+// tests/test_dp_gpu.py::test_gpu_driven_progressive_alignment), with `last` = (D,H,V) at the corner.
+// swapped != 0 means the DP's row profile is p2 (what CProfile::Align decides at profile.cpp:254-304).
+// Children are consumed like in ref_profile_align; the caller frees them.
+void* ref_profile_construct(void* h, void* p1, void* p2, const uint8_t* dirs, const int64_t* last, int swapped)
+{
+    auto* s = static_cast<DpSession*>(h);
+    auto* a = static_cast<CProfile*>(p1);
+    auto* b = static_cast<CProfile*>(p2);
+    CProfile* R = swapped ? b : a;
+    CProfile* C = swapped ? a : b;
+    CProfile* m = new CProfile(&s->params, s->atp.get());
+    CDPMatrix matrix(R->width + 1, C->width + 1);
+    memcpy(matrix.get_row(0), dirs, (R->width + 1) * (C->width + 1));
+    auto pmf = stolen_construct_profile();
+    typename ConstructTraits<decltype(pmf)>::elem_t le(last[0], last[1], last[2]);
+    (m->*pmf)(R, C, matrix, le, 1u);
+    return m;
 }
 
 // Times n independent merges on n_threads host threads (one merge per task, each merge sequential:

@@ -56,3 +56,32 @@ def check_against_reference(results, recs):
         want = pyoracle.path_from_rows(rec["rows"], rec["m1"], rec["m2"], r["swapped"])
         assert r["total"] == rec["total"], f"merge {k}: total {r['total']} != {rec['total']}"
         assert np.array_equal(r["path"], want[:len(r["path"])]) and len(want) == len(r["path"]), f"merge {k}: path differs"
+
+
+def driven_progressive_alignment(seqs, merges, align_level, n_seqs_for_rescale=None):
+    """Level-synchronous progressive alignment in which the DP (direction matrices + corner scores) comes from
+    `align_level(jobs, gaps) -> [dict(dirs, last, swapped), ...]` and everything else -- leaf profiles, the merged
+    profile construction -- is the reference's own host code (ConstructProfile, profile.cpp:694-1002, through
+    oracle/ref_harness.cpp).  Returns the final alignment rows {seq_no: gapped string} and the root total score."""
+    from famsa_b200.schedule import ready_levels
+    n = len(seqs)
+    dp = pyoracle.RefDp(n if n_seqs_for_rescale is None else n_seqs_for_rescale)
+    g = dp.gaps()
+    nodes = {i: dp.leaf(seqs[i], i) for i in range(n)}
+    for lvl in ready_levels(n, merges):
+        jobs = []
+        for k in lvl:
+            a, b = merges[k]
+            s1, c1, k1 = dp.tables(nodes[a])
+            s2, c2, k2 = dp.tables(nodes[b])
+            jobs.append((s1, c1, k1, s2, c2, k2))
+        res = align_level(jobs, g)
+        for k, r in zip(lvl, res):
+            a, b = merges[k]
+            nodes[n + k] = dp.construct(nodes.pop(a), nodes.pop(b), r["dirs"], r["last"], r["swapped"])
+    root = nodes[n + len(merges) - 1]
+    rows = dp.rows(root)
+    total = int(dp.lib.ref_profile_total_score(root))
+    dp.free(root)
+    dp.close()
+    return rows, total

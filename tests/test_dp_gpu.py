@@ -86,6 +86,25 @@ def test_hemopexin_all_merges(engine):
 
 
 @needs_ref
+@pytest.mark.parametrize("fixture", ["adeno_upgma_merges.npz", "hemopexin_medoid_sl.npz"])
+def test_gpu_driven_progressive_alignment(engine, fixture):
+    """Drop-in proof for HP-2: the GPU's direction matrices and corner scores feed the reference's UNMODIFIED
+    ConstructProfile level by level (the loop INTEGRATION.md describes); the final multiple alignment is the
+    reference's -- for adeno_fiber that is the golden upgma.no_refine.fasta, for hemopexin the golden
+    medoid-sl.fasta (4188 sequences, 94 levels), both asserted equal to the reference run when the fixtures
+    were generated."""
+    from dp_cases import driven_progressive_alignment
+    z = np.load(os.path.join(GOLDEN, fixture))
+    seqs = [str(s) for s in z["seqs"]]
+    merges = [tuple(int(x) for x in m) for m in z["merges"]]
+    rows, total = driven_progressive_alignment(
+        seqs, merges, lambda jobs, g: engine.dp_align_batch(jobs, g, want_dirs=True))
+    _, recs = reference_merges(seqs, merges, threads=(1,))
+    assert total == int(z["totals"][-1]) == recs[-1]["total"]
+    assert rows == recs[-1]["rows"]
+
+
+@needs_ref
 @pytest.mark.parametrize("seed,n,length,gaps", [(11, 70, 60, None), (12, 24, 500, None), (13, 40, 33, (-9000, -700, -300, -100)),
                                                 (14, 12, 1300, None), (15, 30, 31, (-20000, -2000, -2500, -900))])
 def test_random_families(engine, seed, n, length, gaps):

@@ -80,3 +80,17 @@ def test_oracle_hemopexin_first_levels():
         o = pyoracle.dp_align(*r["job"], g)
         assert o["total"] == int(z["totals"][k])
         assert zlib.crc32(o["path"].tobytes()) == int(z["path_crc"][k])
+
+
+@needs_ref
+def test_oracle_driven_alignment_equals_reference():
+    """The oracle's direction matrices drive the reference's own ConstructProfile through the whole upgma tree of
+    adeno_fiber: the final alignment must be the reference's, row for row."""
+    from dp_cases import driven_progressive_alignment
+    z = np.load(os.path.join(GOLDEN, "adeno_upgma_merges.npz"))
+    seqs = [str(s) for s in z["seqs"]]
+    merges = [tuple(int(x) for x in m) for m in z["merges"]]
+    rows, total = driven_progressive_alignment(
+        seqs, merges, lambda jobs, g: [pyoracle.dp_align(*j, g) for j in jobs])
+    _, recs = reference_merges(seqs, merges, threads=(1,))
+    assert rows == recs[-1]["rows"] and total == recs[-1]["total"] == int(z["totals"][-1])
