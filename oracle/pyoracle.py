@@ -122,6 +122,8 @@ def ref() -> C.CDLL:
         lib.ref_lcs_row_ids.argtypes = [vp, u32, vp, u32, vp, C.c_int]
         lib.ref_lcs_triangle_mt.argtypes = [vp, u32, u32, C.c_int, C.c_int, vp, vp]
         lib.ref_lcs_triangle_mt.restype = C.c_double
+        lib.ref_upgma_tree.argtypes = [vp, C.c_int, C.c_int, vp]
+        lib.ref_upgma_tree_from_distances.argtypes = [vp, C.c_int, C.c_int, vp]
         lib.ref_transform_f64.argtypes = [C.c_int, u32, u32, u32]
         lib.ref_transform_f64.restype = C.c_double
         lib.ref_transform_f32.argtypes = [C.c_int, u32, u32, u32]
@@ -155,6 +157,14 @@ def ref() -> C.CDLL:
         lib.ref_dp_align_pairs_mt.restype = C.c_double
         _ref = lib
     return _ref
+
+
+def upgma_tree_from_distances(tri: np.ndarray, n: int, modified: bool = False) -> np.ndarray:
+    """The reference's UPGMA agglomeration (computeTree) on an external float distance triangle."""
+    t = np.ascontiguousarray(tri, dtype=np.float32)
+    out = np.zeros((2 * n - 1, 2), dtype=np.int32)
+    ref().ref_upgma_tree_from_distances(_p(t), n, int(modified), _p(out))
+    return out
 
 
 class RefDp:
@@ -289,6 +299,12 @@ class RefSeqSet:
         out = np.zeros(max(len(ids), 1), dtype=np.uint32)
         self.lib.ref_lcs_row_ids(self.h, ref_id, _p(ids), len(ids), _p(out), isa)
         return out[:len(ids)]
+
+    def upgma_tree(self, modified: bool = False, n_threads: int = 2) -> np.ndarray:
+        """The reference's UPGMA guide tree of this set: (2n-1, 2) child ids, leaves are (-1, -1)."""
+        out = np.zeros((2 * self.n - 1, 2), dtype=np.int32)
+        self.lib.ref_upgma_tree(self.h, int(modified), n_threads, _p(out))
+        return out
 
     def triangle_mt(self, row_begin: int, row_end: int, n_threads: int, isa: int = 2, want_lcs: bool = False):
         f = lambda r: r * (r - 1) // 2 if r else 0

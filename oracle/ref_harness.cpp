@@ -34,6 +34,7 @@
 #include "lcs/lcsbp.h"
 #include "tree/AbstractTreeGenerator.h"
 #include "tree/AbstractTreeGenerator.hpp"
+#include "tree/UPGMA.h"
 #undef private
 #undef protected
 
@@ -178,6 +179,31 @@ double ref_lcs_triangle_mt(void* h, uint32_t row_begin, uint32_t row_end, int n_
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (n_pairs) *n_pairs = pairs.load();
     return sec;
+}
+
+// ---------------------------------------------------------------- guide tree consumers of HP-1
+// (a) the reference's UPGMA end to end on the set (its own CLCSBP distances);
+// (b) the reference's UPGMA agglomeration (UPGMA<>::computeTree, UPGMA.cpp:114-295) on an EXTERNAL float
+//     distance triangle -- used to show that GPU LCS lengths + the host Transform reproduce the same tree.
+// out_pairs receives (left, right) for all 2n-1 nodes of tree_structure (leaves are -1, -1).
+void ref_upgma_tree(void* h, int modified, int n_threads, int* out_pairs)
+{
+    auto* s = static_cast<SeqSet*>(h);
+    UPGMA<Distance::indel075_div_lcs> gen(n_threads, instruction_set_t::avx2, modified != 0);
+    tree_structure tree;
+    gen(s->ptrs, tree);
+    for (size_t i = 0; i < tree.size(); ++i) { out_pairs[2 * i] = tree[i].first; out_pairs[2 * i + 1] = tree[i].second; }
+}
+
+void ref_upgma_tree_from_distances(const float* tri, int n, int modified, int* out_pairs)
+{
+    UPGMA<Distance::indel075_div_lcs> gen(1, instruction_set_t::avx2, modified != 0);
+    std::vector<float> d(tri, tri + (size_t)n * (n - 1) / 2);
+    tree_structure tree;
+    tree.resize(n, std::make_pair<int, int>(-1, -1));
+    if (modified) gen.computeTree<true>(d.data(), n, tree);
+    else gen.computeTree<false>(d.data(), n, tree);
+    for (size_t i = 0; i < tree.size(); ++i) { out_pairs[2 * i] = tree[i].first; out_pairs[2 * i + 1] = tree[i].second; }
 }
 
 // The reference's own Transform functors.  kind: 0 indel075_div_lcs, 1 indel_div_lcs, 2 pairwise_identity.

@@ -181,3 +181,36 @@ def test_medoid_assignment_large(engine):
     for x in d[:1000]:
         cost = np.float32(cost + x)                     # the caller keeps std::accumulate's order
     assert np.isfinite(cost)
+
+
+@pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("modified", [False, True])
+def test_gpu_driven_upgma_tree(engine, modified):
+    """Drop-in proof for HP-1: GPU LCS triangle -> host Transform<float, indel075_div_lcs> -> the reference's own,
+    unmodified UPGMA agglomeration (UPGMA<>::computeTree) gives exactly the guide tree the reference builds from
+    its CPU LCS (and, on adeno_fiber, every distance of the golden dist_sq.csv)."""
+    codes, offsets, lens = seqio.synth_family(400, 150, seed=21)
+    n = len(lens)
+    engine.upload(codes, offsets, lens)
+    lcs = engine.triangle(dtype=np.uint32)
+    i, j = np.tril_indices(n, -1)
+    tri = np.zeros(lcs.size, dtype=np.float32)
+    tri[i * (i - 1) // 2 + j] = [engine.transform(0, int(l), int(lens[a]), int(lens[b]), double=False)
+                                 for l, a, b in zip(lcs[i * (i - 1) // 2 + j], i, j)]
+    letters = [seqio.decode(codes[int(o):int(o) + int(ln)]) for o, ln in zip(offsets, lens)]
+    want = pyoracle.RefSeqSet(letters).upgma_tree(modified)
+    got = pyoracle.upgma_tree_from_distances(tri, n, modified)
+    assert np.array_equal(got, want)
+
+
+def test_gpu_distances_match_golden_dist_sq(engine, adeno):
+    """test/adeno_fiber/dist_sq.csv: GPU LCS + host float Transform reproduce every printed distance."""
+    n = len(adeno["lens"])
+    engine.upload(adeno["codes"], adeno["offsets"], adeno["lens"])
+    rows = engine.rows(np.arange(n))
+    lens = adeno["lens"]
+    for a in range(0, n, 3):
+        for b in range(n):
+            if a != b:
+                d = engine.transform(0, int(rows[a, b]), int(lens[a]), int(lens[b]), double=False)
+                assert abs(d - adeno["dist"][a, b]) < 1e-6 * max(1.0, abs(d)) + 6e-7
