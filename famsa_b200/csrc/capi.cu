@@ -1,6 +1,7 @@
 // C ABI of libfamsa_b200.so -- see include/famsa_b200.h for the contract of every entry point.
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 #include "ctx.h"
@@ -73,6 +74,11 @@ void famsa_destroy(famsa_ctx* ctx)
         b->release();
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_block)
+        if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->ev_host)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -144,16 +150,56 @@ int famsa_lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, voi
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (row_begin > row_end || row_end > ctx->lcs.n) { set_error("row range out of bounds"); return FAMSA_E_INVALID; }
     if (elem_bytes != 2 && elem_bytes != 4) { set_error("elem_bytes must be 2 or 4"); return FAMSA_E_INVALID; }
-    const uint64_t pairs = (uint64_t)row_end * (row_end ? row_end - 1 : 0) / 2 -
-                           (uint64_t)row_begin * (row_begin ? row_begin - 1 : 0) / 2;
+    auto tri = [](uint64_t r) { return r ? r * (r - 1) / 2 : 0; };
+    const uint64_t pairs = tri(row_end) - tri(row_begin);
     if (pairs && !out) { set_error("out is NULL"); return FAMSA_E_INVALID; }
     FB_CUDA(cudaSetDevice(ctx->device));
     int rc = ctx->lcs.d_out_stage.reserve(std::max<uint64_t>(pairs, 1) * elem_bytes);
     if (rc) return rc;
-    void* d_out = ctx->lcs.d_out_stage.p;
-    rc = triangle_locked(ctx, row_begin, row_end, d_out, elem_bytes, nullptr);
+    char* d_out = static_cast<char*>(ctx->lcs.d_out_stage.p);
+
+    // Row blocks with equal numbers of pairs: all kernels are queued first, then every block is copied back as
+    // soon as its event fires, so the D2H of block k overlaps the kernels of blocks k+1...
+    constexpr int kBlocks = 8;
+    // (worth it only when the copy is long compared with the tail of a kernel: hundreds of millions of pairs)
+    unsigned long long block_min = 400000000ull;
+    if (const char* e = getenv("FAMSA_LCS_BLOCK_MIN_PAIRS")) block_min = strtoull(e, nullptr, 10);   // test knob
+    const int n_blocks = (ctx->lcs.identity_perm && pairs > block_min) ? kBlocks : 1;
+    uint32_t bounds[kBlocks + 1];
+    bounds[0] = row_begin;
+    for (int b = 1; b < n_blocks; ++b) {
+        const double target = (double)tri(row_begin) + (double)pairs * b / n_blocks;
+        uint32_t r = (uint32_t)((1.0 + std::sqrt(1.0 + 8.0 * target)) / 2.0);
+        bounds[b] = std::min(std::max(r, bounds[b - 1]), row_end);
+    }
+    bounds[n_blocks] = row_end;
+    if (!ctx->copy_stream) {
+        FB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (auto& e : ctx->ev_block) FB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : ctx->ev_host) FB_CUDA(cudaEventCreate(&e));
+    }
+    if (ctx->lcs.n == 0 && row_end > 0) { set_error("famsa_lcs_upload has not been called"); return FAMSA_E_STATE; }
+    rc = check_elem(ctx, elem_bytes);
     if (rc) return rc;
-    if (pairs) FB_CUDA(cudaMemcpy(out, d_out, pairs * elem_bytes, cudaMemcpyDeviceToHost));
+    FB_CUDA(cudaEventRecord(ctx->ev_host[0], ctx->stream));
+    float main_ms = 0.f;
+    rc = fb::lcs_triangle(ctx, row_begin, row_end, d_out, elem_bytes, ctx->stream, bounds, n_blocks, ctx->ev_block);
+    if (rc) return rc;
+    if (!ctx->lcs.identity_perm && n_blocks == 1) FB_CUDA(cudaEventRecord(ctx->ev_block[0], ctx->stream));
+    FB_CUDA(cudaEventRecord(ctx->ev_host[1], ctx->stream));
+    for (int b = 0; b < n_blocks; ++b) {
+        const uint64_t off = (tri(bounds[b]) - tri(row_begin)) * elem_bytes;
+        const uint64_t bytes = (tri(bounds[b + 1]) - tri(bounds[b])) * elem_bytes;
+        if (!bytes) continue;
+        FB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_block[b], 0));
+        FB_CUDA(cudaMemcpyAsync(static_cast<char*>(out) + off, d_out + off, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    }
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    FB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    FB_CUDA(cudaEventElapsedTime(&main_ms, ctx->ev_host[0], ctx->ev_host[1]));
+    ctx->lcs.last_total_ms = main_ms;
+    ctx->lcs.last_main_ms = main_ms;
+    ctx->lcs.last_pairs = pairs;
     return FAMSA_OK;
 }
 

@@ -73,6 +73,9 @@ struct famsa_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;                 // D2H of finished row blocks (famsa_lcs_triangle)
+    cudaEvent_t ev_block[8] = {};
+    cudaEvent_t ev_host[2] = {};
     std::mutex mu;
     uint64_t launches = 0;
     int sm_count = 0;
@@ -85,7 +88,8 @@ namespace fb {
 int lcs_upload(famsa_ctx* ctx, const int8_t* codes, const uint64_t* offsets, const uint32_t* lens,
                uint32_t n);
 int lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_out, int elem_bytes,
-                 cudaStream_t stream);
+                 cudaStream_t stream, const uint32_t* bounds = nullptr, int n_blocks = 1,
+                 cudaEvent_t* block_events = nullptr);
 int lcs_rows(famsa_ctx* ctx, const uint32_t* d_ref_ids, const uint32_t* h_ref_ids, uint32_t n_ref,
              const uint32_t* d_col_ids, uint32_t n_col, void* d_out, int elem_bytes,
              cudaStream_t stream);

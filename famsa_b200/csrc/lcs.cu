@@ -34,7 +34,7 @@ namespace fb {
 constexpr int kMaskRows = 21;     // symbols 0..19 + one all-zero row shared by every other code
 constexpr int kNoMatch = 20;      // device residue code for "never matches" (B, Z, X, *, padding)
 constexpr int kTileWarps = 4;
-constexpr int kSeqPerWarp = 16;
+constexpr int kSeqPerWarp = 8;
 constexpr int kTileQ = kTileWarps * kSeqPerWarp;   // streamed sequences per tile
 constexpr int kMaxNL = 64;        // limbs the register-resident kernel is instantiated for (2048 aa)
 
@@ -606,58 +606,66 @@ static int exact_row(famsa_ctx* ctx, uint32_t row, const uint32_t* d_col_ids, ui
     return FAMSA_OK;
 }
 
-int lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_out, int elem_bytes, cudaStream_t st)
+// Rows [row_begin, row_end) of the packed triangle.  With `bounds` (n_blocks + 1 ascending row indices spanning the
+// range) the work is issued block by block and block_events[b] is recorded after block b, so that a caller can
+// start copying finished blocks while later ones are still being computed; every tile list is uploaded up front.
+int lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_out, int elem_bytes, cudaStream_t st,
+                 const uint32_t* bounds, int n_blocks, cudaEvent_t* block_events)
 {
     LcsState& S = ctx->lcs;
     const uint32_t n = S.n;
     S.last_pairs = (uint64_t)row_end * (row_end ? row_end - 1 : 0) / 2 - (uint64_t)row_begin * (row_begin ? row_begin - 1 : 0) / 2;
     FB_CUDA(cudaEventRecord(ctx->ev[0], st));
+    const uint32_t whole[2] = {row_begin, row_end};
+    if (!bounds || !S.identity_perm) { bounds = whole; n_blocks = 1; }
 
-    // tiles per limb-count class
-    std::vector<std::vector<uint3>> by_nl(kMaxNL + 1);
-    for (uint32_t g = 0; g < S.n_groups; ++g) {
-        const uint32_t nl = S.groups[g].nl;
-        if (nl == 0) continue;
-        if (S.identity_perm && (g * 32 + 32 <= row_begin || g * 32 >= row_end)) continue;
-        const uint32_t q_end = std::min(n, g * 32 + 31);
-        for (uint32_t q0 = 0; q0 < q_end; q0 += kTileQ)
-            by_nl[nl].push_back(make_uint3(g, q0, std::min(q_end, q0 + (uint32_t)kTileQ)));
-    }
+    // tiles per (block, limb-count class); one upload for all of them
+    std::vector<std::vector<std::vector<uint3>>> tiles(n_blocks, std::vector<std::vector<uint3>>(kMaxNL + 1));
     size_t total = 0;
-    for (auto& v : by_nl) total += v.size();
+    for (int b = 0; b < n_blocks; ++b)
+        for (uint32_t g = 0; g < S.n_groups; ++g) {
+            const uint32_t nl = S.groups[g].nl;
+            if (nl == 0) continue;
+            if (S.identity_perm && (g * 32 + 32 <= bounds[b] || g * 32 >= bounds[b + 1])) continue;
+            const uint32_t q_end = std::min(n, g * 32 + 31);
+            for (uint32_t q0 = 0; q0 < q_end; q0 += kTileQ) {
+                tiles[b][nl].push_back(make_uint3(g, q0, std::min(q_end, q0 + (uint32_t)kTileQ)));
+                ++total;
+            }
+        }
+    std::vector<uint3> flat;
+    flat.reserve(total);
+    for (auto& blk : tiles)
+        for (auto& v : blk) flat.insert(flat.end(), v.begin(), v.end());
     FB_TRY(S.d_tiles.reserve(sizeof(uint3) * std::max<size_t>(total, 1)));
-    size_t at = 0;
-    for (auto& v : by_nl) {
-        if (v.empty()) continue;
-        FB_CUDA(cudaMemcpyAsync(S.d_tiles.as<uint3>() + at, v.data(), sizeof(uint3) * v.size(), cudaMemcpyHostToDevice, st));
-        at += v.size();
-    }
+    if (total) FB_CUDA(cudaMemcpyAsync(S.d_tiles.p, flat.data(), sizeof(uint3) * total, cudaMemcpyHostToDevice, st));
     TileParams P = base_params(ctx);
     P.out = d_out;
     P.elem_bytes = elem_bytes;
     P.rows_mode = 0;
-    P.row_begin = row_begin;
-    P.row_end = row_end;
     P.tri_base = (uint64_t)row_begin * (row_begin ? row_begin - 1 : 0) / 2;
+    std::vector<uint32_t> special;      // rows the tile kernel may not answer for: dropped-carry and over-long rows
+    std::set_union(S.h_quirky.begin(), S.h_quirky.end(), S.h_long.begin(), S.h_long.end(), std::back_inserter(special));
     FB_CUDA(cudaEventRecord(ctx->ev[1], st));
-    at = 0;
-    for (uint32_t nl = 1; nl <= (uint32_t)kMaxNL; ++nl) {
-        auto& v = by_nl[nl];
-        if (v.empty()) continue;
-        P.tiles = S.d_tiles.as<uint3>() + at;
-        FB_TRY(launch_tile_nl(ctx, nl, P, (uint32_t)v.size(), st));
-        at += v.size();
+    size_t at = 0;
+    for (int b = 0; b < n_blocks; ++b) {
+        P.row_begin = bounds[b];
+        P.row_end = bounds[b + 1];
+        for (uint32_t nl = 1; nl <= (uint32_t)kMaxNL; ++nl) {
+            auto& v = tiles[b][nl];
+            if (v.empty()) continue;
+            P.tiles = S.d_tiles.as<uint3>() + at;
+            FB_TRY(launch_tile_nl(ctx, nl, P, (uint32_t)v.size(), st));
+            at += v.size();
+        }
+        for (uint32_t row : special) {
+            if (row < bounds[b] || row >= bounds[b + 1] || row == 0) continue;
+            const size_t base = (size_t)row * (row - 1) / 2 - P.tri_base;
+            FB_TRY(exact_row(ctx, row, nullptr, row, 0, d_out, base, elem_bytes, st));
+        }
+        if (block_events) FB_CUDA(cudaEventRecord(block_events[b], st));
     }
     FB_CUDA(cudaEventRecord(ctx->ev[2], st));
-
-    // rows the tile kernel may not answer for: dropped-carry rows and over-long rows
-    std::vector<uint32_t> special;
-    std::set_union(S.h_quirky.begin(), S.h_quirky.end(), S.h_long.begin(), S.h_long.end(), std::back_inserter(special));
-    for (uint32_t row : special) {
-        if (row < row_begin || row >= row_end || row == 0) continue;
-        const size_t base = (size_t)row * (row - 1) / 2 - P.tri_base;
-        FB_TRY(exact_row(ctx, row, nullptr, row, 0, d_out, base, elem_bytes, st));
-    }
     FB_CUDA(cudaEventRecord(ctx->ev[3], st));
     return FAMSA_OK;
 }

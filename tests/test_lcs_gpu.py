@@ -214,3 +214,14 @@ def test_gpu_distances_match_golden_dist_sq(engine, adeno):
             if a != b:
                 d = engine.transform(0, int(rows[a, b]), int(lens[a]), int(lens[b]), double=False)
                 assert abs(d - adeno["dist"][a, b]) < 1e-6 * max(1.0, abs(d)) + 6e-7
+
+
+def test_blockwise_triangle_copy(engine, monkeypatch):
+    """famsa_lcs_triangle's block-wise path (eight equal-pair row blocks, each copied back as soon as it is done;
+    normally used above 4e8 pairs) forced on a small set."""
+    codes, offsets, lens = seqio.synth_family(700, 90, seed=33)
+    engine.upload(codes, offsets, lens)
+    monkeypatch.setenv("FAMSA_LCS_BLOCK_MIN_PAIRS", "1000")
+    want = pyoracle.lcs_triangle(codes, offsets, lens)
+    assert np.array_equal(engine.triangle(dtype=np.uint16), want)
+    assert np.array_equal(engine.triangle(dtype=np.uint32), want)
