@@ -27,6 +27,8 @@
 #include <numeric>
 #include <thread>
 
+#include <cooperative_groups.h>
+
 #include "ctx.h"
 
 namespace fb {
@@ -36,6 +38,8 @@ constexpr long long kNeg = -(1ll << 62);
 constexpr int kDpWarps = 4;               // block size of the one-warp-per-merge fill kernel
 constexpr int kDpTeamWarps = 8;           // warps cooperating on one large merge
 constexpr uint32_t kDpTeamMinWidth = 96;  // min(w1, w2) above which a merge gets a team
+constexpr int kDpCluster = 8;             // thread blocks per cluster for the widest merges
+constexpr uint32_t kDpClusterMinWidth = 1024;   // min(w1, w2) above which a merge gets a whole cluster
 constexpr int kTThreads = 256, kTCellsPerThread = 4;
 
 struct DpJobDev {
@@ -79,7 +83,7 @@ __host__ __device__ inline unsigned long long align_up(unsigned long long v, uns
 
 // scratch layout of one job (all sections 128-byte aligned)
 struct Scratch {
-    unsigned long long col, brow, rownz, s2t, tmp, total;
+    unsigned long long col, brow, rownz, s2t, tmp, lastv, total;
     __host__ __device__ Scratch(uint32_t w1, uint32_t w2)
     {
         const unsigned long long wm = (w1 > w2 ? w1 : w2) + 1ull;
@@ -88,7 +92,8 @@ struct Scratch {
         rownz = align_up(brow + sizeof(Cell) * wm, 128);
         s2t = align_up(rownz + sizeof(RowNz) * wm, 128);
         tmp = align_up(s2t + 8ull * 30 * wm, 128);
-        total = align_up(tmp + w1 + w2, 128);
+        lastv = align_up(tmp + w1 + w2, 128);
+        total = lastv + 128;
     }
 };
 
@@ -318,14 +323,15 @@ __global__ void __launch_bounds__(kTThreads) k_dp_t(const DpParams P)
 // k_dp_fill: the recurrence + traceback
 // ------------------------------------------------------------------------------------------------
 
-// One team = NW warps working on one merge.  Stripe k (rows 32k+1 .. 32k+32) belongs to warp k % NW.  The
+// One team = NW warps (x CL thread blocks of a cluster) working on one merge.  Stripe k (rows 32k+1 .. 32k+32)
+// belongs to team warp k % (NW*CL).  The
 // stripes of a team run as a lock-step staircase over MACRO STEPS of kChunk wavefront steps: stripe k starts
 // kLag macro steps after stripe k-1, which is exactly late enough for every boundary-row column it is about
 // to read (and the chunk it prefetches for the next macro step) to have been parked by lane 31 of stripe k-1.
 // Because the schedule is a closed form, nobody polls: one __syncthreads per macro step orders the hand-over.
 constexpr int kLag = 4;      // macro steps between consecutive stripes: (31 + 2*kChunk) / kChunk rounded up
 
-template <int VAR, int NW>
+template <int VAR, int NW, int CL>
 __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, const long long* __restrict__ T,
                                            const ColInfo* __restrict__ col, Cell* __restrict__ brow,
                                            unsigned char* __restrict__ dirs, uint32_t team_warp,
@@ -338,11 +344,12 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
     const uint32_t n_stripes = (WR + 31) / 32;
     const uint32_t steps = WC + 1 + 31;                              // wavefront steps per stripe
     const uint32_t S = (steps + kChunk - 1) / kChunk;                // macro steps per stripe
-    const uint32_t period = NW == 1 ? S : (S > (uint32_t)NW * kLag ? S : (uint32_t)NW * kLag);
-    const uint32_t rounds = (n_stripes + NW - 1) / NW;
+    constexpr uint32_t TW = (uint32_t)NW * CL;                       // warps in the team (CL > 1: a thread-block cluster)
+    const uint32_t period = TW == 1 ? S : (S > TW * kLag ? S : TW * kLag);
+    const uint32_t rounds = (n_stripes + TW - 1) / TW;
     // stripe k = r*NW + w starts at macro step r*period + w*kLag; the last stripe ends at m_end
     const uint32_t last_k = n_stripes - 1;
-    const uint32_t m_end = (last_k / NW) * period + (last_k % NW) * kLag + S;
+    const uint32_t m_end = (last_k / TW) * period + (last_k % TW) * kLag + S;
 
     // per-stripe state, live across macro steps
     uint32_t i = 0;
@@ -355,12 +362,12 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
     unsigned char* drow = dirs;
     const long long* trow = T;
 
-    for (uint32_t m = 0; m < (NW == 1 ? rounds * S : m_end); ++m) {
+    for (uint32_t m = 0; m < (TW == 1 ? rounds * S : m_end); ++m) {
         // my stripes start at r*period + team_warp*kLag, r = 0, 1, ...; `off` = local macro step inside the stripe
         const int rel = (int)m - (int)(team_warp * kLag);
         const uint32_t r = rel >= 0 ? (uint32_t)rel / period : 0;
         const int off = rel >= 0 ? (int)((uint32_t)rel - r * period) : -1;
-        const uint32_t k = r * NW + team_warp;
+        const uint32_t k = r * TW + team_warp;
         const bool mine = off >= 0 && off < (int)S && k < n_stripes;        // warp-uniform
         if (mine) {
             if (off == 0) {
@@ -490,13 +497,18 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
                 }
             }
         }
-        if (NW > 1) __syncthreads();        // hand-over point: parked columns become visible to the next stripe
+        // hand-over point: parked columns become visible to the next stripe
+        if (CL > 1) cooperative_groups::this_cluster().sync();
+        else if (NW > 1) __syncthreads();
         else __syncwarp();
     }
 }
 
-// NW == 1: four independent merges per 128-thread block (one warp each).  NW > 1: one merge per block.
-template <int NW>
+// NW == 1: four independent merges per 128-thread block (one warp each).  NW > 1: one merge per block.  CL > 1: one
+// merge per thread-block CLUSTER of CL blocks (the very wide merges near the root of the guide tree, where the
+// reference switches to its multi-threaded ParAlign* variants): the staircase then spans NW*CL warps on CL SMs,
+// the boundary row travels through L2 and the hand-over barrier is the cluster barrier.
+template <int NW, int CL>
 __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_fill(const DpParams P)
 {
     constexpr int kBlockWarps = NW == 1 ? kDpWarps : NW;
@@ -504,10 +516,15 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_fill(cons
     __shared__ __align__(16) Cell sm_brow[kBlockWarps][2][kChunk];
     __shared__ unsigned char sm_tile[NW == 1 ? kDpWarps : 1][32 * 32];
     const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const uint32_t team_warp = NW == 1 ? 0 : warp;
-    const uint32_t slot = NW == 1 ? blockIdx.x * kDpWarps + warp : blockIdx.x;
+    const uint32_t cta_rank = CL > 1 ? cooperative_groups::this_cluster().block_rank() : 0;
+    const uint32_t team_warp = NW == 1 ? 0 : cta_rank * NW + warp;
+    const uint32_t slot = NW == 1 ? blockIdx.x * kDpWarps + warp : blockIdx.x / CL;
     if (slot >= P.n_jobs) return;
-    auto team_sync = [&]() { if (NW == 1) __syncwarp(); else __syncthreads(); };
+    auto team_sync = [&]() {
+        if (CL > 1) cooperative_groups::this_cluster().sync();
+        else if (NW == 1) __syncwarp();
+        else __syncthreads();
+    };
     const uint32_t jid = P.order[slot];
     const DpJobDev J = P.jobs[jid];
     const DpMeta M = P.meta[jid];
@@ -517,22 +534,26 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_fill(cons
     const ColInfo* col = reinterpret_cast<const ColInfo*>(scratch + L.col);
     Cell* brow = reinterpret_cast<Cell*>(scratch + L.brow);
     unsigned char* tmp_path = scratch + L.tmp;
+    long long* g_last = reinterpret_cast<long long*>(scratch + L.lastv);
     unsigned char* dirs = P.dirs + J.dirs_off;
     const long long* T = P.T + J.t_off;
     const uint32_t WR = M.WR, WC = M.WC;
     const size_t ld = (size_t)WC + 1;
 
-    long long* last_out = sm_last[warp];
-    if (M.var == 0) dp_stripes<0, NW>(P, M, T, col, brow, dirs, team_warp, last_out, sm_brow[warp]);
-    else if (M.var == 1) dp_stripes<1, NW>(P, M, T, col, brow, dirs, team_warp, last_out, sm_brow[warp]);
-    else dp_stripes<2, NW>(P, M, T, col, brow, dirs, team_warp, last_out, sm_brow[warp]);
-    __threadfence_block();
+    // the lane that owns cell (WR, WC) leaves (D,H,V) in shared memory, or in the job's scratch for a cluster
+    long long* last_out = CL > 1 ? g_last : sm_last[warp];
+    if (M.var == 0) dp_stripes<0, NW, CL>(P, M, T, col, brow, dirs, team_warp, last_out, sm_brow[warp]);
+    else if (M.var == 1) dp_stripes<1, NW, CL>(P, M, T, col, brow, dirs, team_warp, last_out, sm_brow[warp]);
+    else dp_stripes<2, NW, CL>(P, M, T, col, brow, dirs, team_warp, last_out, sm_brow[warp]);
+    __threadfence();
     team_sync();
     if (team_warp != 0) return;
 
     // the warp that owned the final stripe stored (D,H,V)(WR,WC)
     const uint32_t owner_warp = NW == 1 ? warp : ((WR + 31) / 32 - 1) % NW;
-    const long long last[3] = {sm_last[owner_warp][0], sm_last[owner_warp][1], sm_last[owner_warp][2]};
+    long long last[3];
+    if (CL > 1) { last[0] = __ldcg(g_last); last[1] = __ldcg(g_last + 1); last[2] = __ldcg(g_last + 2); }
+    else { last[0] = sm_last[owner_warp][0]; last[1] = sm_last[owner_warp][1]; last[2] = sm_last[owner_warp][2]; }
 
     // ---- traceback (ConstructProfile, profile.cpp:727-775).  The warp fetches the 32 x 32 corner of the direction
     // matrix that ends at the current cell into shared memory (32 independent byte loads per lane instead of one
@@ -636,6 +657,8 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
     if (const char* e = getenv("FAMSA_DP_TEAM_MIN")) team_min = (uint32_t)atoi(e);               // development knob
     int nw = kDpTeamWarps;
     if (const char* e = getenv("FAMSA_DP_TEAM_WARPS")) nw = atoi(e);                             // development knob
+    uint32_t cluster_min = kDpClusterMinWidth;
+    if (const char* e = getenv("FAMSA_DP_CLUSTER_MIN")) cluster_min = (uint32_t)atoi(e);         // development knob
 
     FB_CUDA(cudaEventRecord(ctx->ev[0], st));
     FB_CUDA(cudaEventRecord(ctx->ev[1], st));
@@ -660,15 +683,24 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
         if (tblock[m] > 0x7fffffffull) { set_error("dp sub-batch too large for one launch"); return FAMSA_E_INVALID; }
         // merges whose shorter side spans several 32-row stripes get a whole block (a team of warps pipelined over
         // the stripes); the rest run one warp per merge.  Both groups cost-descending.
-        auto big = [&](uint32_t a) { return std::min(dev[a].w1, dev[a].w2) > team_min; };
+        // class 2: shorter side > cluster_min -> a cluster of blocks; class 1: > team_min -> one block; class 0: one warp
+        // When a level holds only a handful of block-sized merges (the top of the guide tree) the GPU would sit idle:
+        // give every merge with more than 8 stripes a cluster then.
+        uint32_t n_teamable = 0;
+        for (uint32_t a = j0; a < j1; ++a) n_teamable += std::min(dev[a].w1, dev[a].w2) > team_min;
+        uint32_t cl_min = cluster_min;
+        if (n_teamable * kDpCluster <= 2u * (uint32_t)ctx->sm_count) cl_min = std::min(cluster_min, std::max(team_min, 256u));
+        auto cls = [&](uint32_t a) { const uint32_t w = std::min(dev[a].w1, dev[a].w2); return w > cl_min ? 2 : (w > team_min ? 1 : 0); };
         std::vector<uint32_t> order(m);
         std::iota(order.begin(), order.end(), j0);
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-            if (big(a) != big(b)) return big(a);
+            if (cls(a) != cls(b)) return cls(a) > cls(b);
             return (unsigned long long)dev[a].w1 * dev[a].w2 > (unsigned long long)dev[b].w1 * dev[b].w2;
         });
-        uint32_t n_big = 0;
-        while (n_big < m && big(order[n_big])) ++n_big;
+        uint32_t n_huge = 0, n_big = 0;
+        while (n_huge < m && cls(order[n_huge]) == 2) ++n_huge;
+        n_big = n_huge;
+        while (n_big < m && cls(order[n_big]) == 1) ++n_big;
 
         FB_TRY(S.d_jobs.reserve(sizeof(DpJobDev) * n));
         FB_TRY(S.d_meta.reserve(sizeof(DpMeta) * n));
@@ -702,15 +734,33 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
         k_dp_t<<<(unsigned)tblock[m], kTThreads, 0, st>>>(P);
         FB_CUDA(cudaGetLastError());
         ctx->launches += 2;
-        // `order` has the team-kernel jobs first (see the sort above)
-        if (n_big) {
+        // `order`: cluster jobs, then block jobs, then warp jobs (see the sort above)
+        if (n_huge) {
             DpParams Q = P;
-            Q.n_jobs = n_big;
+            Q.n_jobs = n_huge;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(n_huge * kDpCluster);
+            cfg.blockDim = dim3(kDpTeamWarps * 32);
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = kDpCluster;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            FB_CUDA(cudaLaunchKernelEx(&cfg, k_dp_fill<kDpTeamWarps, kDpCluster>, Q));
+            ctx->launches++;
+        }
+        if (n_big > n_huge) {
+            DpParams Q = P;
+            Q.order = P.order + n_huge;
+            Q.n_jobs = n_big - n_huge;
             switch (nw) {
-            case 2: k_dp_fill<2><<<n_big, 2 * 32, 0, st>>>(Q); break;
-            case 4: k_dp_fill<4><<<n_big, 4 * 32, 0, st>>>(Q); break;
-            case 16: k_dp_fill<16><<<n_big, 16 * 32, 0, st>>>(Q); break;
-            default: k_dp_fill<kDpTeamWarps><<<n_big, kDpTeamWarps * 32, 0, st>>>(Q); break;
+            case 2: k_dp_fill<2, 1><<<Q.n_jobs, 2 * 32, 0, st>>>(Q); break;
+            case 4: k_dp_fill<4, 1><<<Q.n_jobs, 4 * 32, 0, st>>>(Q); break;
+            case 16: k_dp_fill<16, 1><<<Q.n_jobs, 16 * 32, 0, st>>>(Q); break;
+            default: k_dp_fill<kDpTeamWarps, 1><<<Q.n_jobs, kDpTeamWarps * 32, 0, st>>>(Q); break;
             }
             FB_CUDA(cudaGetLastError());
             ctx->launches++;
@@ -719,7 +769,7 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
             DpParams Q = P;
             Q.order = P.order + n_big;
             Q.n_jobs = m - n_big;
-            k_dp_fill<1><<<(Q.n_jobs + kDpWarps - 1) / kDpWarps, kDpWarps * 32, 0, st>>>(Q);
+            k_dp_fill<1, 1><<<(Q.n_jobs + kDpWarps - 1) / kDpWarps, kDpWarps * 32, 0, st>>>(Q);
             FB_CUDA(cudaGetLastError());
             ctx->launches++;
         }

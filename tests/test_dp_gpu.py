@@ -121,6 +121,21 @@ def test_random_families(engine, seed, n, length, gaps):
         assert_same(r, pyoracle.dp_align(*rec["job"], g))
 
 
+@needs_ref
+def test_cluster_path(engine, monkeypatch):
+    """Very wide merges run on a thread-block cluster (8 blocks x 8 warps); force that path on ordinary sizes."""
+    rng = np.random.default_rng(21)
+    codes, off, lens = seqio.synth_family(48, 330, 21, sort_desc=False)
+    seqs = [seqio.decode(codes[int(o):int(o) + int(l)]) for o, l in zip(off, lens)]
+    merges = random_tree(48, rng)
+    g, recs = reference_merges(seqs, merges, threads=(1,), rng=rng)
+    monkeypatch.setenv("FAMSA_DP_CLUSTER_MIN", "200")
+    got = engine.dp_align_batch([r["job"] for r in recs], g, want_dirs=True)
+    check_against_reference(got, recs)
+    for r, rec in zip(got, recs):
+        assert_same(r, pyoracle.dp_align(*rec["job"], g))
+
+
 def test_tiny_and_degenerate(engine):
     """Width-1 profiles, 1 x many, without the reference (oracle only)."""
     rng = np.random.default_rng(3)
