@@ -225,3 +225,28 @@ def test_blockwise_triangle_copy(engine, monkeypatch):
     want = pyoracle.lcs_triangle(codes, offsets, lens)
     assert np.array_equal(engine.triangle(dtype=np.uint16), want)
     assert np.array_equal(engine.triangle(dtype=np.uint32), want)
+
+
+def test_concurrent_callers_share_one_context(engine, adeno):
+    """The reference gives every worker thread its own CLCSBP; here all workers may share one context (calls are
+    serialised inside the library).  Eight threads hammer rows() concurrently -- ctypes drops the GIL."""
+    import threading
+    n = len(adeno["lens"])
+    engine.upload(adeno["codes"], adeno["offsets"], adeno["lens"])
+    errors = []
+
+    def work(tid):
+        rng = np.random.default_rng(tid)
+        for _ in range(6):
+            refs = rng.permutation(n)[:3]
+            cols = rng.permutation(n)[:40]
+            got = engine.rows(refs, cols)
+            if not np.array_equal(got, adeno["lcs"][np.ix_(refs, cols)]):
+                errors.append(tid)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors
