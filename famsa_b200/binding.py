@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 EXPORTED_SYMBOLS = [
     "famsa_abi_version", "famsa_create", "famsa_destroy", "famsa_last_error", "famsa_kernel_launches",
     "famsa_lcs_upload", "famsa_lcs_n_seqs", "famsa_lcs_triangle", "famsa_lcs_triangle_device",
-    "famsa_lcs_rows", "famsa_lcs_rows_device", "famsa_lcs_assign", "famsa_transform_f64", "famsa_transform_f32",
+    "famsa_lcs_rows", "famsa_lcs_rows_device", "famsa_lcs_assign", "famsa_lcs_prim", "famsa_transform_f64", "famsa_transform_f32",
     "famsa_lcs_last_timing", "famsa_dp_align_batch", "famsa_dp_align_batch_device", "famsa_dp_last_timing",
 ]
 
@@ -66,6 +66,7 @@ def load_library() -> C.CDLL:
     lib.famsa_lcs_triangle_device.argtypes = [vp, u32, u32, vp, i32, vp]
     lib.famsa_lcs_rows.argtypes = [vp, vp, u32, vp, u32, vp, i32]
     lib.famsa_lcs_rows_device.argtypes = [vp, vp, u32, vp, u32, vp, i32, vp]
+    lib.famsa_lcs_prim.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.famsa_lcs_assign.argtypes = [vp, vp, u32, i32, vp, vp]
     lib.famsa_transform_f64.argtypes = [i32, u32, u32, u32]
     lib.famsa_transform_f64.restype = C.c_double
@@ -146,6 +147,14 @@ class Engine:
         self._check(self.lib.famsa_lcs_rows(self.h, _ptr(ref), len(ref), _ptr(cols), n_col, _ptr(buf),
                                             buf.dtype.itemsize))
         return buf[:len(ref) * n_col].reshape(len(ref), n_col)
+
+    def prim(self, kind: int = 0):
+        """MSTPrim's vertex loop on the device: (edge_from, edge_to, edge_dist, prim_order)."""
+        m = max(self.n - 1, 1)
+        f = np.zeros(m, dtype=np.int32); t = np.zeros(m, dtype=np.int32)
+        d = np.zeros(m, dtype=np.float64); o = np.zeros(max(self.n, 1), dtype=np.int32)
+        self._check(self.lib.famsa_lcs_prim(self.h, kind, _ptr(f), _ptr(t), _ptr(d), _ptr(o)))
+        return f[:self.n - 1], t[:self.n - 1], d[:self.n - 1], o[:self.n]
 
     def assign(self, seed_ids, kind: int = 0) -> tuple[np.ndarray, np.ndarray]:
         """FastTree<>::makeEvaluation's assignment loop: (assignments uint32[n], min_dist float32[n])."""

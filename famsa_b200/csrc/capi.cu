@@ -64,7 +64,8 @@ void famsa_destroy(famsa_ctx* ctx)
     cudaDeviceSynchronize();
     fb::LcsState& S = ctx->lcs;
     for (fb::DevBuf* b : {&S.d_perm, &S.d_invperm, &S.d_len_sorted, &S.d_code_off, &S.d_codes, &S.d_blob,
-                          &S.d_group_blob, &S.d_raw_codes, &S.d_raw_off, &S.d_raw_len, &S.d_flags, &S.d_pow075, &S.d_assign_lcs,
+                          &S.d_group_blob, &S.d_raw_codes, &S.d_raw_off, &S.d_raw_len, &S.d_flags, &S.d_pow075, &S.d_assign_lcs, &S.d_pow075_f64, &S.d_prim_tri, &S.d_prim_side, &S.d_prim_state,
+                          &S.d_prim_out, &S.d_prim_sideidx,
                           &S.d_assign, &S.d_mind, &S.d_tiles,
                           &S.d_res, &S.d_refpos, &S.d_ids_a, &S.d_ids_b, &S.d_out_stage, &S.d_masks64, &S.d_x64})
         b->release();
@@ -264,6 +265,20 @@ int famsa_lcs_rows(famsa_ctx* ctx, const uint32_t* ref_ids, uint32_t n_ref, cons
     if (rc) return rc;
     if (cells) FB_CUDA(cudaMemcpy(out, S.d_out_stage.p, cells * elem_bytes, cudaMemcpyDeviceToHost));
     return FAMSA_OK;
+}
+
+int famsa_lcs_prim(famsa_ctx* ctx, int distance_kind, int32_t* edge_from, int32_t* edge_to, double* edge_dist,
+                   int32_t* prim_order)
+{
+    FB_CHECK_CTX(ctx);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->lcs.n == 0) { set_error("famsa_lcs_upload has not been called"); return FAMSA_E_STATE; }
+    if (!prim_order || (ctx->lcs.n > 1 && (!edge_from || !edge_to || !edge_dist))) { set_error("NULL argument"); return FAMSA_E_INVALID; }
+    if (distance_kind != 0 && distance_kind != 1) { set_error("MSTPrim is instantiated for distance_kind 0 and 1 only"); return FAMSA_E_INVALID; }
+    FB_CUDA(cudaSetDevice(ctx->device));
+    int rc = fb::lcs_prim(ctx, distance_kind, edge_from, edge_to, edge_dist, prim_order);
+    if (rc) return rc;
+    return finish_timing(ctx);
 }
 
 int famsa_lcs_assign(famsa_ctx* ctx, const uint32_t* seed_ids, uint32_t n_seeds, int distance_kind, uint32_t* assignments,

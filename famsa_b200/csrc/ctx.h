@@ -51,7 +51,8 @@ struct LcsState {
     std::vector<uint32_t> h_quirky;    // caller ids whose masks contain an all-ones 64-bit word
     std::vector<uint32_t> h_long;      // caller ids longer than the tile kernel handles as mask side
     DevBuf d_perm, d_invperm, d_len_sorted, d_code_off, d_codes, d_blob, d_group_blob;
-    DevBuf d_raw_codes, d_raw_off, d_raw_len, d_flags, d_pow075, d_assign_lcs, d_assign, d_mind;
+    DevBuf d_raw_codes, d_raw_off, d_raw_len, d_flags, d_pow075, d_assign_lcs, d_assign, d_mind,
+        d_pow075_f64, d_prim_tri, d_prim_side, d_prim_state, d_prim_out, d_prim_sideidx;
     // per-call scratch
     DevBuf d_tiles, d_res, d_refpos, d_ids_a, d_ids_b, d_out_stage, d_masks64, d_x64;
     // last-call timing
@@ -89,10 +90,11 @@ int lcs_upload(famsa_ctx* ctx, const int8_t* codes, const uint64_t* offsets, con
                uint32_t n);
 int lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_out, int elem_bytes,
                  cudaStream_t stream, const uint32_t* bounds = nullptr, int n_blocks = 1,
-                 cudaEvent_t* block_events = nullptr);
+                 cudaEvent_t* block_events = nullptr, bool quirk_fixups = true);
 int lcs_rows(famsa_ctx* ctx, const uint32_t* d_ref_ids, const uint32_t* h_ref_ids, uint32_t n_ref,
              const uint32_t* d_col_ids, uint32_t n_col, void* d_out, int elem_bytes,
              cudaStream_t stream);
+int lcs_prim(famsa_ctx* ctx, int kind, int32_t* h_from, int32_t* h_to, double* h_dist, int32_t* h_order);
 int lcs_assign(famsa_ctx* ctx, const uint32_t* h_seed_ids, uint32_t n_seeds, int kind, uint32_t* h_assign,
                float* h_mind);
 // dp.cu

@@ -392,6 +392,110 @@ __global__ void k_assign(const void* __restrict__ lcs, int elem_bytes, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------------
+// MST-Prim vertex loop (MSTPrim<>::run_view, MSTPrim.cpp:280-549) on the resident LCS triangle
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ double transform_f64(int kind, uint32_t lcs, uint32_t len1, uint32_t len2,
+                                                const double* __restrict__ pow075, double never)
+{
+    const uint32_t indel_i = len1 + len2 - 2 * lcs;
+    if (!lcs) return never;                                  // nextafter(DBL_MAX, 0)
+    if (kind == 0) return __ddiv_rn(pow075[indel_i], (double)lcs);
+    return __ddiv_rn((double)indel_i, (double)lcs);
+}
+
+struct PrimState {                 // per sequence: best known connection to the tree
+    double dist;
+    unsigned long long key;        // ~ids_to_uint64(from, j)  (MSTPrim.h:432-439)
+};
+
+// One block runs the whole loop: n-1 steps of (relax every unvisited j against the current vertex, elect the
+// smallest pair).  The per-step work is n independent lookups, so one SM is enough up to ~1e5 sequences.
+// tri: true-LCS triangle in caller order; side rows hold the row-oriented values of the sequences whose LCS is
+// orientation dependent (dropped-carry corner): side_idx[v] = row in `side` or -1.
+__global__ void __launch_bounds__(1024) k_prim(const void* __restrict__ tri, int eb, uint32_t n,
+                                               const uint32_t* __restrict__ lens, const double* __restrict__ pow075,
+                                               int kind, double never, const int* __restrict__ side_idx,
+                                               const uint32_t* __restrict__ side, PrimState* __restrict__ st,
+                                               unsigned char* __restrict__ visited, int* __restrict__ out_from,
+                                               int* __restrict__ out_to, double* __restrict__ out_dist,
+                                               int* __restrict__ order)
+{
+    __shared__ double sh_d[32];
+    __shared__ unsigned long long sh_k[32];
+    __shared__ int sh_id[32];
+    __shared__ int sh_v;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t j = tid; j < n; j += blockDim.x) {
+        st[j].dist = 1.7976931348623157e308;        // numeric_limits<double>::max()
+        st[j].key = 0;
+        visited[j] = 0;
+        order[j] = (int)n;
+    }
+    if (tid == 0) { sh_v = 0; }
+    __syncthreads();
+    if (tid == 0) { visited[0] = 1; order[0] = 0; }
+    __syncthreads();
+    for (uint32_t step = 1; step < n; ++step) {
+        const uint32_t v = (uint32_t)sh_v;
+        const uint32_t lv = lens[v];
+        const int sv = side_idx[v];
+        double bd = 0.0;
+        unsigned long long bk = 0;
+        int bid = -1;
+        for (uint32_t j = tid; j < n; j += blockDim.x) {
+            if (visited[j]) continue;
+            uint32_t l;
+            if (sv >= 0) l = side[(size_t)sv * n + j];
+            else {
+                const uint32_t hi = v > j ? v : j, lo = v > j ? j : v;
+                const size_t at = (size_t)hi * (hi - 1) / 2 + lo;
+                l = eb == 2 ? static_cast<const uint16_t*>(tri)[at] : static_cast<const uint32_t*>(tri)[at];
+            }
+            const double d = transform_f64(kind, l, lv, lens[j], pow075, never);
+            double cd = st[j].dist;
+            unsigned long long ck = st[j].key;
+            if (d <= cd) {
+                const unsigned long long a = v < j ? v : j, b = v < j ? j : v;
+                const unsigned long long k = ~((a << 32) + b);
+                if (d < cd || k < ck) { cd = d; ck = k; st[j].dist = cd; st[j].key = ck; }     // pair <, given d <= cd
+            }
+            if (bid < 0 || cd < bd || (cd == bd && ck < bk)) { bd = cd; bk = ck; bid = (int)j; }
+        }
+        // block-wide minimum of (dist, key)
+        for (int o = 16; o; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
+            const int oid = __shfl_xor_sync(0xffffffffu, bid, o);
+            if (oid >= 0 && (bid < 0 || od < bd || (od == bd && ok < bk))) { bd = od; bk = ok; bid = oid; }
+        }
+        if (lane == 0) { sh_d[warp] = bd; sh_k[warp] = bk; sh_id[warp] = bid; }
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t nw = blockDim.x / 32;
+            bd = lane < nw ? sh_d[lane] : 0.0; bk = lane < nw ? sh_k[lane] : 0; bid = lane < nw ? sh_id[lane] : -1;
+            for (int o = 16; o; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                const int oid = __shfl_xor_sync(0xffffffffu, bid, o);
+                if (oid >= 0 && (bid < 0 || od < bd || (od == bd && ok < bk))) { bd = od; bk = ok; bid = oid; }
+            }
+            if (lane == 0) {
+                const unsigned long long packed = ~bk;                 // uint64_to_id (MSTPrim.h:441-450)
+                const int id1 = (int)(packed >> 32), id2 = (int)(packed & 0xffffffffull);
+                out_from[step - 1] = id1 < id2 ? id1 : id2;
+                out_to[step - 1] = id1 < id2 ? id2 : id1;
+                out_dist[step - 1] = bd;
+                order[bid] = (int)step;
+                visited[bid] = 1;
+                sh_v = bid;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 
@@ -610,7 +714,7 @@ static int exact_row(famsa_ctx* ctx, uint32_t row, const uint32_t* d_col_ids, ui
 // range) the work is issued block by block and block_events[b] is recorded after block b, so that a caller can
 // start copying finished blocks while later ones are still being computed; every tile list is uploaded up front.
 int lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_out, int elem_bytes, cudaStream_t st,
-                 const uint32_t* bounds, int n_blocks, cudaEvent_t* block_events)
+                 const uint32_t* bounds, int n_blocks, cudaEvent_t* block_events, bool quirk_fixups)
 {
     LcsState& S = ctx->lcs;
     const uint32_t n = S.n;
@@ -645,7 +749,8 @@ int lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_o
     P.rows_mode = 0;
     P.tri_base = (uint64_t)row_begin * (row_begin ? row_begin - 1 : 0) / 2;
     std::vector<uint32_t> special;      // rows the tile kernel may not answer for: dropped-carry and over-long rows
-    std::set_union(S.h_quirky.begin(), S.h_quirky.end(), S.h_long.begin(), S.h_long.end(), std::back_inserter(special));
+    if (quirk_fixups) std::set_union(S.h_quirky.begin(), S.h_quirky.end(), S.h_long.begin(), S.h_long.end(), std::back_inserter(special));
+    else special = S.h_long;         // true LCS everywhere: only the rows the tile kernel cannot reach
     FB_CUDA(cudaEventRecord(ctx->ev[1], st));
     size_t at = 0;
     for (int b = 0; b < n_blocks; ++b) {
@@ -739,6 +844,59 @@ int lcs_rows(famsa_ctx* ctx, const uint32_t* d_ref_ids, const uint32_t* h_ref_id
     (void)d_ref_ids;
     (void)n;
     FB_CUDA(cudaEventRecord(ctx->ev[3], st));
+    return FAMSA_OK;
+}
+
+int lcs_prim(famsa_ctx* ctx, int kind, int32_t* h_from, int32_t* h_to, double* h_dist, int32_t* h_order)
+{
+    LcsState& S = ctx->lcs;
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = S.n;
+    const int eb = S.max_len < 65536 ? 2 : 4;
+    const size_t pairs = (size_t)n * (n - 1) / 2;
+    FB_TRY(S.d_prim_tri.reserve(std::max<size_t>(pairs, 1) * eb));
+    // the true-LCS triangle (orientation-free) ...
+    FB_TRY(lcs_triangle(ctx, 0, n, S.d_prim_tri.p, eb, st, nullptr, 1, nullptr, /*quirk_fixups=*/false));
+    // ... plus, for the few sequences whose LCS depends on which side is the row, their own rows
+    std::vector<int> side_idx(n, -1);
+    for (size_t q = 0; q < S.h_quirky.size(); ++q) side_idx[S.h_quirky[q]] = (int)q;
+    FB_TRY(S.d_prim_sideidx.reserve(sizeof(int) * n));
+    FB_CUDA(cudaMemcpyAsync(S.d_prim_sideidx.p, side_idx.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    const uint32_t nq = (uint32_t)S.h_quirky.size();
+    FB_TRY(S.d_prim_side.reserve(std::max<size_t>((size_t)nq * n, 1) * sizeof(uint32_t)));
+    if (nq) {
+        FB_TRY(S.d_ids_a.reserve(sizeof(uint32_t) * nq));
+        FB_CUDA(cudaMemcpyAsync(S.d_ids_a.p, S.h_quirky.data(), sizeof(uint32_t) * nq, cudaMemcpyHostToDevice, st));
+        FB_TRY(lcs_rows(ctx, S.d_ids_a.as<uint32_t>(), S.h_quirky.data(), nq, nullptr, n, S.d_prim_side.p, 4, st));
+    }
+    {   // (double) pow(i, 0.75), host libm, like Transform<double, indel075_div_lcs>'s table
+        std::vector<double> pw((size_t)2 * S.max_len + 2);
+        for (size_t v = 0; v < pw.size(); ++v) pw[v] = pow((double)v, 0.75);
+        FB_TRY(S.d_pow075_f64.reserve(sizeof(double) * pw.size()));
+        FB_CUDA(cudaMemcpyAsync(S.d_pow075_f64.p, pw.data(), sizeof(double) * pw.size(), cudaMemcpyHostToDevice, st));
+        FB_CUDA(cudaStreamSynchronize(st));
+    }
+    FB_TRY(S.d_prim_state.reserve((sizeof(PrimState) + 1) * (size_t)n + 64));
+    FB_TRY(S.d_prim_out.reserve((sizeof(int) * 3 + sizeof(double)) * (size_t)n + 64));
+    PrimState* d_state = S.d_prim_state.as<PrimState>();
+    unsigned char* d_vis = reinterpret_cast<unsigned char*>(d_state + n);
+    double* d_dist = S.d_prim_out.as<double>();
+    int* d_from = reinterpret_cast<int*>(d_dist + n);
+    int* d_to = d_from + n;
+    int* d_order = d_to + n;
+    k_prim<<<1, 1024, 0, st>>>(S.d_prim_tri.p, eb, n, S.d_raw_len.as<uint32_t>(), S.d_pow075_f64.as<double>(), kind,
+                               nextafter(DBL_MAX, 0.0), S.d_prim_sideidx.as<int>(), S.d_prim_side.as<uint32_t>(), d_state,
+                               d_vis, d_from, d_to, d_dist, d_order);
+    FB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    FB_CUDA(cudaEventRecord(ctx->ev[3], st));
+    if (n > 1) {
+        FB_CUDA(cudaMemcpyAsync(h_from, d_from, sizeof(int) * (n - 1), cudaMemcpyDeviceToHost, st));
+        FB_CUDA(cudaMemcpyAsync(h_to, d_to, sizeof(int) * (n - 1), cudaMemcpyDeviceToHost, st));
+        FB_CUDA(cudaMemcpyAsync(h_dist, d_dist, sizeof(double) * (n - 1), cudaMemcpyDeviceToHost, st));
+    }
+    FB_CUDA(cudaMemcpyAsync(h_order, d_order, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaStreamSynchronize(st));
     return FAMSA_OK;
 }
 

@@ -111,6 +111,19 @@ int famsa_lcs_rows_device(famsa_ctx* ctx, const uint32_t* d_ref_ids, uint32_t n_
 int famsa_lcs_assign(famsa_ctx* ctx, const uint32_t* seed_ids, uint32_t n_seeds, int distance_kind,
                      uint32_t* assignments, float* min_dist);
 
+/* The default guide tree (-gt sl): the vertex loop of MSTPrim<>::run_view (src/tree/MSTPrim.cpp:280-549) on the
+ * device.  Per step: distances from the current vertex (as the row, seq0) to every unvisited sequence through
+ * Transform<double, distance>, the relaxation  s = {d, ~ids_to_uint64(v, j)};  if (d <= best[j].first && s < best[j])
+ * best[j] = s  (MSTPrim.cpp:492-503), and the election of the unvisited vertex with the smallest pair
+ * (:366-386); the reference's lower-bound pruning (:450-467) does not change results and is not needed.
+ * Runs on the LCS triangle kept in HBM, so no n^2 data leaves the device: the n-1 MST edges come back in Prim
+ * order -- edge k joins edge_from[k] < edge_to[k] at distance edge_dist[k] (positive; the reference stores the
+ * negated value) and was added with the (k+1)-th vertex -- plus prim_order[i], the visiting position of every
+ * sequence.  The caller hands them to the unchanged mst_to_dendogram (MSTPrim.cpp:784-833).
+ * distance_kind 0 (indel075_div_lcs) or 1 (indel_div_lcs), the two MSTPrim instantiations.  HOST pointers. */
+int famsa_lcs_prim(famsa_ctx* ctx, int distance_kind, int32_t* edge_from, int32_t* edge_to, double* edge_dist,
+                   int32_t* prim_order);
+
 /* Host-side Transform<T, Distance> (AbstractTreeGenerator.hpp:28-82), provided so bindings that
  * are not C++ get bit-identical distances.  kind: 0 indel075_div_lcs, 1 indel_div_lcs,
  * 2 pairwise_identity. */

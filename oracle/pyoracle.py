@@ -122,6 +122,8 @@ def ref() -> C.CDLL:
         lib.ref_lcs_row_ids.argtypes = [vp, u32, vp, u32, vp, C.c_int]
         lib.ref_lcs_triangle_mt.argtypes = [vp, u32, u32, C.c_int, C.c_int, vp, vp]
         lib.ref_lcs_triangle_mt.restype = C.c_double
+        lib.ref_mst_prim_tree.argtypes = [vp, C.c_int, vp]
+        lib.ref_mst_to_dendogram.argtypes = [C.c_int, vp, vp, vp, vp, vp]
         lib.ref_upgma_tree.argtypes = [vp, C.c_int, C.c_int, vp]
         lib.ref_upgma_tree_from_distances.argtypes = [vp, C.c_int, C.c_int, vp]
         lib.ref_transform_f64.argtypes = [C.c_int, u32, u32, u32]
@@ -157,6 +159,16 @@ def ref() -> C.CDLL:
         lib.ref_dp_align_pairs_mt.restype = C.c_double
         _ref = lib
     return _ref
+
+
+def mst_to_dendogram(edge_from, edge_to, edge_dist, prim_orders) -> np.ndarray:
+    """The reference's own mst_to_dendogram on external MST edges (Prim order)."""
+    n = len(prim_orders)
+    f = np.ascontiguousarray(edge_from, dtype=np.int32); t = np.ascontiguousarray(edge_to, dtype=np.int32)
+    d = np.ascontiguousarray(edge_dist, dtype=np.float64); o = np.ascontiguousarray(prim_orders, dtype=np.int32)
+    out = np.zeros((2 * n - 1, 2), dtype=np.int32)
+    ref().ref_mst_to_dendogram(n, _p(f), _p(t), _p(d), _p(o), _p(out))
+    return out
 
 
 def upgma_tree_from_distances(tri: np.ndarray, n: int, modified: bool = False) -> np.ndarray:
@@ -299,6 +311,12 @@ class RefSeqSet:
         out = np.zeros(max(len(ids), 1), dtype=np.uint32)
         self.lib.ref_lcs_row_ids(self.h, ref_id, _p(ids), len(ids), _p(out), isa)
         return out[:len(ids)]
+
+    def mst_prim_tree(self, n_threads: int = 2) -> np.ndarray:
+        """The reference's default (-gt sl) guide tree of this set: (2n-1, 2) child ids."""
+        out = np.zeros((2 * self.n - 1, 2), dtype=np.int32)
+        self.lib.ref_mst_prim_tree(self.h, n_threads, _p(out))
+        return out
 
     def upgma_tree(self, modified: bool = False, n_threads: int = 2) -> np.ndarray:
         """The reference's UPGMA guide tree of this set: (2n-1, 2) child ids, leaves are (-1, -1)."""

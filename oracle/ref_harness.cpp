@@ -35,6 +35,7 @@
 #include "tree/AbstractTreeGenerator.h"
 #include "tree/AbstractTreeGenerator.hpp"
 #include "tree/UPGMA.h"
+#include "tree/MSTPrim.h"
 #undef private
 #undef protected
 
@@ -79,6 +80,19 @@ template <class T> struct ConstructTraits;
 template <class C, class R, class A1, class A2, class A3, class A4, class A5>
 struct ConstructTraits<R (C::*)(A1, A2, A3, A4, A5)> {
     using elem_t = std::remove_reference_t<A4>;      // CProfile::dp_row_elem_t
+};
+
+// Same trick for MSTPrim<>::mst_to_dendogram (private) and its vector<mst_edge_t> argument.
+using PrimRef = MSTPrim<Distance::indel075_div_lcs>;
+auto stolen_mst_to_dendogram();
+template <auto M> struct StealPrimMember {
+    friend auto stolen_mst_to_dendogram() { return M; }
+};
+template struct StealPrimMember<&PrimRef::mst_to_dendogram>;
+template <class T> struct DendTraits;
+template <class C, class R, class A1, class A2, class A3>
+struct DendTraits<R (C::*)(A1, A2, A3)> {
+    using edges_t = std::remove_reference_t<A1>;     // std::vector<MSTPrim::mst_edge_t>
 };
 
 extern "C" {
@@ -203,6 +217,33 @@ void ref_upgma_tree_from_distances(const float* tri, int n, int modified, int* o
     tree.resize(n, std::make_pair<int, int>(-1, -1));
     if (modified) gen.computeTree<true>(d.data(), n, tree);
     else gen.computeTree<false>(d.data(), n, tree);
+    for (size_t i = 0; i < tree.size(); ++i) { out_pairs[2 * i] = tree[i].first; out_pairs[2 * i + 1] = tree[i].second; }
+}
+
+// (c) the reference's default guide tree: MSTPrim<indel075_div_lcs> end to end (MSTPrim.cpp:280-549 + 784-833)
+void ref_mst_prim_tree(void* h, int n_threads, int* out_pairs)
+{
+    auto* s = static_cast<SeqSet*>(h);
+    PrimRef gen(n_threads, instruction_set_t::avx2);
+    tree_structure tree;
+    gen(s->ptrs, tree);
+    for (size_t i = 0; i < tree.size(); ++i) { out_pairs[2 * i] = tree[i].first; out_pairs[2 * i + 1] = tree[i].second; }
+}
+
+// (d) the reference's own mst_to_dendogram (MSTPrim.cpp:784-833) on EXTERNAL MST edges given in Prim order:
+// edge k (k = 0..n-2) joins from[k] < to[k] at distance dist[k] and was found when the (k+1)-th vertex was added;
+// prim_orders[i] = position of sequence i in the Prim visiting order.
+void ref_mst_to_dendogram(int n, const int* from, const int* to, const double* dist, const int* prim_orders, int* out_pairs)
+{
+    PrimRef gen(1, instruction_set_t::avx2);
+    auto pmf = stolen_mst_to_dendogram();
+    typename DendTraits<decltype(pmf)>::edges_t edges;
+    edges.reserve(n);
+    for (int k = 0; k + 1 < n; ++k) edges.emplace_back(from[k], to[k], k + 1, -dist[k]);   // negated: MSTPrim.cpp:384
+    std::vector<int> orders(prim_orders, prim_orders + n);
+    tree_structure tree;
+    tree.resize(n, std::make_pair<int, int>(-1, -1));
+    (gen.*pmf)(edges, orders, tree);
     for (size_t i = 0; i < tree.size(); ++i) { out_pairs[2 * i] = tree[i].first; out_pairs[2 * i + 1] = tree[i].second; }
 }
 

@@ -250,3 +250,77 @@ def test_concurrent_callers_share_one_context(engine, adeno):
     for t in threads:
         t.join()
     assert not errors
+
+
+def _prim_restated(codes, offsets, lens, kind):
+    """MSTPrim<>::run_view's vertex loop (MSTPrim.cpp:280-549) restated with the oracle; validated against the
+    reference's own tree in test_gpu_prim_tree (kind 0) and used here for kind 1."""
+    n = len(lens)
+    lcs = pyoracle.lcs_rows(codes, offsets, lens, np.arange(n))          # lcs[v][j], v = row (seq0)
+    dist = np.full(n, np.finfo(np.float64).max)
+    key = np.zeros(n, dtype=np.uint64)
+    visited = np.zeros(n, dtype=bool)
+    order = np.full(n, n, dtype=np.int32)
+    full = np.uint64(0xFFFFFFFFFFFFFFFF)
+    v = 0
+    visited[0] = True
+    order[0] = 0
+    ef, et, ed = [], [], []
+    for step in range(1, n):
+        best = -1
+        for j in range(n):
+            if visited[j]:
+                continue
+            d = pyoracle.transform(kind, int(lcs[v, j]), int(lens[v]), int(lens[j]), True)
+            if d <= dist[j]:
+                a, b = (v, j) if v < j else (j, v)
+                k = full ^ np.uint64((a << 32) + b)
+                if d < dist[j] or k < key[j]:
+                    dist[j], key[j] = d, k
+            if best < 0 or dist[j] < dist[best] or (dist[j] == dist[best] and key[j] < key[best]):
+                best = j
+        p = int(full ^ key[best])
+        a, b = p >> 32, p & 0xFFFFFFFF
+        ef.append(min(a, b)); et.append(max(a, b)); ed.append(dist[best])
+        order[best] = step
+        visited[best] = True
+        v = best
+    return np.array(ef, np.int32), np.array(et, np.int32), np.array(ed), order
+
+
+@pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", ["family", "adeno", "quirky", "tiny"])
+def test_gpu_prim_tree(engine, adeno, case):
+    """Drop-in proof for the DEFAULT guide tree (-gt sl): famsa_lcs_prim's MST edges, passed to the reference's own
+    unmodified mst_to_dendogram, give exactly the tree MSTPrim<indel075_div_lcs> builds on the CPU."""
+    if case == "family":
+        codes, offsets, lens = seqio.synth_family(700, 130, seed=41)
+    elif case == "adeno":
+        order = sorted(range(len(adeno["lens"])), key=lambda i: (-int(adeno["lens"][i]), adeno["code_list"][i].tobytes()))
+        codes, offsets, lens = seqio.pack([adeno["code_list"][i] for i in order])      # FAMSA's own order (msa.cpp:245-256)
+    elif case == "quirky":
+        rng = np.random.default_rng(8)
+        cl = random_set(rng, 60, 60, 260, alphabet=3)
+        cl += [np.zeros(200, np.int8), np.zeros(130, np.int8), np.concatenate([np.ones(64, np.int8), np.zeros(70, np.int8)])]
+        cl.sort(key=lambda c: (-len(c), c.tobytes()))
+        codes, offsets, lens = seqio.pack(cl)
+    else:
+        codes, offsets, lens = seqio.pack([seqio.encode(s) for s in ["ACDEFGHIKL", "ACDEFGHIK", "ACDFGHIK"]])
+    n = len(lens)
+    engine.upload(codes, offsets, lens)
+    ef, et, ed, order = engine.prim(0)
+    letters = [seqio.decode(codes[int(o):int(o) + int(ln)]) for o, ln in zip(offsets, lens)]
+    want = pyoracle.RefSeqSet(letters).mst_prim_tree(3)
+    got = pyoracle.mst_to_dendogram(ef, et, ed, order)
+    assert np.array_equal(got, want)
+    assert sorted(order.tolist()) == list(range(n))
+
+
+def test_gpu_prim_edges_match_restatement(engine):
+    codes, offsets, lens = seqio.synth_family(90, 70, seed=43)
+    engine.upload(codes, offsets, lens)
+    for kind in (0, 1):
+        got = engine.prim(kind)
+        want = _prim_restated(codes, offsets, lens, kind)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
