@@ -27,6 +27,8 @@
 #include <cstring>
 #include <numeric>
 
+#include <cooperative_groups.h>
+
 #include "ctx.h"
 
 namespace fb {
@@ -409,65 +411,93 @@ struct PrimState {                 // per sequence: best known connection to the
     unsigned long long key;        // ~ids_to_uint64(from, j)  (MSTPrim.h:432-439)
 };
 
-// One block runs the whole loop: n-1 steps of (relax every unvisited j against the current vertex, elect the
-// smallest pair).  The per-step work is n independent lookups, so one SM is enough up to ~1e5 sequences.
+// Cooperative grid (one block per SM, all co-resident): per step every thread relaxes its own unvisited sequences
+// against the current vertex (one triangle lookup + one pow-table lookup each, all independent), blocks publish their
+// best (dist, key) pair, ONE grid-wide barrier, and every block reduces the published candidates itself, so all
+// blocks agree on the next vertex without a second barrier.  Candidate slots are double-buffered by step parity.
 // tri: true-LCS triangle in caller order; side rows hold the row-oriented values of the sequences whose LCS is
 // orientation dependent (dropped-carry corner): side_idx[v] = row in `side` or -1.
+struct PrimCand {
+    double dist;
+    unsigned long long key;
+    int id;
+    int pad;
+};
+
 __global__ void __launch_bounds__(1024) k_prim(const void* __restrict__ tri, int eb, uint32_t n,
                                                const uint32_t* __restrict__ lens, const double* __restrict__ pow075,
                                                int kind, double never, const int* __restrict__ side_idx,
                                                const uint32_t* __restrict__ side, PrimState* __restrict__ st,
-                                               unsigned char* __restrict__ visited, int* __restrict__ out_from,
-                                               int* __restrict__ out_to, double* __restrict__ out_dist,
-                                               int* __restrict__ order)
+                                               unsigned char* __restrict__ visited, PrimCand* __restrict__ cand,
+                                               int* __restrict__ out_from, int* __restrict__ out_to,
+                                               double* __restrict__ out_dist, int* __restrict__ order)
 {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
     __shared__ double sh_d[32];
     __shared__ unsigned long long sh_k[32];
     __shared__ int sh_id[32];
     __shared__ int sh_v;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (uint32_t j = tid; j < n; j += blockDim.x) {
+    const uint32_t gtid = blockIdx.x * blockDim.x + tid, gthreads = gridDim.x * blockDim.x;
+    const uint32_t nblk = gridDim.x;
+    auto better = [](double d, unsigned long long k, int id, double bd, unsigned long long bk, int bid) {
+        return id >= 0 && (bid < 0 || d < bd || (d == bd && k < bk));
+    };
+    for (uint32_t j = gtid; j < n; j += gthreads) {
         st[j].dist = 1.7976931348623157e308;        // numeric_limits<double>::max()
         st[j].key = 0;
-        visited[j] = 0;
-        order[j] = (int)n;
+        visited[j] = j == 0;
+        order[j] = j == 0 ? 0 : (int)n;
     }
-    if (tid == 0) { sh_v = 0; }
-    __syncthreads();
-    if (tid == 0) { visited[0] = 1; order[0] = 0; }
-    __syncthreads();
+    // the first sequence a thread owns lives in registers (with n <= gridDim.x * 1024 that is all of them)
+    const bool has0 = gtid < n;
+    const uint32_t len0 = has0 ? lens[gtid] : 0;
+    bool vis0 = gtid == 0;
+    double d0 = 1.7976931348623157e308;
+    unsigned long long k0 = 0;
+    uint32_t v = 0;
+    grid.sync();
     for (uint32_t step = 1; step < n; ++step) {
-        const uint32_t v = (uint32_t)sh_v;
         const uint32_t lv = lens[v];
         const int sv = side_idx[v];
         double bd = 0.0;
         unsigned long long bk = 0;
         int bid = -1;
-        for (uint32_t j = tid; j < n; j += blockDim.x) {
-            if (visited[j]) continue;
-            uint32_t l;
-            if (sv >= 0) l = side[(size_t)sv * n + j];
-            else {
-                const uint32_t hi = v > j ? v : j, lo = v > j ? j : v;
-                const size_t at = (size_t)hi * (hi - 1) / 2 + lo;
-                l = eb == 2 ? static_cast<const uint16_t*>(tri)[at] : static_cast<const uint32_t*>(tri)[at];
+        auto lookup = [&](uint32_t j) -> uint32_t {
+            if (sv >= 0) return side[(size_t)sv * n + j];
+            const uint32_t hi = v > j ? v : j, lo = v > j ? j : v;
+            const size_t at = (size_t)hi * (hi - 1) / 2 + lo;
+            return eb == 2 ? static_cast<const uint16_t*>(tri)[at] : static_cast<const uint32_t*>(tri)[at];
+        };
+        if (has0 && !vis0) {
+            const uint32_t j = gtid;
+            const double d = transform_f64(kind, lookup(j), lv, len0, pow075, never);
+            if (d <= d0) {
+                const unsigned long long a = v < j ? v : j, b = v < j ? j : v;
+                const unsigned long long k = ~((a << 32) + b);
+                if (d < d0 || k < k0) { d0 = d; k0 = k; }                                  // pair <, given d <= d0
             }
-            const double d = transform_f64(kind, l, lv, lens[j], pow075, never);
+            bd = d0; bk = k0; bid = (int)j;
+        }
+        for (uint32_t j = gtid + gthreads; j < n; j += gthreads) {                         // only when n > grid size
+            if (visited[j]) continue;
+            const double d = transform_f64(kind, lookup(j), lv, lens[j], pow075, never);
             double cd = st[j].dist;
             unsigned long long ck = st[j].key;
             if (d <= cd) {
                 const unsigned long long a = v < j ? v : j, b = v < j ? j : v;
                 const unsigned long long k = ~((a << 32) + b);
-                if (d < cd || k < ck) { cd = d; ck = k; st[j].dist = cd; st[j].key = ck; }     // pair <, given d <= cd
+                if (d < cd || k < ck) { cd = d; ck = k; st[j].dist = cd; st[j].key = ck; }
             }
-            if (bid < 0 || cd < bd || (cd == bd && ck < bk)) { bd = cd; bk = ck; bid = (int)j; }
+            if (better(cd, ck, (int)j, bd, bk, bid)) { bd = cd; bk = ck; bid = (int)j; }
         }
-        // block-wide minimum of (dist, key)
+        // block-wide minimum of (dist, key) ...
         for (int o = 16; o; o >>= 1) {
             const double od = __shfl_xor_sync(0xffffffffu, bd, o);
             const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
             const int oid = __shfl_xor_sync(0xffffffffu, bid, o);
-            if (oid >= 0 && (bid < 0 || od < bd || (od == bd && ok < bk))) { bd = od; bk = ok; bid = oid; }
+            if (better(od, ok, oid, bd, bk, bid)) { bd = od; bk = ok; bid = oid; }
         }
         if (lane == 0) { sh_d[warp] = bd; sh_k[warp] = bk; sh_id[warp] = bid; }
         __syncthreads();
@@ -478,20 +508,43 @@ __global__ void __launch_bounds__(1024) k_prim(const void* __restrict__ tri, int
                 const double od = __shfl_xor_sync(0xffffffffu, bd, o);
                 const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
                 const int oid = __shfl_xor_sync(0xffffffffu, bid, o);
-                if (oid >= 0 && (bid < 0 || od < bd || (od == bd && ok < bk))) { bd = od; bk = ok; bid = oid; }
+                if (better(od, ok, oid, bd, bk, bid)) { bd = od; bk = ok; bid = oid; }
             }
             if (lane == 0) {
-                const unsigned long long packed = ~bk;                 // uint64_to_id (MSTPrim.h:441-450)
-                const int id1 = (int)(packed >> 32), id2 = (int)(packed & 0xffffffffull);
-                out_from[step - 1] = id1 < id2 ? id1 : id2;
-                out_to[step - 1] = id1 < id2 ? id2 : id1;
-                out_dist[step - 1] = bd;
-                order[bid] = (int)step;
-                visited[bid] = 1;
+                PrimCand c; c.dist = bd; c.key = bk; c.id = bid; c.pad = 0;
+                cand[(step & 1) * nblk + blockIdx.x] = c;
+            }
+        }
+        // ... one grid barrier, then every block reduces the published candidates for itself
+        grid.sync();
+        if (warp == 0) {
+            bd = 0.0; bk = 0; bid = -1;
+            for (uint32_t b = lane; b < nblk; b += 32) {
+                const PrimCand c = cand[(step & 1) * nblk + b];
+                if (better(c.dist, c.key, c.id, bd, bk, bid)) { bd = c.dist; bk = c.key; bid = c.id; }
+            }
+            for (int o = 16; o; o >>= 1) {
+                const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+                const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, o);
+                const int oid = __shfl_xor_sync(0xffffffffu, bid, o);
+                if (better(od, ok, oid, bd, bk, bid)) { bd = od; bk = ok; bid = oid; }
+            }
+            if (lane == 0) {
                 sh_v = bid;
+                if (blockIdx.x == 0) {
+                    const unsigned long long packed = ~bk;             // uint64_to_id (MSTPrim.h:441-450)
+                    const int id1 = (int)(packed >> 32), id2 = (int)(packed & 0xffffffffull);
+                    out_from[step - 1] = id1 < id2 ? id1 : id2;
+                    out_to[step - 1] = id1 < id2 ? id2 : id1;
+                    out_dist[step - 1] = bd;
+                    order[bid] = (int)step;
+                }
+                if ((uint32_t)bid >= gthreads && (uint32_t)bid % gthreads / blockDim.x == blockIdx.x) visited[bid] = 1;   // its owner block
             }
         }
         __syncthreads();
+        v = (uint32_t)sh_v;
+        if (v == gtid) vis0 = true;
     }
 }
 
@@ -884,10 +937,20 @@ int lcs_prim(famsa_ctx* ctx, int kind, int32_t* h_from, int32_t* h_to, double* h
     int* d_from = reinterpret_cast<int*>(d_dist + n);
     int* d_to = d_from + n;
     int* d_order = d_to + n;
-    k_prim<<<1, 1024, 0, st>>>(S.d_prim_tri.p, eb, n, S.d_raw_len.as<uint32_t>(), S.d_pow075_f64.as<double>(), kind,
-                               nextafter(DBL_MAX, 0.0), S.d_prim_sideidx.as<int>(), S.d_prim_side.as<uint32_t>(), d_state,
-                               d_vis, d_from, d_to, d_dist, d_order);
-    FB_CUDA(cudaGetLastError());
+    {
+        int per_sm = 0;
+        FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prim, 1024, 0));
+        const uint32_t nblk = std::max(1u, std::min((uint32_t)(ctx->sm_count * std::max(per_sm, 1)), (n + 1023) / 1024));
+        FB_TRY(S.d_prim_cand.reserve(sizeof(PrimCand) * 2 * nblk));
+        const void* a_tri = S.d_prim_tri.p; int a_eb = eb; uint32_t a_n = n;
+        const uint32_t* a_len = S.d_raw_len.as<uint32_t>(); const double* a_pow = S.d_pow075_f64.as<double>();
+        int a_kind = kind; double a_never = nextafter(DBL_MAX, 0.0);
+        const int* a_sidx = S.d_prim_sideidx.as<int>(); const uint32_t* a_side = S.d_prim_side.as<uint32_t>();
+        PrimCand* a_cand = S.d_prim_cand.as<PrimCand>();
+        void* args[] = {&a_tri, &a_eb, &a_n, &a_len, &a_pow, &a_kind, &a_never, &a_sidx, &a_side, &d_state, &d_vis,
+                        &a_cand, &d_from, &d_to, &d_dist, &d_order};
+        FB_CUDA(cudaLaunchCooperativeKernel((void*)k_prim, dim3(nblk), dim3(1024), args, 0, st));
+    }
     ctx->launches++;
     FB_CUDA(cudaEventRecord(ctx->ev[3], st));
     if (n > 1) {
