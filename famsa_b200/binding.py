@@ -13,7 +13,11 @@ EXPORTED_SYMBOLS = [
     "famsa_lcs_upload", "famsa_lcs_n_seqs", "famsa_lcs_triangle", "famsa_lcs_triangle_device",
     "famsa_lcs_rows", "famsa_lcs_rows_device", "famsa_lcs_assign", "famsa_lcs_prim", "famsa_transform_f64", "famsa_transform_f32",
     "famsa_lcs_last_timing", "famsa_dp_align_batch", "famsa_dp_align_batch_device", "famsa_dp_last_timing",
+    "famsa_prof_set_scoring", "famsa_prof_put", "famsa_prof_merge_batch", "famsa_prof_get", "famsa_prof_drop",
+    "famsa_prof_last_timing", "famsa_prof_stats",
 ]
+
+PROF_LEAF = 0x80000000            # FAMSA_PROF_LEAF
 
 
 class DpProfile(C.Structure):
@@ -28,6 +32,10 @@ class DpResult(C.Structure):
     _fields_ = [("total_score", C.c_int64), ("last", C.c_int64 * 3), ("path_offset", C.c_uint64),
                 ("dirs_offset", C.c_uint64), ("path_len", C.c_uint32), ("rows_width", C.c_uint32),
                 ("cols_width", C.c_uint32), ("swapped", C.c_uint8), ("variant", C.c_uint8), ("pad", C.c_uint8 * 2)]
+
+
+class ProfMerge(C.Structure):
+    _fields_ = [("child1", C.c_uint32), ("child2", C.c_uint32)]
 
 
 class FamsaError(RuntimeError):
@@ -73,6 +81,13 @@ def load_library() -> C.CDLL:
     lib.famsa_transform_f32.argtypes = [i32, u32, u32, u32]
     lib.famsa_transform_f32.restype = C.c_float
     lib.famsa_lcs_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(u64)]
+    lib.famsa_prof_set_scoring.argtypes = [vp, vp]
+    lib.famsa_prof_put.argtypes = [vp, vp, u32, vp]
+    lib.famsa_prof_merge_batch.argtypes = [vp, vp, u32, vp, vp, vp, vp, u64]
+    lib.famsa_prof_get.argtypes = [vp, u32, C.POINTER(u32), C.POINTER(u32), vp, vp]
+    lib.famsa_prof_drop.argtypes = [vp, vp, u32]
+    lib.famsa_prof_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.famsa_prof_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     lib.famsa_dp_align_batch.argtypes = [vp, vp, u32, vp, vp, vp, vp]
     lib.famsa_dp_align_batch_device.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp]
     lib.famsa_dp_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(u64)]
@@ -211,6 +226,70 @@ class Engine:
         self._check(self.lib.famsa_dp_align_batch_device(self.h, C.byref(job_array), n, _ptr(g), C.c_void_p(d_results),
                                                          C.c_void_p(d_path), C.c_void_p(d_dirs) if d_dirs else None,
                                                          C.c_void_p(stream) if stream else None))
+
+    # ---- resident profiles (ConstructProfile's merge part on the device)
+    def prof_set_scoring(self, score_matrix):
+        sm = np.ascontiguousarray(score_matrix, dtype=np.int64)
+        assert sm.shape == (24, 24)
+        self._check(self.lib.famsa_prof_set_scoring(self.h, _ptr(sm)))
+
+    def prof_put(self, profiles) -> list[int]:
+        """profiles: list of (scores (W+1,32) int64, counters (W+1,32) int32, card).  Returns resident ids."""
+        n = len(profiles)
+        arr = (DpProfile * max(n, 1))()
+        keep = []
+        for k, (s, c, card) in enumerate(profiles):
+            s = np.ascontiguousarray(s, dtype=np.int64); c = np.ascontiguousarray(c, dtype=np.int32)
+            keep += [s, c]
+            arr[k] = DpProfile(s.ctypes.data, c.ctypes.data, s.shape[0] - 1, card)
+        ids = np.zeros(max(n, 1), dtype=np.uint32)
+        self._check(self.lib.famsa_prof_put(self.h, C.byref(arr), n, _ptr(ids)))
+        return [int(x) for x in ids[:n]]
+
+    def prof_merge_batch(self, merges, gaps, widths):
+        """merges: list of (child1, child2) -- resident ids or PROF_LEAF | sequence id; widths: matching list of
+        (W1, W2) (the caller tracks them: leaf length or an earlier merge's path length).  Consumes resident
+        children.  Returns (merged ids, list of dict(path, total, last, swapped, variant))."""
+        n = len(merges)
+        arr = (ProfMerge * max(n, 1))()
+        for k, (a, b) in enumerate(merges):
+            arr[k] = ProfMerge(int(a), int(b))
+        cap = int(sum(w1 + w2 for w1, w2 in widths))
+        g = np.ascontiguousarray(gaps, dtype=np.int64)
+        res = (DpResult * max(n, 1))()
+        path = np.zeros(max(cap, 1), dtype=np.uint8)
+        ids = np.zeros(max(n, 1), dtype=np.uint32)
+        self._check(self.lib.famsa_prof_merge_batch(self.h, C.byref(arr), n, _ptr(g), _ptr(ids), C.byref(res), _ptr(path), cap))
+        out = []
+        for k in range(n):
+            r = res[k]
+            out.append(dict(path=path[r.path_offset:r.path_offset + r.path_len].copy(), total=int(r.total_score),
+                            last=np.array(list(r.last), dtype=np.int64), swapped=bool(r.swapped), variant=int(r.variant)))
+        return [int(x) for x in ids[:n]], out
+
+    def prof_get(self, pid: int, tables: bool = True):
+        """(scores, counters, card) of a resident profile, or (width, card) with tables=False."""
+        w, k = C.c_uint32(), C.c_uint32()
+        self._check(self.lib.famsa_prof_get(self.h, pid, C.byref(w), C.byref(k), None, None))
+        if not tables:
+            return w.value, k.value
+        s = np.zeros((w.value + 1, 32), dtype=np.int64); c = np.zeros((w.value + 1, 32), dtype=np.int32)
+        self._check(self.lib.famsa_prof_get(self.h, pid, None, None, _ptr(s), _ptr(c)))
+        return s, c, k.value
+
+    def prof_drop(self, ids):
+        a = np.ascontiguousarray(ids, dtype=np.uint32)
+        self._check(self.lib.famsa_prof_drop(self.h, _ptr(a), len(a)))
+
+    def prof_last_timing(self) -> tuple[float, float]:
+        t, m = C.c_float(), C.c_float()
+        self._check(self.lib.famsa_prof_last_timing(self.h, C.byref(t), C.byref(m)))
+        return t.value, m.value
+
+    def prof_stats(self) -> tuple[int, int]:
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self.lib.famsa_prof_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def dp_last_timing(self) -> tuple[float, float, int]:
         t, m, p = C.c_float(), C.c_float(), C.c_uint64()

@@ -69,6 +69,7 @@ void famsa_destroy(famsa_ctx* ctx)
                           &S.d_assign, &S.d_mind, &S.d_tiles,
                           &S.d_res, &S.d_refpos, &S.d_ids_a, &S.d_ids_b, &S.d_out_stage, &S.d_masks64, &S.d_x64})
         b->release();
+    fb::prof_release_all(ctx);
     fb::DpState& D = ctx->dp;
     if (D.h_pinned) cudaFreeHost(D.h_pinned);
     for (fb::DevBuf* b : {&D.d_jobs, &D.d_order, &D.d_scratch, &D.d_dirs, &D.d_tables, &D.d_results, &D.d_path, &D.d_meta, &D.d_tblock, &D.d_T})
@@ -351,6 +352,72 @@ int famsa_dp_last_timing(const famsa_ctx* ctx, float* total_ms, float* kernel_ms
     if (total_ms) *total_ms = ctx->dp.last_total_ms;
     if (kernel_ms) *kernel_ms = ctx->dp.last_kernel_ms;
     if (n_cells) *n_cells = ctx->dp.last_cells;
+    return FAMSA_OK;
+}
+
+// ------------------------------------------------------------------ resident profiles
+
+int famsa_prof_set_scoring(famsa_ctx* ctx, const int64_t score_matrix[24 * 24])
+{
+    FB_CHECK_CTX(ctx);
+    if (!score_matrix) { set_error("NULL argument"); return FAMSA_E_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    FB_CUDA(cudaSetDevice(ctx->device));
+    return fb::prof_set_scoring(ctx, score_matrix);
+}
+
+int famsa_prof_put(famsa_ctx* ctx, const famsa_dp_profile* profiles, uint32_t n, uint32_t* ids_out)
+{
+    FB_CHECK_CTX(ctx);
+    if (n && (!profiles || !ids_out)) { set_error("NULL argument"); return FAMSA_E_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    FB_CUDA(cudaSetDevice(ctx->device));
+    return fb::prof_put(ctx, profiles, n, ids_out);
+}
+
+int famsa_prof_merge_batch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t n, const int64_t gaps[4],
+                           uint32_t* merged_ids_out, famsa_dp_result* results, uint8_t* path_buf, uint64_t path_cap)
+{
+    FB_CHECK_CTX(ctx);
+    if (n && (!merges || !gaps || !merged_ids_out || !results || !path_buf)) { set_error("NULL argument"); return FAMSA_E_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    FB_CUDA(cudaSetDevice(ctx->device));
+    int rc = fb::prof_merge_batch(ctx, merges, n, gaps, merged_ids_out, results, path_buf, path_cap);
+    if (rc || !n) return rc;
+    return dp_finish_timing(ctx);
+}
+
+int famsa_prof_get(famsa_ctx* ctx, uint32_t id, uint32_t* width, uint32_t* card, int64_t* scores, int32_t* counters)
+{
+    FB_CHECK_CTX(ctx);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    FB_CUDA(cudaSetDevice(ctx->device));
+    return fb::prof_get(ctx, id, width, card, scores, counters);
+}
+
+int famsa_prof_drop(famsa_ctx* ctx, const uint32_t* ids, uint32_t n)
+{
+    FB_CHECK_CTX(ctx);
+    if (n && !ids) { set_error("NULL argument"); return FAMSA_E_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    FB_CUDA(cudaSetDevice(ctx->device));
+    return fb::prof_drop(ctx, ids, n);
+}
+
+int famsa_prof_last_timing(famsa_ctx* ctx, float* total_ms, float* construct_ms)
+{
+    FB_CHECK_CTX(ctx);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    FB_CUDA(cudaSetDevice(ctx->device));
+    return fb::prof_last_timing(ctx, total_ms, construct_ms);
+}
+
+int famsa_prof_stats(famsa_ctx* ctx, uint64_t* n_live, uint64_t* resident_bytes)
+{
+    FB_CHECK_CTX(ctx);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n_live) *n_live = ctx->prof.n_live;
+    if (resident_bytes) *resident_bytes = ctx->prof.resident_bytes;
     return FAMSA_OK;
 }
 

@@ -68,6 +68,31 @@ struct DpState {
     float last_total_ms = 0.f, last_kernel_ms = 0.f;
 };
 
+// Profiles kept resident in HBM between the levels of the guide tree (prof.cu).
+struct ProfEntry {
+    long long* scores = nullptr;   // (width+1) x 32 int64
+    int* counters = nullptr;       // (width+1) x 32 int32
+    uint32_t width = 0, card = 0;
+    int slab = -1;
+    bool live = false;
+};
+struct ProfSlab {
+    void* p = nullptr;
+    size_t bytes = 0;
+    uint32_t live = 0;             // resident profiles still inside
+};
+struct ProfState {
+    std::vector<ProfEntry> entries;
+    std::vector<uint32_t> free_ids;
+    std::vector<ProfSlab> slabs;
+    std::vector<int> free_slabs;
+    bool has_scoring = false, pool_ready = false;
+    DevBuf d_sm, d_leaf, d_leafdesc, d_results, d_path, d_cjobs;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    uint64_t resident_bytes = 0, n_live = 0;
+    bool timing_valid = false;
+};
+
 } // namespace fb
 
 struct famsa_ctx {
@@ -82,6 +107,7 @@ struct famsa_ctx {
     int sm_count = 0;
     fb::LcsState lcs;
     fb::DpState dp;
+    fb::ProfState prof;
 };
 
 namespace fb {
@@ -102,4 +128,13 @@ int dp_run_host(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int6
                 uint8_t* path_buf, uint8_t* dirs_buf);
 int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int64_t gaps[4],
                   famsa_dp_result* d_results, uint8_t* d_path, uint8_t* d_dirs, cudaStream_t st);
+// prof.cu
+int prof_set_scoring(famsa_ctx* ctx, const int64_t* sm);
+int prof_put(famsa_ctx* ctx, const famsa_dp_profile* profs, uint32_t n, uint32_t* ids);
+int prof_merge_batch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t n, const int64_t gaps[4], uint32_t* merged_ids,
+                     famsa_dp_result* results, uint8_t* path_buf, uint64_t path_cap);
+int prof_get(famsa_ctx* ctx, uint32_t id, uint32_t* width, uint32_t* card, int64_t* scores, int32_t* counters);
+int prof_drop(famsa_ctx* ctx, const uint32_t* ids, uint32_t n);
+int prof_last_timing(famsa_ctx* ctx, float* total_ms, float* construct_ms);
+void prof_release_all(famsa_ctx* ctx);
 } // namespace fb

@@ -1,0 +1,483 @@
+// Resident profiles: leaf materialisation and ConstructProfile's merge part on the device.
+//
+// What the reference does per merge (src/core/profile.cpp:784-1002) is one sequential walk over the traceback
+// path that (a) adds the children's columns into the merged profile (InsertColumn :1107-1111), (b) for an H / V
+// step inserts a column of gaps into the row / column child (InsertGaps :1005-1050) whose open / ext / term_open /
+// term_ext split comes from SolveGapsProblemWhenStarting / WhenContinuing (:1146-1220 / :1114-1143), and (c) turns
+// "open" into "ext" in the child column right of a freshly started gap run (the n_gap_to_transfer bookkeeping).
+//
+// None of that carries state further than one run of equal directions, so here every merged column is built
+// independently (one warp per column, lane = one of the 32 rows of CProfileValues):
+//   * i_k / j_k, the child columns consumed up to merged column k, are prefix counts over the path;
+//   * a gap column's split depends only on whether it starts its run (path[k-2] != path[k-1]) and on the child's
+//     counters at src and src+1.  For a continued run the reference's "values at left" recurrence collapses after
+//     one step to  term_ext = TO[src+1] + TO[src] + TE[src],  ext = card - term_ext,  open = term_open = 0
+//     (interior) or term_ext = card (src == 0 or src == width);
+//   * the transfer into a consumed child column is pending exactly when the previous step was a gap in that child:
+//     term_transfer = TO[col], transfer = GO[col] (0 when the run sat before the child's first column);
+//     it moves GO->GE, TO->TE and adds transfer*(ge-go) + term_transfer*(te-to) to the 24 residue scores.
+//   The sums GO+GE and TO+TE that later gap starts read from an already adjusted column are invariant under (c),
+//   which is what makes the columns independent.
+// tests/test_prof_gpu.py compares this kernel with a CPU restatement of the reference's sequential walk and with the
+// reference's own ConstructProfile.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "ctx.h"
+
+namespace fb {
+
+#define FB_TRY(expr)                      \
+    do {                                  \
+        int rc__ = (expr);                \
+        if (rc__ != FAMSA_OK) return rc__; \
+    } while (0)
+
+namespace {
+
+constexpr int kRows = 32;                 // NO_SYMBOLS, defs.h:69
+constexpr int kGO = 25, kGE = 26, kTE = 27, kTO = 28, kGAP = 30, kNAA = 24;   // defs.h:62-74
+constexpr int kConThreads = 256, kConTile = 64;
+constexpr size_t kColBytes = kRows * (sizeof(long long) + sizeof(int));        // 384 B per profile column
+
+struct LeafDesc {
+    uint32_t seq;
+    long long* scores;
+    int* counters;
+};
+
+// One block per leaf: CalculateCounters + CalculateScores for a profile of one ungapped sequence
+// (profile.cpp:101-217): column c >= 1 holds counter 1 at its residue, the residue's substitution row in
+// scores[0..23] and the four gap costs; column 0 holds card(=1) x gap costs.
+__global__ void __launch_bounds__(256) k_prof_leaf(const LeafDesc* __restrict__ leaves, const int8_t* __restrict__ codes,
+                                                   const uint64_t* __restrict__ off, const uint32_t* __restrict__ len,
+                                                   const long long* __restrict__ sm, long long go, long long ge,
+                                                   long long to, long long te)
+{
+    const LeafDesc L = leaves[blockIdx.x];
+    const uint32_t n = len[L.seq];
+    const int8_t* s = codes + off[L.seq];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long gapv = lane == kGO ? go : lane == kGE ? ge : lane == kTE ? te : lane == kTO ? to : 0;
+    for (uint32_t c = warp; c <= n; c += 8) {
+        long long sc = gapv;
+        int cn = 0;
+        if (c) {
+            const int sym = s[c - 1];
+            cn = lane == sym;
+            if (lane < kNAA) sc = sm[sym * kNAA + lane];
+        }
+        L.scores[(size_t)c * kRows + lane] = sc;
+        L.counters[(size_t)c * kRows + lane] = cn;
+    }
+}
+
+struct ConJob {
+    const long long* sr; const int* cr;    // row child (ConstructProfile's profile1)
+    const long long* sc; const int* cc;    // column child (profile2)
+    long long* os; int* oc;                // merged profile
+    const uint8_t* path;
+    uint32_t wr, wc, cardr, cardc, W, tile0;
+};
+
+struct GapSplit { int o, e, to, te; };
+
+// Column of gaps inserted into a child (counters `c`, width `w`, `card` members) after its column `src`.
+// col / nxt: this lane's counters of columns src and src+1 (nxt = 0 past the end).
+__device__ __forceinline__ GapSplit gap_split(int col, int nxt, uint32_t src, uint32_t w, int card, bool starts)
+{
+    const int go_s = __shfl_sync(0xffffffffu, col, kGO), ge_s = __shfl_sync(0xffffffffu, col, kGE);
+    const int to_s = __shfl_sync(0xffffffffu, col, kTO), te_s = __shfl_sync(0xffffffffu, col, kTE);
+    const int to_n = __shfl_sync(0xffffffffu, nxt, kTO);
+    GapSplit g{0, 0, 0, 0};
+    if (starts) {
+        if (src == 0) g.to = card;
+        else if (src >= w) { g.te = to_s + te_s; g.to = card - g.te; }
+        else { g.to = to_n; g.te = to_s + te_s; g.e = go_s + ge_s; g.o = card - g.e - g.to - g.te; }
+    } else {
+        if (src == 0 || src == w) g.te = card;
+        else { g.te = to_n + to_s + te_s; g.e = card - g.te; }
+    }
+    return g;
+}
+
+__global__ void __launch_bounds__(kConThreads) k_prof_construct(const ConJob* __restrict__ jobs, uint32_t n_jobs,
+                                                                long long go, long long ge, long long to, long long te)
+{
+    // block -> (job, tile of kConTile merged columns)
+    uint32_t lo = 0, hi = n_jobs;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (jobs[mid].tile0 <= blockIdx.x) lo = mid; else hi = mid;
+    }
+    const ConJob J = jobs[lo];
+    const uint32_t k0 = (blockIdx.x - J.tile0) * kConTile;          // first merged column of the tile (0 = column 0)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    __shared__ uint32_t s_cnt[2][kConThreads / 32];
+    __shared__ uint8_t s_dir[kConTile + 1];                         // s_dir[t] = path[k0 + t - 2]  (dir of column k0+t-1)
+    __shared__ uint32_t s_nh[kConTile], s_nv[kConTile];
+
+    // H / V counts over the path entries of the columns before the tile: path[0 .. k0-2]
+    const uint32_t before = k0 ? k0 - 1 : 0;
+    uint32_t nh = 0, nv = 0;
+    for (uint32_t p = threadIdx.x; p < before; p += kConThreads) {
+        const uint8_t d = J.path[p];
+        nh += d == 1; nv += d == 2;
+    }
+    for (int o = 16; o; o >>= 1) { nh += __shfl_xor_sync(0xffffffffu, nh, o); nv += __shfl_xor_sync(0xffffffffu, nv, o); }
+    if (lane == 0) { s_cnt[0][warp] = nh; s_cnt[1][warp] = nv; }
+    if (threadIdx.x <= kConTile) {
+        const long long p = (long long)k0 + threadIdx.x - 2;
+        s_dir[threadIdx.x] = (p >= 0 && p < (long long)J.W) ? J.path[p] : 0;      // "previous" of the first column is D
+    }
+    __syncthreads();
+    nh = nv = 0;
+    for (int w = 0; w < kConThreads / 32; ++w) { nh += s_cnt[0][w]; nv += s_cnt[1][w]; }
+    if (threadIdx.x < kConTile) {
+        // inclusive counts up to and including the direction of column k0 + threadIdx.x
+        uint32_t a = nh, b = nv;
+        for (uint32_t u = (k0 ? 0 : 1); u <= threadIdx.x; ++u) { a += s_dir[u + 1] == 1; b += s_dir[u + 1] == 2; }
+        s_nh[threadIdx.x] = a; s_nv[threadIdx.x] = b;
+    }
+    __syncthreads();
+
+    const long long tr_open = ge - go, tr_term = te - to;
+    for (int t = warp; t < kConTile; t += kConThreads / 32) {
+        const uint32_t k = k0 + t;
+        if (k > J.W) break;
+        long long os = 0;
+        int oc = 0;
+        if (k == 0) {                                               // profile.cpp:998-1001
+            const long long tot = (long long)J.cardr + J.cardc;
+            os = lane == kGO ? go * tot : lane == kGE ? ge * tot : lane == kTO ? to * tot : lane == kTE ? te * tot : 0;
+        } else {
+            const int d = s_dir[t + 1], prev = s_dir[t];
+            const uint32_t i = k - s_nh[t], j = k - s_nv[t];        // child columns consumed after this step
+            if (d != 1) {                                           // D or V: the row child's column i
+                const int c = J.cr[(size_t)i * kRows + lane];
+                long long s = J.sr[(size_t)i * kRows + lane];
+                int tt = __shfl_sync(0xffffffffu, c, kTO), tg = __shfl_sync(0xffffffffu, c, kGO);
+                if (prev != 1) tt = tg = 0;
+                if (i == 1) tg = 0;                                 // the run sat before the first column: terminal only
+                oc += c + (lane == kGE ? tg : lane == kGO ? -tg : lane == kTE ? tt : lane == kTO ? -tt : 0);
+                if (lane < kNAA) s += tg * tr_open + tt * tr_term;
+                os += s;
+            }
+            if (d != 2) {                                           // D or H: the column child's column j
+                const int c = J.cc[(size_t)j * kRows + lane];
+                long long s = J.sc[(size_t)j * kRows + lane];
+                int tt = __shfl_sync(0xffffffffu, c, kTO), tg = __shfl_sync(0xffffffffu, c, kGO);
+                if (prev != 2) tt = tg = 0;
+                if (j == 1) tg = 0;
+                oc += c + (lane == kGE ? tg : lane == kGO ? -tg : lane == kTE ? tt : lane == kTO ? -tt : 0);
+                if (lane < kNAA) s += tg * tr_open + tt * tr_term;
+                os += s;
+            }
+            if (d != 0) {                                           // a column of gaps in the row (H) / column (V) child
+                const bool isH = d == 1;
+                const int* cg = isH ? J.cr : J.cc;
+                const uint32_t src = isH ? i : j, w = isH ? J.wr : J.wc;
+                const int card = (int)(isH ? J.cardr : J.cardc);
+                const int col = cg[(size_t)src * kRows + lane];
+                const int nxt = src < w ? cg[(size_t)(src + 1) * kRows + lane] : 0;
+                const GapSplit g = gap_split(col, nxt, src, w, card, prev != d);
+                oc += lane == kGO ? g.o : lane == kGE ? g.e : lane == kTO ? g.to : lane == kTE ? g.te : lane == kGAP ? card : 0;
+                if (lane < kNAA) os += g.o * go + g.e * ge + g.to * to + g.te * te;
+            }
+        }
+        J.os[(size_t)k * kRows + lane] = os;
+        J.oc[(size_t)k * kRows + lane] = oc;
+    }
+}
+
+size_t table_bytes(uint32_t width) { return ((size_t)width + 1) * kColBytes; }
+
+int ensure_pool(famsa_ctx* ctx)
+{
+    ProfState& P = ctx->prof;
+    if (P.pool_ready) return FAMSA_OK;
+    cudaMemPool_t pool;
+    FB_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+    unsigned long long keep = ~0ull;                                // slabs are recycled by the pool, never trimmed
+    FB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    for (auto& e : P.ev) FB_CUDA(cudaEventCreate(&e));
+    P.pool_ready = true;
+    return FAMSA_OK;
+}
+
+int new_slab(famsa_ctx* ctx, size_t bytes, int* out)
+{
+    ProfState& P = ctx->prof;
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(bytes, 256), ctx->stream);
+    if (e != cudaSuccess) {
+        set_error(std::string("cudaMallocAsync(") + std::to_string(bytes) + ") for resident profiles failed: " + cudaGetErrorString(e));
+        return FAMSA_E_NOMEM;
+    }
+    int id;
+    if (!P.free_slabs.empty()) { id = P.free_slabs.back(); P.free_slabs.pop_back(); }
+    else { id = (int)P.slabs.size(); P.slabs.emplace_back(); }
+    P.slabs[id].p = p; P.slabs[id].bytes = bytes; P.slabs[id].live = 0;
+    P.resident_bytes += bytes;
+    *out = id;
+    return FAMSA_OK;
+}
+
+uint32_t new_entry(ProfState& P)
+{
+    if (!P.free_ids.empty()) { const uint32_t id = P.free_ids.back(); P.free_ids.pop_back(); return id; }
+    P.entries.emplace_back();
+    return (uint32_t)P.entries.size() - 1;
+}
+
+// Carves one profile out of slab `slab` at *cursor.
+void place(ProfState& P, uint32_t id, int slab, size_t* cursor, uint32_t width, uint32_t card)
+{
+    ProfEntry& e = P.entries[id];
+    char* base = static_cast<char*>(P.slabs[slab].p) + *cursor;
+    e.scores = reinterpret_cast<long long*>(base);
+    e.counters = reinterpret_cast<int*>(base + ((size_t)width + 1) * kRows * sizeof(long long));
+    e.width = width; e.card = card; e.slab = slab; e.live = true;
+    *cursor += table_bytes(width);                                  // multiple of 384: keeps 128-byte alignment
+    ++P.slabs[slab].live;
+    ++P.n_live;
+}
+
+int release_entry(famsa_ctx* ctx, uint32_t id)
+{
+    ProfState& P = ctx->prof;
+    ProfEntry& e = P.entries[id];
+    e.live = false;
+    --P.n_live;
+    ProfSlab& s = P.slabs[e.slab];
+    if (--s.live == 0) {
+        FB_CUDA(cudaFreeAsync(s.p, ctx->stream));                   // stream-ordered: after the kernels that read it
+        P.resident_bytes -= s.bytes;
+        s.p = nullptr; s.bytes = 0;
+        P.free_slabs.push_back(e.slab);
+    }
+    e.slab = -1;
+    P.free_ids.push_back(id);
+    return FAMSA_OK;
+}
+
+int check_id(const ProfState& P, uint32_t id, const char* what)
+{
+    if (id >= P.entries.size() || !P.entries[id].live) {
+        set_error(std::string(what) + ": " + std::to_string(id) + " is not a resident profile");
+        return FAMSA_E_INVALID;
+    }
+    return FAMSA_OK;
+}
+
+} // namespace
+
+int prof_set_scoring(famsa_ctx* ctx, const int64_t* sm)
+{
+    ProfState& P = ctx->prof;
+    FB_TRY(ensure_pool(ctx));
+    FB_TRY(P.d_sm.reserve(sizeof(long long) * kNAA * kNAA));
+    FB_CUDA(cudaMemcpyAsync(P.d_sm.p, sm, sizeof(long long) * kNAA * kNAA, cudaMemcpyHostToDevice, ctx->stream));
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    P.has_scoring = true;
+    return FAMSA_OK;
+}
+
+int prof_put(famsa_ctx* ctx, const famsa_dp_profile* profs, uint32_t n, uint32_t* ids)
+{
+    ProfState& P = ctx->prof;
+    FB_TRY(ensure_pool(ctx));
+    if (!n) return FAMSA_OK;
+    size_t bytes = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        if (!profs[k].scores || !profs[k].counters || !profs[k].width || !profs[k].card) {
+            set_error("famsa_prof_put: profile " + std::to_string(k) + " is empty");
+            return FAMSA_E_INVALID;
+        }
+        bytes += table_bytes(profs[k].width);
+    }
+    int slab;
+    FB_TRY(new_slab(ctx, bytes, &slab));
+    size_t cur = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint32_t id = new_entry(P);
+        place(P, id, slab, &cur, profs[k].width, profs[k].card);
+        const size_t cols = (size_t)profs[k].width + 1;
+        FB_CUDA(cudaMemcpyAsync(P.entries[id].scores, profs[k].scores, cols * kRows * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        FB_CUDA(cudaMemcpyAsync(P.entries[id].counters, profs[k].counters, cols * kRows * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        ids[k] = id;
+    }
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FAMSA_OK;
+}
+
+int prof_merge_batch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t n, const int64_t gaps[4], uint32_t* merged_ids,
+                     famsa_dp_result* results, uint8_t* path_buf, uint64_t path_cap)
+{
+    ProfState& P = ctx->prof;
+    LcsState& L = ctx->lcs;
+    FB_TRY(ensure_pool(ctx));
+    P.timing_valid = false;
+    if (!n) return FAMSA_OK;
+    cudaStream_t st = ctx->stream;
+
+    // resolve the children; leaves get scratch tables for the duration of the call
+    std::vector<famsa_dp_job> jobs(n);
+    std::vector<LeafDesc> leaves;
+    std::vector<std::pair<uint32_t, int>> leaf_slot;                 // (job, side) per leaf, in `leaves` order
+    std::vector<uint8_t> seen(P.entries.size(), 0);
+    size_t leaf_bytes = 0;
+    uint64_t path_need = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        for (int side = 0; side < 2; ++side) {
+            const uint32_t c = side ? merges[k].child2 : merges[k].child1;
+            famsa_dp_profile& p = side ? jobs[k].p2 : jobs[k].p1;
+            if (c & FAMSA_PROF_LEAF) {
+                const uint32_t seq = c & ~FAMSA_PROF_LEAF;
+                if (seq >= L.n) { set_error("famsa_prof_merge_batch: leaf " + std::to_string(seq) + " was not uploaded (famsa_lcs_upload)"); return FAMSA_E_INVALID; }
+                if (!P.has_scoring) { set_error("famsa_prof_merge_batch: leaves need famsa_prof_set_scoring first"); return FAMSA_E_INVALID; }
+                p.width = L.h_len_sorted[L.h_invperm[seq]];
+                p.card = 1;
+                if (!p.width) { set_error("famsa_prof_merge_batch: leaf " + std::to_string(seq) + " is empty"); return FAMSA_E_INVALID; }
+                leaves.push_back(LeafDesc{seq, nullptr, nullptr});
+                leaf_slot.emplace_back(k, side);
+                leaf_bytes += table_bytes(p.width);
+            } else {
+                FB_TRY(check_id(P, c, "famsa_prof_merge_batch"));
+                if (seen[c]) { set_error("famsa_prof_merge_batch: profile " + std::to_string(c) + " is used twice"); return FAMSA_E_INVALID; }
+                seen[c] = 1;
+                const ProfEntry& e = P.entries[c];
+                p.scores = reinterpret_cast<const int64_t*>(e.scores); p.counters = e.counters; p.width = e.width; p.card = e.card;
+            }
+        }
+        path_need += (uint64_t)jobs[k].p1.width + jobs[k].p2.width;
+    }
+    if (path_need > path_cap) {
+        set_error("famsa_prof_merge_batch: path_buf holds " + std::to_string(path_cap) + " bytes, " + std::to_string(path_need) + " needed");
+        return FAMSA_E_INVALID;
+    }
+
+    FB_CUDA(cudaEventRecord(P.ev[0], st));
+    if (!leaves.empty()) {
+        FB_TRY(P.d_leaf.reserve(leaf_bytes));
+        FB_TRY(P.d_leafdesc.reserve(sizeof(LeafDesc) * leaves.size()));
+        size_t cur = 0;
+        for (size_t a = 0; a < leaves.size(); ++a) {
+            famsa_dp_profile& p = leaf_slot[a].second ? jobs[leaf_slot[a].first].p2 : jobs[leaf_slot[a].first].p1;
+            char* base = P.d_leaf.as<char>() + cur;
+            leaves[a].scores = reinterpret_cast<long long*>(base);
+            leaves[a].counters = reinterpret_cast<int*>(base + ((size_t)p.width + 1) * kRows * sizeof(long long));
+            p.scores = reinterpret_cast<const int64_t*>(leaves[a].scores);
+            p.counters = leaves[a].counters;
+            cur += table_bytes(p.width);
+        }
+        FB_CUDA(cudaMemcpyAsync(P.d_leafdesc.p, leaves.data(), sizeof(LeafDesc) * leaves.size(), cudaMemcpyHostToDevice, st));
+        k_prof_leaf<<<(unsigned)leaves.size(), 256, 0, st>>>(P.d_leafdesc.as<LeafDesc>(), L.d_raw_codes.as<int8_t>(),
+                                                             L.d_raw_off.as<uint64_t>(), L.d_raw_len.as<uint32_t>(),
+                                                             P.d_sm.as<long long>(), gaps[0], gaps[1], gaps[2], gaps[3]);
+        FB_CUDA(cudaGetLastError());
+        ++ctx->launches;
+    }
+
+    // DP + traceback on the resident tables (dp.cu)
+    FB_TRY(P.d_results.reserve(sizeof(famsa_dp_result) * n));
+    FB_TRY(P.d_path.reserve(std::max<uint64_t>(path_need, 64)));
+    FB_TRY(dp_run_device(ctx, jobs.data(), n, gaps, P.d_results.as<famsa_dp_result>(), P.d_path.as<uint8_t>(), nullptr, st));
+    FB_CUDA(cudaMemcpyAsync(results, P.d_results.p, sizeof(famsa_dp_result) * n, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaMemcpyAsync(path_buf, P.d_path.p, path_need, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaStreamSynchronize(st));                             // the merged widths size the new tables
+
+    // merged tables: one slab per call
+    size_t bytes = 0;
+    for (uint32_t k = 0; k < n; ++k) bytes += table_bytes(results[k].path_len);
+    int slab;
+    FB_TRY(new_slab(ctx, bytes, &slab));
+    std::vector<ConJob> cj(n);
+    size_t cur = 0;
+    uint32_t tiles = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const famsa_dp_result& r = results[k];
+        const famsa_dp_profile& R = r.swapped ? jobs[k].p2 : jobs[k].p1;
+        const famsa_dp_profile& C = r.swapped ? jobs[k].p1 : jobs[k].p2;
+        const uint32_t id = new_entry(P);
+        place(P, id, slab, &cur, r.path_len, R.card + C.card);
+        merged_ids[k] = id;
+        ConJob& j = cj[k];
+        j.sr = reinterpret_cast<const long long*>(R.scores); j.cr = R.counters;
+        j.sc = reinterpret_cast<const long long*>(C.scores); j.cc = C.counters;
+        j.os = P.entries[id].scores; j.oc = P.entries[id].counters;
+        j.path = P.d_path.as<uint8_t>() + r.path_offset;
+        j.wr = R.width; j.wc = C.width; j.cardr = R.card; j.cardc = C.card; j.W = r.path_len; j.tile0 = tiles;
+        tiles += (r.path_len + 1 + kConTile - 1) / kConTile;
+    }
+    FB_TRY(P.d_cjobs.reserve(sizeof(ConJob) * n));
+    FB_CUDA(cudaMemcpyAsync(P.d_cjobs.p, cj.data(), sizeof(ConJob) * n, cudaMemcpyHostToDevice, st));
+    FB_CUDA(cudaEventRecord(P.ev[1], st));
+    k_prof_construct<<<tiles, kConThreads, 0, st>>>(P.d_cjobs.as<ConJob>(), n, gaps[0], gaps[1], gaps[2], gaps[3]);
+    FB_CUDA(cudaGetLastError());
+    ++ctx->launches;
+    FB_CUDA(cudaEventRecord(P.ev[2], st));
+    P.timing_valid = true;
+
+    // the children are consumed (msa.cpp:406-407); frees are ordered after the construct kernel
+    for (uint32_t k = 0; k < n; ++k)
+        for (uint32_t c : {merges[k].child1, merges[k].child2})
+            if (!(c & FAMSA_PROF_LEAF)) FB_TRY(release_entry(ctx, c));
+    // cj (pageable) was handed to an async copy: make sure it has been consumed before it goes out of scope
+    FB_CUDA(cudaEventSynchronize(P.ev[1]));
+    return FAMSA_OK;
+}
+
+int prof_get(famsa_ctx* ctx, uint32_t id, uint32_t* width, uint32_t* card, int64_t* scores, int32_t* counters)
+{
+    ProfState& P = ctx->prof;
+    FB_TRY(check_id(P, id, "famsa_prof_get"));
+    const ProfEntry& e = P.entries[id];
+    if (width) *width = e.width;
+    if (card) *card = e.card;
+    const size_t cells = ((size_t)e.width + 1) * kRows;
+    if (scores) FB_CUDA(cudaMemcpyAsync(scores, e.scores, cells * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (counters) FB_CUDA(cudaMemcpyAsync(counters, e.counters, cells * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (scores || counters) FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return FAMSA_OK;
+}
+
+int prof_drop(famsa_ctx* ctx, const uint32_t* ids, uint32_t n)
+{
+    ProfState& P = ctx->prof;
+    for (uint32_t k = 0; k < n; ++k) FB_TRY(check_id(P, ids[k], "famsa_prof_drop"));
+    for (uint32_t k = 0; k < n; ++k) {
+        if (!P.entries[ids[k]].live) { set_error("famsa_prof_drop: profile listed twice"); return FAMSA_E_INVALID; }
+        FB_TRY(release_entry(ctx, ids[k]));
+    }
+    return FAMSA_OK;
+}
+
+int prof_last_timing(famsa_ctx* ctx, float* total_ms, float* construct_ms)
+{
+    ProfState& P = ctx->prof;
+    if (!P.timing_valid) { set_error("no famsa_prof_merge_batch has run"); return FAMSA_E_INVALID; }
+    FB_CUDA(cudaEventSynchronize(P.ev[2]));
+    float a = 0.f, b = 0.f;
+    FB_CUDA(cudaEventElapsedTime(&a, P.ev[0], P.ev[2]));
+    FB_CUDA(cudaEventElapsedTime(&b, P.ev[1], P.ev[2]));
+    if (total_ms) *total_ms = a;
+    if (construct_ms) *construct_ms = b;
+    return FAMSA_OK;
+}
+
+void prof_release_all(famsa_ctx* ctx)
+{
+    ProfState& P = ctx->prof;
+    for (ProfSlab& s : P.slabs)
+        if (s.p) cudaFreeAsync(s.p, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    for (DevBuf* b : {&P.d_sm, &P.d_leaf, &P.d_leafdesc, &P.d_results, &P.d_path, &P.d_cjobs}) b->release();
+    for (auto& e : P.ev)
+        if (e) cudaEventDestroy(e);
+    P = ProfState();
+}
+
+} // namespace fb

@@ -198,6 +198,51 @@ int famsa_dp_align_batch_device(famsa_ctx* ctx, const famsa_dp_job* h_jobs_with_
  * launch stream), and the number of DP cells (sum of rows_width * cols_width). */
 int famsa_dp_last_timing(const famsa_ctx* ctx, float* total_ms, float* kernel_ms, uint64_t* n_cells);
 
+/* ---------------------------------------------------------------------------------------------
+ * Resident profiles: ConstructProfile's merge part on the device.
+ *
+ * Replaces, for a whole level of the guide tree, CProfile::Align + the table-building half of
+ * CProfile::ConstructProfile (src/core/profile.cpp:244-305 and :784-1002: InsertColumn :1107-1111,
+ * InsertGaps :1005-1050, SolveGapsProblemWhenStarting/Continuing :1114-1220, column 0 :998-1001).
+ * scores/counters of every profile stay in HBM between levels; per merge only the traceback path
+ * (<= W1+W2 bytes) returns to the host, where FinalizeGaps (profile.cpp:1053-1104) applies its H runs
+ * to the members of the row profile and its V runs to the members of the column profile.
+ * Leaves are materialised on the device from the sequences of famsa_lcs_upload
+ * (CProfile::CalculateCountersScores for one sequence, profile.cpp:101-231).
+ */
+#define FAMSA_PROF_LEAF 0x80000000u   /* child = FAMSA_PROF_LEAF | sequence id (caller order of famsa_lcs_upload) */
+
+typedef struct {
+    uint32_t child1, child2;  /* the two arguments of CProfile::Align, in call order: resident profile id or leaf */
+} famsa_prof_merge;
+
+/* CParams::score_matrix (src/core/params.h), 24 x 24 row-major, needed to materialise leaves. */
+int famsa_prof_set_scoring(famsa_ctx* ctx, const int64_t score_matrix[24 * 24]);
+
+/* Uploads n host profiles (same layout as famsa_dp_profile for famsa_dp_align_batch) as resident ones. */
+int famsa_prof_put(famsa_ctx* ctx, const famsa_dp_profile* profiles, uint32_t n, uint32_t* ids_out);
+
+/* Aligns and merges n independent pairs.  Resident children are consumed (as ComputeAlignment deletes
+ * them, msa.cpp:406-407).  merged_ids_out[k] is the resident id of merge k's profile (width =
+ * results[k].path_len, card = sum of the children's).  results/path_buf as in famsa_dp_align_batch
+ * (job k's path at path_offset = sum_{m<k}(W1_m + W2_m)); path_cap = bytes available in path_buf. */
+int famsa_prof_merge_batch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t n, const int64_t gaps[4],
+                           uint32_t* merged_ids_out, famsa_dp_result* results, uint8_t* path_buf, uint64_t path_cap);
+
+/* width/card of a resident profile; scores ((width+1)*32 int64) / counters ((width+1)*32 int32) are
+ * copied to the host when non-NULL. */
+int famsa_prof_get(famsa_ctx* ctx, uint32_t id, uint32_t* width, uint32_t* card, int64_t* scores, int32_t* counters);
+
+/* Frees resident profiles that will not be merged (e.g. the root once the alignment is done). */
+int famsa_prof_drop(famsa_ctx* ctx, const uint32_t* ids, uint32_t n);
+
+/* Device time of the most recent famsa_prof_merge_batch: whole call and the construct kernel alone;
+ * the DP part is reported by famsa_dp_last_timing. */
+int famsa_prof_last_timing(famsa_ctx* ctx, float* total_ms, float* construct_ms);
+
+/* Number of resident profiles and the HBM they occupy. */
+int famsa_prof_stats(famsa_ctx* ctx, uint64_t* n_live, uint64_t* resident_bytes);
+
 #ifdef __cplusplus
 }
 #endif

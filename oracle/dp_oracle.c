@@ -259,3 +259,124 @@ int dp_oracle_align(const dp_oracle_profile *p1, const dp_oracle_profile *p2, co
     *variant = var;
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Merge part of ConstructProfile: given the traceback path, build the merged profile's
+ * scores/counters and the gap-run lists that FinalizeGaps applies to the members of either child.
+ * Follows profile.cpp:784-1002 (the walk over the path), :1005-1050 (InsertGaps), :1107-1111
+ * (InsertColumn), :1114-1143 / :1146-1220 (SolveGapsProblemWhenContinuing / WhenStarting), written the
+ * way the reference runs it: one sequential walk that carries the pending "open becomes ext" transfers
+ * and mutates (a private copy of) the children's tables.  R = rows of the DP matrix (ConstructProfile's
+ * profile1), C = columns (profile2); path = direction_t bytes in forward order (path[1..width]).
+ *
+ * Pinned by tests/test_oracle_dp.py against the reference's own ConstructProfile (oracle/_ref) on every
+ * merge of the adeno_fiber / hemopexin guide trees and random families.
+ * out_scores/out_counters: (plen+1) x 32.  gaps1/gaps2: (first column, run length) pairs, at most plen each.
+ */
+typedef struct { int32_t to_transfer, term_to_transfer, o_left, e_left, to_left, te_left; } walk_side;
+
+static void apply_transfer(int64_t *s, int32_t *c, uint32_t col, walk_side *w, const int64_t g[4])
+{
+    if (!w->to_transfer && !w->term_to_transfer) return;
+    c[(size_t)col * NSYM + GE] += w->to_transfer;       c[(size_t)col * NSYM + GO] -= w->to_transfer;
+    c[(size_t)col * NSYM + TE] += w->term_to_transfer;  c[(size_t)col * NSYM + TO] -= w->term_to_transfer;
+    const int64_t cost = w->to_transfer * (g[1] - g[0]) + w->term_to_transfer * (g[3] - g[2]);
+    for (int k = 0; k < 24; ++k) s[(size_t)col * NSYM + k] += cost;
+    w->to_transfer = w->term_to_transfer = 0;
+}
+
+int dp_oracle_construct(const dp_oracle_profile *R, const dp_oracle_profile *Cc, const uint8_t *path, uint32_t plen,
+                        const int64_t gaps[4], int64_t *out_scores, int32_t *out_counters,
+                        uint32_t *gaps1, uint32_t *n_gaps1, uint32_t *gaps2, uint32_t *n_gaps2)
+{
+    const size_t n1 = ((size_t)R->width + 1) * NSYM, n2 = ((size_t)Cc->width + 1) * NSYM;
+    int64_t *s1 = malloc(n1 * 8), *s2 = malloc(n2 * 8);
+    int32_t *c1 = malloc(n1 * 4), *c2 = malloc(n2 * 4);
+    if (!s1 || !s2 || !c1 || !c2) return -1;
+    memcpy(s1, R->scores, n1 * 8); memcpy(c1, R->counters, n1 * 4);
+    memcpy(s2, Cc->scores, n2 * 8); memcpy(c2, Cc->counters, n2 * 4);
+    memset(out_scores, 0, ((size_t)plen + 1) * NSYM * 8);
+    memset(out_counters, 0, ((size_t)plen + 1) * NSYM * 4);
+    walk_side w1 = {0}, w2 = {0};
+    uint32_t i = 0, j = 0, run = 0;
+    *n_gaps1 = *n_gaps2 = 0;
+    int prev = DIR_D;
+    for (uint32_t k = 1; k <= plen; ++k) {
+        const int dir = path[k - 1];
+        const int next = k < plen ? path[k] : -1;          /* the reference appends a V that never continues a run */
+        int64_t *os = out_scores + (size_t)k * NSYM;
+        int32_t *oc = out_counters + (size_t)k * NSYM;
+        if (dir == DIR_D) {
+            ++i; ++j;
+            apply_transfer(s1, c1, i, &w1, gaps);
+            apply_transfer(s2, c2, j, &w2, gaps);
+            w1.o_left = w1.e_left = w1.to_left = w1.te_left = 0;
+            w2.o_left = w2.e_left = w2.to_left = w2.te_left = 0;
+            for (int r = 0; r < NSYM; ++r) {
+                oc[r] += c1[(size_t)i * NSYM + r] + c2[(size_t)j * NSYM + r];
+                os[r] += s1[(size_t)i * NSYM + r] + s2[(size_t)j * NSYM + r];
+            }
+        } else {
+            /* gap column inserted into G (rows side for H, columns side for V); the other child supplies a column */
+            const int isH = dir == DIR_H;
+            const dp_oracle_profile *G = isH ? R : Cc;
+            int32_t *cg = isH ? c1 : c2;
+            walk_side *wg = isH ? &w1 : &w2;
+            const uint32_t src = isH ? i : j, W = G->width;
+            const int32_t size = (int32_t)G->card;
+            int32_t o = 0, e = 0, to = 0, te = 0;
+            if (prev == dir) {                              /* SolveGapsProblemWhenContinuing */
+                if (src == W || src == 0) te += size;
+                else {
+                    te += wg->to_left; te += wg->te_left;
+                    e = wg->o_left; e += wg->e_left;
+                    o = size - e - te;
+                }
+            } else {                                        /* SolveGapsProblemWhenStarting */
+                if (src == 0) {
+                    to += size;
+                    wg->term_to_transfer = cg[(size_t)(src + 1) * NSYM + TO];
+                } else if (src >= W) {
+                    const int32_t cnt = cg[(size_t)src * NSYM + TO] + cg[(size_t)src * NSYM + TE];
+                    te = cnt; to += size - cnt;
+                } else {
+                    to += cg[(size_t)(src + 1) * NSYM + TO];
+                    wg->term_to_transfer = to;
+                    te += cg[(size_t)src * NSYM + TO]; te += cg[(size_t)src * NSYM + TE];
+                    e = cg[(size_t)src * NSYM + GO]; e += cg[(size_t)src * NSYM + GE];
+                    o = cg[(size_t)(src + 1) * NSYM + GO];
+                    wg->to_transfer += o;
+                    o = size - e - to - te;
+                }
+            }
+            wg->o_left = o; wg->e_left = e; wg->to_left = to; wg->te_left = te;
+            /* InsertGaps: run-length list + the gap column's contribution */
+            ++run;
+            if (!(next == dir)) {
+                uint32_t *lst = isH ? gaps1 : gaps2;
+                uint32_t *cnt = isH ? n_gaps1 : n_gaps2;
+                lst[2 * *cnt] = k + 1 - run; lst[2 * *cnt + 1] = run; ++*cnt;
+                run = 0;
+            }
+            const int64_t cost = o * gaps[0] + e * gaps[1] + to * gaps[2] + te * gaps[3];
+            oc[GO] += o; oc[GE] += e; oc[TO] += to; oc[TE] += te; oc[30] += size;
+            for (int r = 0; r < 24; ++r) os[r] += cost;
+            /* the other child's next column, after its own pending transfer */
+            if (isH) {
+                apply_transfer(s2, c2, j + 1, &w2, gaps);
+                ++j;
+                for (int r = 0; r < NSYM; ++r) { oc[r] += c2[(size_t)j * NSYM + r]; os[r] += s2[(size_t)j * NSYM + r]; }
+            } else {
+                apply_transfer(s1, c1, i + 1, &w1, gaps);
+                ++i;
+                for (int r = 0; r < NSYM; ++r) { oc[r] += c1[(size_t)i * NSYM + r]; os[r] += s1[(size_t)i * NSYM + r]; }
+            }
+        }
+        prev = dir;
+    }
+    const int64_t tot = (int64_t)R->card + Cc->card;        /* profile.cpp:998-1001 */
+    out_scores[GO] = gaps[0] * tot; out_scores[GE] = gaps[1] * tot;
+    out_scores[TO] = gaps[2] * tot; out_scores[TE] = gaps[3] * tot;
+    free(s1); free(s2); free(c1); free(c2);
+    return (i == R->width && j == Cc->width) ? 0 : -2;
+}

@@ -44,6 +44,7 @@ def oracle() -> C.CDLL:
         lib.lcs_oracle_transform_f32.argtypes = [C.c_int, u32, u32, u32]
         lib.lcs_oracle_transform_f32.restype = C.c_float
         lib.dp_oracle_align.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        lib.dp_oracle_construct.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, vp, vp]
         _oracle = lib
     return _oracle
 
@@ -72,6 +73,29 @@ def dp_align(scores1, counters1, card1, scores2, counters2, card2, gaps, score_m
     wr, wc = (w2, w1) if sw.value else (w1, w2)
     return dict(path=path[:plen.value].copy(), total=total.value, last=last, swapped=bool(sw.value),
                 variant=var.value, dirs=dirs.reshape(wr + 1, wc + 1))
+
+
+def dp_construct(rows_prof, cols_prof, path, gaps):
+    """Oracle version of ConstructProfile's merge part.  rows_prof / cols_prof = (scores, counters, card) of the
+    DP matrix's row / column profile (i.e. after the orientation swap); path = forward direction bytes.
+    Returns (scores (W+1,32) int64, counters (W+1,32) int32, gap runs of the row profile's members (m,2),
+    gap runs of the column profile's members (m,2)) -- runs are (first merged column, length)."""
+    lib = oracle()
+    s1 = np.ascontiguousarray(rows_prof[0], dtype=np.int64); c1 = np.ascontiguousarray(rows_prof[1], dtype=np.int32)
+    s2 = np.ascontiguousarray(cols_prof[0], dtype=np.int64); c2 = np.ascontiguousarray(cols_prof[1], dtype=np.int32)
+    p1 = DpProfile(s1.ctypes.data, c1.ctypes.data, s1.shape[0] - 1, int(rows_prof[2]))
+    p2 = DpProfile(s2.ctypes.data, c2.ctypes.data, s2.shape[0] - 1, int(cols_prof[2]))
+    path = np.ascontiguousarray(path, dtype=np.uint8)
+    w = len(path)
+    g = np.ascontiguousarray(gaps, dtype=np.int64)
+    os_ = np.zeros((w + 1, 32), dtype=np.int64); oc = np.zeros((w + 1, 32), dtype=np.int32)
+    g1 = np.zeros((max(w, 1), 2), dtype=np.uint32); g2 = np.zeros((max(w, 1), 2), dtype=np.uint32)
+    n1 = C.c_uint32(); n2 = C.c_uint32()
+    rc = lib.dp_oracle_construct(C.byref(p1), C.byref(p2), _p(path), w, _p(g), _p(os_), _p(oc), _p(g1), C.byref(n1),
+                                 _p(g2), C.byref(n2))
+    if rc:
+        raise ValueError(f"dp_oracle_construct: path does not span the two profiles (rc={rc})")
+    return os_, oc, g1[:n1.value].copy(), g2[:n2.value].copy()
 
 
 def lcs_rows(codes, offsets, lens, ref_ids, col_ids=None, n_col=None) -> np.ndarray:

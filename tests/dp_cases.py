@@ -24,7 +24,7 @@ def random_tree(n: int, rng, caterpillar: float = 0.3) -> list[tuple[int, int]]:
 
 
 def reference_merges(seqs: list[str], merges, n_seqs_for_rescale: int | None = None, threads=(1, 2), rng=None,
-                     gaps=None):
+                     gaps=None, want_merged: bool = False):
     """Runs the reference's progressive alignment.  Returns (gaps, records) where each record is a dict with
     the Align inputs (s1,c1,k1,s2,c2,k2), members, and the reference's result (total, rows of the merged
     profile -> path via pyoracle.path_from_rows once the orientation is known)."""
@@ -43,6 +43,8 @@ def reference_merges(seqs: list[str], merges, n_seqs_for_rescale: int | None = N
         s2, c2, k2 = dp.tables(pb)
         m, total = dp.align(pa, pb, int(rng.choice(threads)))
         recs.append(dict(job=(s1, c1, k1, s2, c2, k2), m1=ma, m2=mb, total=total, rows=dp.rows(m)))
+        if want_merged:                          # the tables ConstructProfile built (profile.cpp:784-1002)
+            recs[-1]["merged"] = dp.tables(m)
         nodes[n + k] = (m, ma | mb)
     for p, _ in nodes.values():
         dp.free(p)
@@ -85,3 +87,44 @@ def driven_progressive_alignment(seqs, merges, align_level, n_seqs_for_rescale=N
     dp.free(root)
     dp.close()
     return rows, total
+
+
+def resident_progressive_alignment(engine, seqs, merges, gaps, score_matrix, on_level=None):
+    """Level-synchronous progressive alignment with every profile resident on the GPU (famsa_prof_merge_batch):
+    leaves come from the uploaded sequences, merged tables never leave HBM, the host receives one path per merge
+    and applies its gap runs to the member rows (what FinalizeGaps does, profile.cpp:1053-1104).
+    on_level(level_merge_indices, merged_ids, results) is called after each level, before the next consumes them.
+    Returns ({seq_no: gapped string}, results per merge, root id)."""
+    from famsa_b200 import seqio
+    from famsa_b200.binding import PROF_LEAF
+    from famsa_b200.schedule import ready_levels
+    n = len(seqs)
+    codes, off, lens = seqio.pack([seqio.encode(s) for s in seqs])
+    engine.upload(codes, off, lens)
+    engine.prof_set_scoring(score_matrix)
+    node = {i: PROF_LEAF | i for i in range(n)}
+    width = {i: len(seqs[i]) for i in range(n)}
+    rows = {i: {i: np.frombuffer(seqs[i].encode(), dtype=np.uint8)} for i in range(n)}
+    results = [None] * len(merges)
+    for lvl in ready_levels(n, merges):
+        pairs = [(node.pop(merges[k][0]), node.pop(merges[k][1])) for k in lvl]
+        ids, res = engine.prof_merge_batch(pairs, gaps, [(width[merges[k][0]], width[merges[k][1]]) for k in lvl])
+        for k, pid, r in zip(lvl, ids, res):
+            a, b = merges[k]
+            node[n + k] = pid
+            width[n + k] = len(r["path"])
+            ra, rb = rows.pop(a), rows.pop(b)
+            rrows, crows = (rb, ra) if r["swapped"] else (ra, rb)
+            out = {}
+            for members, gapdir in ((rrows, 1), (crows, 2)):
+                keep = r["path"] != gapdir
+                for no, row in members.items():
+                    g = np.full(len(r["path"]), ord("-"), dtype=np.uint8)
+                    g[keep] = row
+                    out[no] = g
+            rows[n + k] = out
+            results[k] = r
+        if on_level:
+            on_level(lvl, ids, res)
+    root = n + len(merges) - 1
+    return {no: row.tobytes().decode() for no, row in rows[root].items()}, results, node[root]

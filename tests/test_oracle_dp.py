@@ -94,3 +94,48 @@ def test_oracle_driven_alignment_equals_reference():
         seqs, merges, lambda jobs, g: [pyoracle.dp_align(*j, g) for j in jobs])
     _, recs = reference_merges(seqs, merges, threads=(1,))
     assert rows == recs[-1]["rows"] and total == recs[-1]["total"] == int(z["totals"][-1])
+
+
+def _check_construct(res, recs, g):
+    """oracle ConstructProfile merge part == the reference's merged scores/counters, merge by merge."""
+    for k, (r, rec) in enumerate(zip(res, recs)):
+        s1, c1, k1, s2, c2, k2 = rec["job"]
+        rp, cp = ((s2, c2, k2), (s1, c1, k1)) if r["swapped"] else ((s1, c1, k1), (s2, c2, k2))
+        s, c, g1, g2 = pyoracle.dp_construct(rp, cp, r["path"], g)
+        ws, wc, wk = rec["merged"]
+        assert wk == k1 + k2 and ws.shape == s.shape, f"merge {k}"
+        assert np.array_equal(c, wc), f"merge {k}: counters differ"
+        assert np.array_equal(s, ws), f"merge {k}: scores differ"
+        # gap runs: exactly the H (resp. V) runs of the path, as (first merged column, length)
+        for runs, d in ((g1, 1), (g2, 2)):
+            mask = np.zeros(len(r["path"]) + 2, dtype=bool)
+            for a, ln in runs:
+                assert not mask[a:a + ln].any()
+                mask[a:a + ln] = True
+            assert np.array_equal(mask[1:-1], r["path"] == d)
+            assert all(not mask[a - 1] and not mask[a + ln] for a, ln in runs), "runs must be maximal"
+
+
+@needs_ref
+def test_oracle_construct_golden_upgma_tree():
+    """Merged profile tables after each of the 241 merges behind upgma.no_refine.fasta (ConstructProfile,
+    profile.cpp:784-1002) -- the widened row SURVEY 8f-2."""
+    z = np.load(os.path.join(GOLDEN, "adeno_upgma_merges.npz"))
+    seqs = [str(s) for s in z["seqs"]]
+    merges = [tuple(int(x) for x in m) for m in z["merges"]]
+    g, recs = reference_merges(seqs, merges, threads=(1,), want_merged=True)
+    res = [pyoracle.dp_align(*r["job"], g) for r in recs]
+    _check_construct(res, recs, g)
+
+
+@needs_ref
+@pytest.mark.parametrize("seed,n,length,gaps", [(11, 50, 80, None), (12, 40, 200, (-9000, -700, -300, -100))])
+def test_oracle_construct_random_families(seed, n, length, gaps):
+    rng = np.random.default_rng(seed)
+    codes, off, lens = seqio.synth_family(n, length, seed, sort_desc=False)
+    seqs = [seqio.decode(codes[int(o):int(o) + int(l)]) for o, l in zip(off, lens)]
+    seqs[1] = seqs[1][:3] + "XBZ" + seqs[1][6:]
+    merges = random_tree(n, rng, caterpillar=0.5)
+    g, recs = reference_merges(seqs, merges, threads=(1, 2), rng=rng, gaps=gaps, want_merged=True)
+    res = [pyoracle.dp_align(*r["job"], g) for r in recs]
+    _check_construct(res, recs, g)
