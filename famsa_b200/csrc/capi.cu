@@ -72,7 +72,7 @@ void famsa_destroy(famsa_ctx* ctx)
     fb::prof_release_all(ctx);
     fb::DpState& D = ctx->dp;
     if (D.h_pinned) cudaFreeHost(D.h_pinned);
-    for (fb::DevBuf* b : {&D.d_jobs, &D.d_order, &D.d_scratch, &D.d_dirs, &D.d_tables, &D.d_results, &D.d_path, &D.d_meta, &D.d_tblock, &D.d_T})
+    for (fb::DevBuf* b : {&D.d_jobs, &D.d_order, &D.d_scratch, &D.d_dirs, &D.d_dirs_out, &D.d_tables, &D.d_results, &D.d_path, &D.d_meta, &D.d_tblock, &D.d_T})
         b->release();
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);

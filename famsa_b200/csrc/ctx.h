@@ -61,7 +61,7 @@ struct LcsState {
 };
 
 struct DpState {
-    DevBuf d_jobs, d_order, d_scratch, d_dirs, d_tables, d_results, d_path, d_meta, d_tblock, d_T;
+    DevBuf d_jobs, d_order, d_scratch, d_dirs, d_dirs_out, d_tables, d_results, d_path, d_meta, d_tblock, d_T;
     void* h_pinned = nullptr;          // pinned staging buffer of the host entry point
     size_t h_pinned_cap = 0;
     uint64_t last_cells = 0;

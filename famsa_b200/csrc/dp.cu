@@ -46,7 +46,7 @@ struct DpJobDev {
     const long long* s1; const int* c1;
     const long long* s2; const int* c2;
     uint32_t w1, card1, w2, card2;
-    unsigned long long path_off, dirs_off, scratch_off, t_off;
+    unsigned long long path_off, dirs_off, scratch_off, t_off;   // t_off: element offset of the job's skewed T / directions
 };
 
 struct DpMeta {            // written by k_dp_prep
@@ -81,14 +81,32 @@ constexpr int kChunk = 16;                  // boundary-row columns handed over 
 
 __host__ __device__ inline unsigned long long align_up(unsigned long long v, unsigned long long a) { return (v + a - 1) / a * a; }
 
+// Skewed (wavefront-major) storage of per-cell data: stripe k (rows 32k+1 .. 32k+32), wavefront step s, lane l hold
+// cell (32k+1+l, s-l).  One warp step of k_dp_fill then touches 32 consecutive elements (one 256-byte T read, one
+// 32-byte direction write) instead of 32 different rows.
+__host__ __device__ inline unsigned long long skew_elems_oriented(uint32_t wr, uint32_t wc)
+{
+    return (unsigned long long)((wr + 31) / 32) * 32ull * ((unsigned long long)wc + 32);
+}
+// the orientation is chosen on the device (k_dp_prep): reserve for the larger of the two
+__host__ __device__ inline unsigned long long skew_elems(uint32_t w1, uint32_t w2)
+{
+    const unsigned long long a = skew_elems_oriented(w1, w2), b = skew_elems_oriented(w2, w1);
+    return a > b ? a : b;
+}
+
+constexpr int kColFields = 8;               // ColInfo as structure-of-arrays: field f of column j at col[f * cstride + j]
+constexpr int kRing = 64;                   // shared-memory window of column records per warp (columns mod 64)
+
 // scratch layout of one job (all sections 128-byte aligned)
 struct Scratch {
-    unsigned long long col, brow, rownz, s2t, tmp, lastv, total;
+    unsigned long long col, brow, rownz, s2t, tmp, lastv, total, cstride;
     __host__ __device__ Scratch(uint32_t w1, uint32_t w2)
     {
         const unsigned long long wm = (w1 > w2 ? w1 : w2) + 1ull;
+        cstride = align_up(wm + 1, 16);
         col = 0;
-        brow = align_up(col + sizeof(ColInfo) * wm, 128);
+        brow = align_up(col + 8ull * kColFields * cstride, 128);
         rownz = align_up(brow + sizeof(Cell) * wm, 128);
         s2t = align_up(rownz + sizeof(RowNz) * wm, 128);
         tmp = align_up(s2t + 8ull * 30 * wm, 128);
@@ -122,6 +140,11 @@ __device__ __forceinline__ void cp_async_cell(Cell* smem_dst, const Cell* gsrc)
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(reinterpret_cast<const char*>(gsrc) + 16) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 constexpr int kPrefetch = 8;                 // columns of look-ahead for the L1 prefetches
@@ -172,7 +195,8 @@ struct DpParams {
     uint32_t n_jobs;              // jobs of this launch (a sub-batch, or one fill class of it)
     uint32_t job_base;            // first job id of the sub-batch (k_dp_prep / k_dp_t index jobs as job_base + x)
     long long go, ge, to, te;
-    unsigned char* dirs;          // all direction matrices
+    unsigned char* dirs;          // caller-visible row-major direction matrices (CDPMatrix layout) or nullptr
+    unsigned char* sdirs;         // internal skewed direction bytes of the sub-batch
     unsigned char* path;          // all paths (forward order)
     unsigned char* scratch;
     long long* T;                 // all T matrices
@@ -221,15 +245,14 @@ __global__ void __launch_bounds__(128) k_dp_prep(const DpParams P)
     }
     const Scratch L(J.w1, J.w2);
     unsigned char* scratch = P.scratch + J.scratch_off;
-    ColInfo* col = reinterpret_cast<ColInfo*>(scratch + L.col);
+    long long* col = reinterpret_cast<long long*>(scratch + L.col);
     Cell* brow = reinterpret_cast<Cell*>(scratch + L.brow);
     RowNz* rownz = reinterpret_cast<RowNz*>(scratch + L.rownz);
     long long* s2t = reinterpret_cast<long long*>(scratch + L.s2t);
-    unsigned char* dirs = P.dirs + J.dirs_off;
     const long long go = P.go, ge = P.ge, to = P.to, te = P.te;
     const size_t ldc = (size_t)WC + 1;
 
-    // column records + row 0 of the direction matrix
+    // column records (structure of arrays)
     for (uint32_t j = tid; j <= WC; j += nthr) {
         ColInfo ci = {0, 0, 0, 0, 0, 0, 0, 0};
         if (j >= 1 && var != 0) {
@@ -242,20 +265,33 @@ __global__ void __launch_bounds__(128) k_dp_prep(const DpParams P)
             if (var == 2) { ci.b0 = pack2(s_o, s_e); ci.b1 = pack2(s_to, s_te); ci.b2 = pack2(k_e, k_te); }
             else { ci.b0 = go * s_o + ge * s_e + to * s_to + te * s_te; ci.b1 = ge * k_e + te * k_te; }
         }
-        col[j] = ci;
-        dirs[j] = j == 0 ? 0 : (unsigned char)(1 | 1 << 2 | 1 << 4);
+        const long long v[kColFields] = {ci.cgo, ci.cge, ci.cto, ci.cte, ci.chg, ci.b0, ci.b1, ci.b2};
+#pragma unroll
+        for (int f = 0; f < kColFields; ++f) col[(size_t)f * L.cstride + j] = v[f];
     }
-    // row 0 (profile_par.cpp:531-555; SeqSeq profile_seq.cpp:48-69)
-    if (tid == 0) {
-        store_cell(brow, Cell{0, kNeg, kNeg, 0});
-        long long h = 0;
-        for (uint32_t j = 1; j <= WC; ++j) {
+    // row 0 (profile_par.cpp:531-555; SeqSeq profile_seq.cpp:48-69): H(0, j) is a running sum over the columns --
+    // every thread sums a contiguous segment, the segment totals are combined through shared memory
+    {
+        __shared__ long long sm_seg[128];
+        auto term = [&](uint32_t j) -> long long {
             const long long* sc = SC + (size_t)j * 32;
-            if (var == 0) h = j == 1 ? to : h + te;            // max(H, D = NEG) + te
-            else if (var == 1) h = j == 1 ? sc[kTO] : h + sc[kTE];
-            else h = j == 1 ? sc[kTO] * nR : h + sc[kTE] * nR;
+            if (var == 0) return j == 1 ? to : te;             // max(H, D = NEG) + te
+            if (var == 1) return j == 1 ? sc[kTO] : sc[kTE];
+            return (j == 1 ? sc[kTO] : sc[kTE]) * nR;
+        };
+        const uint32_t seg = (WC + nthr - 1) / nthr;
+        const uint32_t ja = 1 + tid * seg, jb = ja + seg - 1 < WC ? ja + seg - 1 : WC;
+        long long sum = 0;
+        for (uint32_t j = ja; j <= jb; ++j) sum += term(j);
+        sm_seg[tid] = sum;
+        __syncthreads();
+        long long h = 0;
+        for (uint32_t u = 0; u < tid; ++u) h += sm_seg[u];
+        for (uint32_t j = ja; j <= jb; ++j) {
+            h += term(j);
             store_cell(brow + j, Cell{kNeg, j == WC ? kNeg : h, kNeg, 0});
         }
+        if (tid == 0) store_cell(brow, Cell{0, kNeg, kNeg, 0});
     }
     // non-zero lists of the row profile (ProfProf) or its residue (Seq*)
     for (uint32_t i = tid; i <= WR; i += nthr) {
@@ -301,7 +337,7 @@ __global__ void __launch_bounds__(kTThreads) k_dp_t(const DpParams P)
     const RowNz* rownz = reinterpret_cast<const RowNz*>(scratch + L.rownz);
     const long long* s2t = reinterpret_cast<const long long*>(scratch + L.s2t);
     long long* T = P.T + J.t_off;
-    const size_t ldc = (size_t)M.WC + 1;
+    const size_t ldc = (size_t)M.WC + 1, steps = (size_t)M.WC + 32;
     const size_t cells = ((size_t)M.WR + 1) * ldc;
     const size_t base = (size_t)(b - P.tblock[lo]) * kTThreads * kTCellsPerThread;
 #pragma unroll
@@ -309,13 +345,47 @@ __global__ void __launch_bounds__(kTThreads) k_dp_t(const DpParams P)
         const size_t c = base + (size_t)u * kTThreads + threadIdx.x;
         if (c >= cells) break;
         const uint32_t i = (uint32_t)c / (uint32_t)ldc, j = (uint32_t)c - i * (uint32_t)ldc;   // cells < 2^32 per merge
-        long long t = 0;
         if (i >= 1 && j >= 1) {
+            long long t = 0;
             const RowNz* r = rownz + i;
             const int n = r->n;
             for (int q = 0; q < n; ++q) t += (long long)r->c[q] * s2t[(size_t)r->k[q] * ldc + j];
+            const uint32_t q = i - 1, l = q & 31;
+            T[((size_t)(q >> 5) * steps + (j + l)) * 32 + l] = t;     // skewed: (stripe, step = j + lane, lane)
         }
-        T[c] = t;
+    }
+}
+
+// Caller-visible CDPMatrix bytes (row-major, row 0 all-H, column 0 all-V) from the skewed internal directions.
+__device__ __forceinline__ unsigned char dir_at(const unsigned char* __restrict__ sdirs, size_t steps, uint32_t i, uint32_t j)
+{
+    if (i == 0) return j ? (unsigned char)(1 | 1 << 2 | 1 << 4) : 0;
+    const uint32_t q = i - 1, l = q & 31;
+    return __ldcg(sdirs + ((size_t)(q >> 5) * steps + (j + l)) * 32 + l);
+}
+
+__global__ void __launch_bounds__(kTThreads) k_dp_unskew(const DpParams P)
+{
+    uint32_t lo = 0, hi = P.n_jobs;
+    const unsigned long long b = blockIdx.x;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) / 2;
+        if (P.tblock[mid] <= b) lo = mid; else hi = mid;
+    }
+    const uint32_t jid = P.job_base + lo;
+    const DpJobDev J = P.jobs[jid];
+    const DpMeta M = P.meta[jid];
+    const size_t ldc = (size_t)M.WC + 1, steps = (size_t)M.WC + 32;
+    const size_t cells = ((size_t)M.WR + 1) * ldc;
+    const unsigned char* sd = P.sdirs + J.t_off;
+    unsigned char* out = P.dirs + J.dirs_off;
+    const size_t base = (size_t)(b - P.tblock[lo]) * kTThreads * kTCellsPerThread;
+#pragma unroll
+    for (int u = 0; u < kTCellsPerThread; ++u) {
+        const size_t c = base + (size_t)u * kTThreads + threadIdx.x;
+        if (c >= cells) break;
+        const uint32_t i = (uint32_t)c / (uint32_t)ldc, j = (uint32_t)c - i * (uint32_t)ldc;
+        out[c] = dir_at(sd, steps, i, j);
     }
 }
 
@@ -329,17 +399,22 @@ __global__ void __launch_bounds__(kTThreads) k_dp_t(const DpParams P)
 // kLag macro steps after stripe k-1, which is exactly late enough for every boundary-row column it is about
 // to read (and the chunk it prefetches for the next macro step) to have been parked by lane 31 of stripe k-1.
 // Because the schedule is a closed form, nobody polls: one __syncthreads per macro step orders the hand-over.
-constexpr int kLag = 4;      // macro steps between consecutive stripes: (31 + 2*kChunk) / kChunk rounded up
+// Macro steps between consecutive stripes for a chunk of CH columns.  The consumer requests chunk `off` right after
+// the barrier that opens its macro step off-1; by then the producer (kLag macro steps ahead) must have parked column
+// off*CH + CH-1, which its lane 31 computes at wavefront step off*CH + CH-1 + 31:  kLag >= 3 + floor(30 / CH).
+// Block teams use CH = 16 (64 columns of lag, fewer barriers); clusters, which exist to shorten the critical path of
+// one very wide merge, use CH = 8 (48 columns of lag).
+__host__ __device__ constexpr int lag_of(int ch) { return 3 + 30 / ch; }
 
-template <int VAR, int NW, int CL>
+template <int VAR, int NW, int CL, int CH>
 __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, const long long* __restrict__ T,
-                                           const ColInfo* __restrict__ col, Cell* __restrict__ brow,
+                                           const long long* __restrict__ col, uint32_t cstride, Cell* __restrict__ brow,
                                            unsigned char* __restrict__ dirs, uint32_t team_warp,
-                                           long long* last_out, Cell (*sb)[kChunk])
+                                           long long* last_out, Cell (*sb)[CH], long long (*ring)[kRing])
 {
+    constexpr int kChunk = CH, kLag = lag_of(CH);
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t WR = M.WR, WC = M.WC;
-    const size_t ld = (size_t)WC + 1;
     const long long go = P.go, ge = P.ge, to = P.to, te = P.te;
     const uint32_t n_stripes = (WR + 31) / 32;
     const uint32_t steps = WC + 1 + 31;                              // wavefront steps per stripe
@@ -358,9 +433,19 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
     long long nongap1 = 0, srgo = 0, srge = 0, srto = 0, srte = 0, col0cost = 0;
     Cell cur = {kNeg, kNeg, kNeg, 0}, up = {kNeg, kNeg, kNeg, 0};
     long long t_next = 0;
-    ColInfo c_next = {0, 0, 0, 0, 0, 0, 0, 0};
-    unsigned char* drow = dirs;
-    const long long* trow = T;
+    unsigned char* dk = dirs;          // this stripe's skewed directions / T: element (s, lane) at [s * 32 + lane]
+    const long long* tk = T;
+    // columns c0 .. c0+CH-1 of the column records -> this warp's shared-memory window (16-byte copies, two columns each)
+    auto request_columns = [&](uint32_t c0) {
+        if (VAR == 0) return;
+        constexpr int per_field = CH / 2;
+#pragma unroll
+        for (int idx = (int)lane; idx < kColFields * per_field; idx += 32) {
+            const int f = idx / per_field;
+            const uint32_t c = c0 + 2u * (uint32_t)(idx % per_field);
+            if (c <= WC) cp_async16(&ring[f][c & (kRing - 1)], col + (size_t)f * cstride + c);
+        }
+    };
 
     for (uint32_t m = 0; m < (TW == 1 ? rounds * S : m_end); ++m) {
         // my stripes start at r*period + team_warp*kLag, r = 0, 1, ...; `off` = local macro step inside the stripe
@@ -392,10 +477,11 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
                 cur = Cell{kNeg, kNeg, kNeg, 0};
                 up = Cell{kNeg, kNeg, kNeg, 0};
                 t_next = 0;
-                drow = dirs + (size_t)i * ld;
-                trow = T + (size_t)i * ld;
-                // first boundary chunk (columns 0..kChunk-1): nobody could prefetch it for us
+                dk = dirs + (size_t)k * 32 * steps;
+                tk = T + (size_t)k * 32 * steps;
+                // first boundary / column-record chunk (columns 0..kChunk-1): nobody could prefetch it for us
                 if (lane < kChunk && lane <= WC) cp_async_cell(&sb[0][lane], brow + lane);
+                request_columns(0);
                 cp_async_commit();
             }
             // the chunk of this macro step was requested one macro step ago (or just above)
@@ -404,6 +490,7 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
             {   // request the next one: columns (off+1)*kChunk ... have been parked (see kLag)
                 const uint32_t nb = (uint32_t)(off + 1) * kChunk;
                 if (lane < kChunk && nb + lane <= WC) cp_async_cell(&sb[(off + 1) & 1][lane], brow + nb + lane);
+                request_columns(nb);
                 cp_async_commit();
             }
             const Cell* chunk = sb[off & 1];
@@ -417,15 +504,18 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
                 const int j = (int)s - (int)lane;                        // column handled now
                 const bool active = valid && j >= 0 && j <= (int)WC;
                 const long long t = t_next;
-                const ColInfo ci = c_next;
-                if (valid && j + 1 >= 1 && j + 1 <= (int)WC) {
-                    t_next = trow[j + 1];
-                    if (VAR != 0) c_next = col[j + 1];
+                // T of the next step: one coalesced 256-byte read per warp; the lines of the step after next few are
+                // pulled into L1 by two lanes
+                if (s + 1 < steps) t_next = tk[(size_t)(s + 1) * 32 + lane];
+                if (lane < 2 && s + kPrefetch < steps) prefetch_l1(tk + (size_t)(s + kPrefetch) * 32 + lane * 16);
+                // this column's record from the shared-memory window (consecutive lanes -> consecutive slots)
+                ColInfo ci = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (VAR != 0) {
+                    const uint32_t slot = (uint32_t)j & (kRing - 1);
+                    ci.cgo = ring[0][slot]; ci.cge = ring[1][slot]; ci.cto = ring[2][slot]; ci.cte = ring[3][slot];
+                    ci.chg = ring[4][slot]; ci.b0 = ring[5][slot]; ci.b1 = ring[6][slot];
+                    if (VAR == 2) ci.b2 = ring[7][slot];
                 }
-                // pull what the next few steps will read into L1 now: every lane streams its own T row (a new
-                // 32-byte sector every 4 steps), lane 0 is the first to touch each column record
-                if (valid && (j & 3) == 0 && j + kPrefetch <= (int)WC) prefetch_l1(trow + j + kPrefetch);
-                if (VAR != 0 && lane == 0 && s + kPrefetch <= WC) prefetch_l1(col + s + kPrefetch);
                 // (i-1, j): the lane above computed it one step ago; lane 0 takes it from the boundary row
                 Cell U;
                 U.D = shfl_up_ll(cur.D); U.H = shfl_up_ll(cur.H); U.V = shfl_up_ll(cur.V);
@@ -487,7 +577,7 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
                     db = 2 | 2 << 2 | 2 << 4;
                 }
                 if (active) {
-                    drow[j] = db;
+                    dk[(size_t)s * 32 + lane] = db;
                     cur = out;
                     if (last_row) {
                         if (j == (int)WC) { last_out[0] = out.D; last_out[1] = out.H; last_out[2] = out.V; }
@@ -513,8 +603,10 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_fill(cons
 {
     constexpr int kBlockWarps = NW == 1 ? kDpWarps : NW;
     __shared__ long long sm_last[kBlockWarps][3];
-    __shared__ __align__(16) Cell sm_brow[kBlockWarps][2][kChunk];
+    constexpr int CH = CL > 1 ? 8 : kChunk;
+    __shared__ __align__(16) Cell sm_brow[kBlockWarps][2][CH];
     __shared__ unsigned char sm_tile[NW == 1 ? kDpWarps : 1][32 * 32];
+    __shared__ __align__(16) long long sm_ring[kBlockWarps][kColFields][kRing];
     const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const uint32_t cta_rank = CL > 1 ? cooperative_groups::this_cluster().block_rank() : 0;
     const uint32_t team_warp = NW == 1 ? 0 : cta_rank * NW + warp;
@@ -531,20 +623,21 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_fill(cons
 
     const Scratch L(J.w1, J.w2);
     unsigned char* scratch = P.scratch + J.scratch_off;
-    const ColInfo* col = reinterpret_cast<const ColInfo*>(scratch + L.col);
+    const long long* col = reinterpret_cast<const long long*>(scratch + L.col);
+    const uint32_t cstride = (uint32_t)L.cstride;
     Cell* brow = reinterpret_cast<Cell*>(scratch + L.brow);
     unsigned char* tmp_path = scratch + L.tmp;
     long long* g_last = reinterpret_cast<long long*>(scratch + L.lastv);
-    unsigned char* dirs = P.dirs + J.dirs_off;
+    unsigned char* dirs = P.sdirs + J.t_off;
     const long long* T = P.T + J.t_off;
     const uint32_t WR = M.WR, WC = M.WC;
-    const size_t ld = (size_t)WC + 1;
+    const size_t steps = (size_t)WC + 32;
 
     // the lane that owns cell (WR, WC) leaves (D,H,V) in shared memory, or in the job's scratch for a cluster
     long long* last_out = CL > 1 ? g_last : sm_last[warp];
-    if (M.var == 0) dp_stripes<0, NW, CL>(P, M, T, col, brow, dirs, team_warp, last_out, sm_brow[warp]);
-    else if (M.var == 1) dp_stripes<1, NW, CL>(P, M, T, col, brow, dirs, team_warp, last_out, sm_brow[warp]);
-    else dp_stripes<2, NW, CL>(P, M, T, col, brow, dirs, team_warp, last_out, sm_brow[warp]);
+    if (M.var == 0) dp_stripes<0, NW, CL, CH>(P, M, T, col, cstride, brow, dirs, team_warp, last_out, sm_brow[warp], sm_ring[warp]);
+    else if (M.var == 1) dp_stripes<1, NW, CL, CH>(P, M, T, col, cstride, brow, dirs, team_warp, last_out, sm_brow[warp], sm_ring[warp]);
+    else dp_stripes<2, NW, CL, CH>(P, M, T, col, cstride, brow, dirs, team_warp, last_out, sm_brow[warp], sm_ring[warp]);
     __threadfence();
     team_sync();
     if (team_warp != 0) return;
@@ -570,11 +663,10 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_fill(cons
         while (ti || tj) {
             const uint32_t i0 = ti >= 31 ? ti - 31 : 0, j0 = tj >= 31 ? tj - 31 : 0;
             if (ti >= lane && ti - lane >= i0) {
-                const unsigned char* src = dirs + (size_t)(ti - lane) * ld + j0;
                 const uint32_t w = tj - j0 + 1;
 #pragma unroll
                 for (uint32_t c = 0; c < 32; ++c)
-                    if (c < w) tile[lane * 32 + c] = __ldcg(src + c);
+                    if (c < w) tile[lane * 32 + c] = dir_at(dirs, steps, ti - lane, j0 + c);
             }
             __syncwarp();
             if (lane == 0) {
@@ -671,10 +763,9 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
             const unsigned long long mat = ((unsigned long long)dev[j1].w1 + 1) * (dev[j1].w2 + 1);
             if (j1 > j0 && mat_sum + mat > max_cells) break;
             dev[j1].scratch_off = scratch_off;
-            dev[j1].t_off = t_off;
-            if (!d_dirs) dev[j1].dirs_off = t_off;              // internal direction matrices are per sub-batch
+            dev[j1].t_off = t_off;                              // skewed T / directions are per sub-batch
             scratch_off += Scratch(dev[j1].w1, dev[j1].w2).total;
-            t_off += mat;
+            t_off += skew_elems(dev[j1].w1, dev[j1].w2);
             mat_sum += mat;
             tblock.push_back(tblock.back() + (mat + kTThreads * kTCellsPerThread - 1) / (kTThreads * kTCellsPerThread));
             ++j1;
@@ -708,11 +799,7 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
         FB_TRY(S.d_tblock.reserve(sizeof(unsigned long long) * (m + 1)));
         FB_TRY(S.d_scratch.reserve(std::max<unsigned long long>(scratch_off, 64)));
         FB_TRY(S.d_T.reserve(std::max<unsigned long long>(t_off * 8, 64)));
-        uint8_t* dirs = d_dirs;
-        if (!dirs) {
-            FB_TRY(S.d_dirs.reserve(std::max<unsigned long long>(t_off, 64)));
-            dirs = S.d_dirs.as<uint8_t>();
-        }
+        FB_TRY(S.d_dirs.reserve(std::max<unsigned long long>(t_off, 64)));
         FB_CUDA(cudaMemcpyAsync(S.d_jobs.as<DpJobDev>() + j0, dev.data() + j0, sizeof(DpJobDev) * m, cudaMemcpyHostToDevice, st));
         FB_CUDA(cudaMemcpyAsync(S.d_order.p, order.data(), sizeof(uint32_t) * m, cudaMemcpyHostToDevice, st));
         FB_CUDA(cudaMemcpyAsync(S.d_tblock.p, tblock.data(), sizeof(unsigned long long) * (m + 1), cudaMemcpyHostToDevice, st));
@@ -723,7 +810,8 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
         P.n_jobs = m;
         P.job_base = j0;
         P.go = gaps[0]; P.ge = gaps[1]; P.to = gaps[2]; P.te = gaps[3];
-        P.dirs = dirs;
+        P.dirs = d_dirs;
+        P.sdirs = S.d_dirs.as<uint8_t>();
         P.path = d_path;
         P.scratch = S.d_scratch.as<uint8_t>();
         P.T = S.d_T.as<long long>();
@@ -759,7 +847,6 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
             switch (nw) {
             case 2: k_dp_fill<2, 1><<<Q.n_jobs, 2 * 32, 0, st>>>(Q); break;
             case 4: k_dp_fill<4, 1><<<Q.n_jobs, 4 * 32, 0, st>>>(Q); break;
-            case 16: k_dp_fill<16, 1><<<Q.n_jobs, 16 * 32, 0, st>>>(Q); break;
             default: k_dp_fill<kDpTeamWarps, 1><<<Q.n_jobs, kDpTeamWarps * 32, 0, st>>>(Q); break;
             }
             FB_CUDA(cudaGetLastError());
@@ -770,6 +857,11 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
             Q.order = P.order + n_big;
             Q.n_jobs = m - n_big;
             k_dp_fill<1, 1><<<(Q.n_jobs + kDpWarps - 1) / kDpWarps, kDpWarps * 32, 0, st>>>(Q);
+            FB_CUDA(cudaGetLastError());
+            ctx->launches++;
+        }
+        if (d_dirs) {                                            // caller wants CDPMatrix bytes: un-skew
+            k_dp_unskew<<<(unsigned)tblock[m], kTThreads, 0, st>>>(P);
             FB_CUDA(cudaGetLastError());
             ctx->launches++;
         }
@@ -857,8 +949,8 @@ int dp_run_host(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int6
     FB_TRY(S.d_path.reserve(std::max<unsigned long long>(path_total, 64)));
     uint8_t* d_dirs = nullptr;
     if (dirs_buf) {
-        FB_TRY(S.d_dirs.reserve(std::max<unsigned long long>(dirs_total, 64)));
-        d_dirs = S.d_dirs.as<uint8_t>();
+        FB_TRY(S.d_dirs_out.reserve(std::max<unsigned long long>(dirs_total, 64)));   // row-major copy for the caller
+        d_dirs = S.d_dirs_out.as<uint8_t>();
     }
     FB_TRY(dp_run_device(ctx, dj.data(), n, gaps, S.d_results.as<famsa_dp_result>(), S.d_path.as<uint8_t>(), d_dirs, st));
     if (n) FB_CUDA(cudaMemcpyAsync(results, S.d_results.p, sizeof(famsa_dp_result) * n, cudaMemcpyDeviceToHost, st));
