@@ -8,19 +8,23 @@
 //
 // Design (three kernels per batch):
 //   k_dp_prep  one block per merge: variant + orientation (CProfile::Align), the column-side constant
-//              records (gap scores + gap-correction counts, 64 B per column), row 0 of the DP, the compact
-//              non-zero lists of the row profile's counters and a transposed copy of the column profile's
-//              scores (so the next kernel reads them coalesced).
+//              records (gap scores + gap-correction counts, 8 x int64 per column, structure of arrays), row 0 of
+//              the DP (block-parallel prefix sum) and, for the Seq* variants, each row's residue plus a transposed
+//              copy of the column profile's scores.
 //   k_dp_t     embarrassingly parallel: T[i][j] = sum_k counters_row[i][k] * scores_col[j][k], the column-
-//              pair score that does not depend on the DP state (profile_par.cpp:695-711).  Taking this
-//              gather-heavy dot product out of the wavefront removes the dependent-load chain from the
-//              latency-critical loop.
+//              pair score that does not depend on the DP state (profile_par.cpp:695-711).  Taking this dot
+//              product out of the wavefront removes it from the latency-critical loop.  One block = one 32-row
+//              stripe x 128 columns, column scores in registers, row counters broadcast; the result is stored
+//              SKEWED (stripe, wavefront step, lane) so that the fill kernel reads it with one 256-byte load per step.
 //   k_dp_fill  the recurrence itself: a team of warps per merge, 32-row stripes, lane L owns row i0+L and
 //              at step s computes column s-L (anti-diagonal wavefront); (D,H,V) of the cell above arrives
-//              by warp shuffle, the left neighbour stays in registers, T and the column record of the NEXT
-//              step are prefetched into registers.  Stripes of one merge run as a staircase over the warps
-//              of the block, handing the boundary row over through L2 with a shared-memory progress counter.
-//              The same kernel then walks the direction matrix back and emits the path.
+//              by warp shuffle, the left neighbour stays in registers, T of the next step is prefetched into a
+//              register, the column records live in a per-warp shared-memory ring filled by cp.async one chunk
+//              ahead, and the direction bytes go out skewed as well (one 32-byte store per step).  Stripes of one
+//              merge run as a lock-step staircase over the warps of the block (or of a thread-block cluster for
+//              very wide merges), handing the boundary row over through L2.  The same kernel then walks the
+//              direction matrix back and emits the path.
+//   k_dp_unskew only when the caller asks for CDPMatrix bytes: skewed directions -> row-major.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -200,7 +204,8 @@ struct DpParams {
     unsigned char* path;          // all paths (forward order)
     unsigned char* scratch;
     long long* T;                 // all T matrices
-    const unsigned long long* tblock;   // k_dp_t: first block of each job (n_jobs + 1 entries)
+    const unsigned long long* tblock;   // k_dp_unskew: first block of each job (n_jobs + 1 entries)
+    const unsigned long long* t2block;  // k_dp_t: first block of each job (n_jobs + 1 entries)
     famsa_dp_result* results;
 };
 
@@ -293,24 +298,14 @@ __global__ void __launch_bounds__(128) k_dp_prep(const DpParams P)
         }
         if (tid == 0) store_cell(brow, Cell{0, kNeg, kNeg, 0});
     }
-    // non-zero lists of the row profile (ProfProf) or its residue (Seq*)
+    if (var == 2) return;       // k_dp_t reads the ProfProf tables directly
+    // Seq* variants: the residue of every row, and a transposed copy of the column profile's scores (s2t[k][j], k < 30)
+    // so that k_dp_t's single look-up per cell is coalesced
     for (uint32_t i = tid; i <= WR; i += nthr) {
         RowNz* dst = rownz + i;
-        int n = 0;
-        if (i >= 1) {
-            if (var == 2) {
-                const int* rc = CR + (size_t)i * 32;
-                for (int k = 0; k < 30; ++k) {
-                    const int c = rc[k];
-                    if (c) { dst->c[n] = c; dst->k[n] = (unsigned char)k; ++n; }
-                }
-            } else {
-                dst->c[0] = 1; dst->k[0] = (unsigned char)seq_symbol(CR, i); n = 1;
-            }
-        }
-        dst->n = n;
+        dst->n = i >= 1;
+        if (i >= 1) { dst->c[0] = 1; dst->k[0] = (unsigned char)seq_symbol(CR, i); }
     }
-    // transposed scores of the column profile: s2t[k][j], k < 30
     for (size_t e = tid; e < ldc * 32; e += nthr) {
         const uint32_t j = (uint32_t)(e / 32), k = (uint32_t)(e % 32);
         if (k < 30) s2t[(size_t)k * ldc + j] = SC[e];
@@ -318,41 +313,94 @@ __global__ void __launch_bounds__(128) k_dp_prep(const DpParams P)
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_dp_t: T[i][j] for every cell of every job
+// k_dp_t: T[i][j] = sum_k counters_row[i][k] * scores_col[j][k] for every cell of every job, written in the
+// skewed layout k_dp_fill streams.  A block owns one 32-row stripe x 128 columns of one merge: every thread keeps
+// its column's 30 scores in registers (as 32-bit halves) and walks down the 32 rows; the row's counters are the
+// same for the whole block (broadcast 128-bit loads), so a cell costs 30 x (IMAD.WIDE + IMAD) and a fraction of a
+// load wavefront.  The tile goes through shared memory so that the skewed store is made of full 256-byte rows.
+// Seq* variants (one residue per row) read the single score they need from the transposed copy instead.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTThreads) k_dp_t(const DpParams P)
+constexpr int kTCols = 128;                 // columns (= threads) per k_dp_t block
+
+__host__ __device__ inline unsigned long long t_blocks_oriented(uint32_t wr, uint32_t wc)
 {
+    return (unsigned long long)((wc + kTCols - 1) / kTCols) * ((wr + 31) / 32);
+}
+__host__ __device__ inline unsigned long long t_blocks(uint32_t w1, uint32_t w2)
+{
+    const unsigned long long a = t_blocks_oriented(w1, w2), b = t_blocks_oriented(w2, w1);
+    return a > b ? a : b;
+}
+
+__global__ void __launch_bounds__(kTCols) k_dp_t(const DpParams P)
+{
+    __shared__ long long tile[32][kTCols];
     // which job does this block belong to?
     uint32_t lo = 0, hi = P.n_jobs;
     const unsigned long long b = blockIdx.x;
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) / 2;
-        if (P.tblock[mid] <= b) lo = mid; else hi = mid;
+        if (P.t2block[mid] <= b) lo = mid; else hi = mid;
     }
     const uint32_t jid = P.job_base + lo;
     const DpJobDev J = P.jobs[jid];
     const DpMeta M = P.meta[jid];
-    const Scratch L(J.w1, J.w2);
-    const unsigned char* scratch = P.scratch + J.scratch_off;
-    const RowNz* rownz = reinterpret_cast<const RowNz*>(scratch + L.rownz);
-    const long long* s2t = reinterpret_cast<const long long*>(scratch + L.s2t);
-    long long* T = P.T + J.t_off;
-    const size_t ldc = (size_t)M.WC + 1, steps = (size_t)M.WC + 32;
-    const size_t cells = ((size_t)M.WR + 1) * ldc;
-    const size_t base = (size_t)(b - P.tblock[lo]) * kTThreads * kTCellsPerThread;
+    const uint32_t WR = M.WR, WC = M.WC;
+    const uint32_t ctiles = (WC + kTCols - 1) / kTCols;
+    const uint32_t bj = (uint32_t)(b - P.t2block[lo]);
+    if (bj >= ctiles * ((WR + 31) / 32)) return;                    // reserved for the other orientation
+    const uint32_t stripe = bj / ctiles;
+    const uint32_t j0 = 1 + (bj % ctiles) * kTCols;                 // first column of the tile
+    const uint32_t j = j0 + threadIdx.x;
+    const uint32_t i0 = 1 + stripe * 32;
+    const uint32_t nrows = WR - i0 + 1 < 32 ? WR - i0 + 1 : 32;
+    const bool ok = j <= WC;
+    if (M.var == 2) {
+        unsigned slo[30], shi[30];
+        {
+            const longlong2* sc = reinterpret_cast<const longlong2*>(M.SC + (size_t)(ok ? j : 1) * 32);
 #pragma unroll
-    for (int u = 0; u < kTCellsPerThread; ++u) {
-        const size_t c = base + (size_t)u * kTThreads + threadIdx.x;
-        if (c >= cells) break;
-        const uint32_t i = (uint32_t)c / (uint32_t)ldc, j = (uint32_t)c - i * (uint32_t)ldc;   // cells < 2^32 per merge
-        if (i >= 1 && j >= 1) {
-            long long t = 0;
-            const RowNz* r = rownz + i;
-            const int n = r->n;
-            for (int q = 0; q < n; ++q) t += (long long)r->c[q] * s2t[(size_t)r->k[q] * ldc + j];
-            const uint32_t q = i - 1, l = q & 31;
-            T[((size_t)(q >> 5) * steps + (j + l)) * 32 + l] = t;     // skewed: (stripe, step = j + lane, lane)
+            for (int k = 0; k < 15; ++k) {
+                const longlong2 v = sc[k];
+                slo[2 * k] = (unsigned)v.x; shi[2 * k] = (unsigned)((unsigned long long)v.x >> 32);
+                slo[2 * k + 1] = (unsigned)v.y; shi[2 * k + 1] = (unsigned)((unsigned long long)v.y >> 32);
+            }
         }
+        for (uint32_t l = 0; l < nrows; ++l) {
+            const int4* rc = reinterpret_cast<const int4*>(M.CR + (size_t)(i0 + l) * 32);   // same address in every thread
+            unsigned long long acc = 0;
+            unsigned acch = 0;
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) {
+                const int4 c = rc[k4];
+                const unsigned cv[4] = {(unsigned)c.x, (unsigned)c.y, (unsigned)c.z, (unsigned)c.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = 4 * k4 + u;
+                    if (k < 30) {                                   // counters are >= 0: 32 x 64 -> 64 bits, wrapping
+                        acc += (unsigned long long)cv[u] * slo[k];
+                        acch += cv[u] * shi[k];
+                    }
+                }
+            }
+            tile[l][threadIdx.x] = (long long)(acc + ((unsigned long long)acch << 32));
+        }
+    } else {
+        const Scratch L(J.w1, J.w2);
+        const unsigned char* scratch = P.scratch + J.scratch_off;
+        const RowNz* rownz = reinterpret_cast<const RowNz*>(scratch + L.rownz);
+        const long long* s2t = reinterpret_cast<const long long*>(scratch + L.s2t);
+        const size_t ldc = (size_t)WC + 1;
+        for (uint32_t l = 0; l < nrows; ++l) tile[l][threadIdx.x] = ok ? s2t[(size_t)rownz[i0 + l].k[0] * ldc + j] : 0;
+    }
+    __syncthreads();
+    // skewed store: wavefront step s of this stripe holds cells (i0 + l, s - l); the tile covers steps j0 .. j0+127+31
+    long long* Tk = P.T + J.t_off + (size_t)stripe * 32 * ((size_t)WC + 32);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t ds = warp; ds < kTCols + 31; ds += kTCols / 32) {
+        const int c = (int)ds - (int)lane;                           // column inside the tile
+        if (c >= 0 && c < kTCols && lane < nrows && j0 + (uint32_t)c <= WC)
+            Tk[(size_t)(j0 + ds) * 32 + lane] = tile[lane][c];
     }
 }
 
@@ -758,7 +806,7 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
         // [j0, j1): as many consecutive jobs as fit
         uint32_t j1 = j0;
         unsigned long long mat_sum = 0, scratch_off = 0, t_off = 0;
-        std::vector<unsigned long long> tblock(1, 0);
+        std::vector<unsigned long long> tblock(1, 0), t2block(1, 0);
         while (j1 < n) {
             const unsigned long long mat = ((unsigned long long)dev[j1].w1 + 1) * (dev[j1].w2 + 1);
             if (j1 > j0 && mat_sum + mat > max_cells) break;
@@ -768,10 +816,11 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
             t_off += skew_elems(dev[j1].w1, dev[j1].w2);
             mat_sum += mat;
             tblock.push_back(tblock.back() + (mat + kTThreads * kTCellsPerThread - 1) / (kTThreads * kTCellsPerThread));
+            t2block.push_back(t2block.back() + t_blocks(dev[j1].w1, dev[j1].w2));
             ++j1;
         }
         const uint32_t m = j1 - j0;
-        if (tblock[m] > 0x7fffffffull) { set_error("dp sub-batch too large for one launch"); return FAMSA_E_INVALID; }
+        if (tblock[m] > 0x7fffffffull || t2block[m] > 0x7fffffffull) { set_error("dp sub-batch too large for one launch"); return FAMSA_E_INVALID; }
         // merges whose shorter side spans several 32-row stripes get a whole block (a team of warps pipelined over
         // the stripes); the rest run one warp per merge.  Both groups cost-descending.
         // class 2: shorter side > cluster_min -> a cluster of blocks; class 1: > team_min -> one block; class 0: one warp
@@ -796,13 +845,15 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
         FB_TRY(S.d_jobs.reserve(sizeof(DpJobDev) * n));
         FB_TRY(S.d_meta.reserve(sizeof(DpMeta) * n));
         FB_TRY(S.d_order.reserve(sizeof(uint32_t) * m));
-        FB_TRY(S.d_tblock.reserve(sizeof(unsigned long long) * (m + 1)));
+        FB_TRY(S.d_tblock.reserve(sizeof(unsigned long long) * 2 * (m + 1)));
         FB_TRY(S.d_scratch.reserve(std::max<unsigned long long>(scratch_off, 64)));
         FB_TRY(S.d_T.reserve(std::max<unsigned long long>(t_off * 8, 64)));
         FB_TRY(S.d_dirs.reserve(std::max<unsigned long long>(t_off, 64)));
         FB_CUDA(cudaMemcpyAsync(S.d_jobs.as<DpJobDev>() + j0, dev.data() + j0, sizeof(DpJobDev) * m, cudaMemcpyHostToDevice, st));
         FB_CUDA(cudaMemcpyAsync(S.d_order.p, order.data(), sizeof(uint32_t) * m, cudaMemcpyHostToDevice, st));
         FB_CUDA(cudaMemcpyAsync(S.d_tblock.p, tblock.data(), sizeof(unsigned long long) * (m + 1), cudaMemcpyHostToDevice, st));
+        FB_CUDA(cudaMemcpyAsync(S.d_tblock.as<unsigned long long>() + (m + 1), t2block.data(), sizeof(unsigned long long) * (m + 1),
+                                cudaMemcpyHostToDevice, st));
         DpParams P{};
         P.jobs = S.d_jobs.as<DpJobDev>();
         P.meta = S.d_meta.as<DpMeta>();
@@ -816,10 +867,11 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
         P.scratch = S.d_scratch.as<uint8_t>();
         P.T = S.d_T.as<long long>();
         P.tblock = S.d_tblock.as<unsigned long long>();
+        P.t2block = P.tblock + (m + 1);
         P.results = d_results;
         k_dp_prep<<<m, 128, 0, st>>>(P);
         FB_CUDA(cudaGetLastError());
-        k_dp_t<<<(unsigned)tblock[m], kTThreads, 0, st>>>(P);
+        k_dp_t<<<(unsigned)t2block[m], kTCols, 0, st>>>(P);
         FB_CUDA(cudaGetLastError());
         ctx->launches += 2;
         // `order`: cluster jobs, then block jobs, then warp jobs (see the sort above)
