@@ -9,6 +9,9 @@
 //   calculateDistanceVector/Range/Matrix     AbstractTreeGenerator.hpp:131,191,379   same names, same transforms
 //   Transform<T, Distance::*>                AbstractTreeGenerator.hpp:28-82         famsa_b200::Transform<T, D>
 //   CProfile::Align(p1, p2, ...)             src/core/profile.cpp:244                famsa_b200::AlignBatch(...)
+//   MSTPrim<>::run_view's vertex loop        src/tree/MSTPrim.cpp:280-549            CLCSBP::PrimEdges(...)
+//   CProfile(p1, p2) merge ctor, tables kept  profile.cpp:69-75, 784-1002            famsa_b200::ResidentProfiles
+//     on the device between tree levels
 // Errors: the reference throws std::runtime_error and catches it in main() (src/famsa.cpp:160-165);
 // every non-zero C-ABI status is rethrown here the same way.  There is no CPU fallback.
 #pragma once
@@ -131,6 +134,25 @@ public:
     }
 };
 
+// MST edges in Prim order, ready for the reference's mst_to_dendogram (MSTPrim.cpp:784-833): edge k joins
+// from[k] < to[k] at distance dist[k] (store -dist[k] in mst_edge_t as MSTPrim.cpp:384 does), order[i] = visiting
+// position of sequence i.
+struct PrimEdges {
+    std::vector<int32_t> from, to, order;
+    std::vector<double> dist;
+};
+
+// The default -gt sl guide tree: MSTPrim<distance>::run_view's relax/elect loop on the device.
+inline PrimEdges PrimMST(Context& ctx, Distance measure)
+{
+    const uint32_t n = famsa_lcs_n_seqs(ctx.get());
+    PrimEdges e;
+    e.from.resize(n ? n - 1 : 0); e.to.resize(n ? n - 1 : 0); e.dist.resize(n ? n - 1 : 0); e.order.resize(n);
+    if (measure == Distance::pairwise_identity) throw std::runtime_error("famsa_b200: MSTPrim is instantiated for the two indel distances only");
+    check(famsa_lcs_prim(ctx.get(), measure == Distance::indel075_div_lcs ? 0 : 1, e.from.data(), e.to.data(), e.dist.data(), e.order.data()));
+    return e;
+}
+
 // ---- profile alignment: what CProfile::Align hands to ConstructProfile
 struct AlignResult {
     std::vector<uint8_t> path;     // direction_t per merged column, forward order (ConstructProfile's path[1..width])
@@ -160,6 +182,70 @@ inline std::vector<AlignResult> AlignBatch(Context& ctx, const std::vector<famsa
     }
     return out;
 }
+
+// (first merged column, run length) of the gap columns a path inserts into the members of the DP's row profile
+// (direction H = 1) or column profile (direction V = 2) -- ConstructProfile's v_gaps_prof1 / v_gaps_prof2
+// (profile.cpp:1020-1029), the input of FinalizeGaps (profile.cpp:1053-1104).
+inline std::vector<std::pair<uint32_t, uint32_t>> GapRuns(const std::vector<uint8_t>& path, uint8_t dir)
+{
+    std::vector<std::pair<uint32_t, uint32_t>> runs;
+    for (uint32_t k = 0; k < path.size();) {
+        if (path[k] != dir) { ++k; continue; }
+        uint32_t e = k;
+        while (e < path.size() && path[e] == dir) ++e;
+        runs.emplace_back(k + 1, e - k);
+        k = e;
+    }
+    return runs;
+}
+
+// Profiles whose scores/counters stay in HBM between the levels of the guide tree (famsa_prof_*).  A node is either
+// a leaf (sequence id of CLCSBP's upload) or the id a previous MergeLevel returned.  Per merge only the path comes
+// back; the host applies GapRuns(path, 1 / 2) to the member sequences of the row / column profile with the
+// reference's FinalizeGaps and concatenates `data` as ConstructProfile does (profile.cpp:990-996).
+class ResidentProfiles {
+    Context& ctx_;
+    std::vector<uint32_t> width_;           // by resident id
+    std::vector<uint32_t> leaf_len_;
+public:
+    static uint32_t Leaf(uint32_t seq_id) { return FAMSA_PROF_LEAF | seq_id; }
+    // score_matrix: CParams::score_matrix, 24 x 24; leaf_lengths: CSequence::length of the uploaded sequences
+    ResidentProfiles(Context& ctx, const int64_t* score_matrix, std::vector<uint32_t> leaf_lengths)
+        : ctx_(ctx), leaf_len_(std::move(leaf_lengths)) { check(famsa_prof_set_scoring(ctx.get(), score_matrix)); }
+    uint32_t Width(uint32_t node) const { return (node & FAMSA_PROF_LEAF) ? leaf_len_.at(node & ~FAMSA_PROF_LEAF) : width_.at(node); }
+    // all ready merges of one level; children are consumed; out_ids[k] = resident id of merge k
+    std::vector<AlignResult> MergeLevel(const std::vector<famsa_prof_merge>& merges, const int64_t gaps[4], std::vector<uint32_t>& out_ids)
+    {
+        const size_t n = merges.size();
+        size_t cap = 0;
+        for (auto& m : merges) cap += (size_t)Width(m.child1) + Width(m.child2);
+        std::vector<famsa_dp_result> res(std::max<size_t>(1, n));
+        std::vector<uint8_t> path(std::max<size_t>(1, cap));
+        out_ids.assign(n, 0);
+        check(famsa_prof_merge_batch(ctx_.get(), merges.data(), (uint32_t)n, gaps, out_ids.data(), res.data(), path.data(), cap));
+        std::vector<AlignResult> out(n);
+        for (size_t k = 0; k < n; ++k) {
+            const famsa_dp_result& r = res[k];
+            out[k].path.assign(path.begin() + r.path_offset, path.begin() + r.path_offset + r.path_len);
+            out[k].total_score = r.total_score;
+            std::copy(r.last, r.last + 3, out[k].last);
+            out[k].swapped = r.swapped != 0;
+            out[k].variant = r.variant;
+            if (width_.size() <= out_ids[k]) width_.resize(out_ids[k] + 1);
+            width_[out_ids[k]] = r.path_len;
+        }
+        return out;
+    }
+    // scores ((width+1) x 32) and counters of a resident profile, e.g. the root for refinement
+    void Download(uint32_t id, std::vector<int64_t>& scores, std::vector<int32_t>& counters, uint32_t& card)
+    {
+        uint32_t w = 0;
+        check(famsa_prof_get(ctx_.get(), id, &w, &card, nullptr, nullptr));
+        scores.resize(((size_t)w + 1) * 32); counters.resize(((size_t)w + 1) * 32);
+        check(famsa_prof_get(ctx_.get(), id, nullptr, nullptr, scores.data(), counters.data()));
+    }
+    void Drop(const std::vector<uint32_t>& ids) { check(famsa_prof_drop(ctx_.get(), ids.data(), (uint32_t)ids.size())); }
+};
 
 // Level-synchronous order of the guide tree's merges (replaces CProfileQueue's one-at-a-time hand-out,
 // queues.cpp:17-187): tree = the reference's tree_structure, n leaves then internal nodes (left, right).
