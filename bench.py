@@ -238,6 +238,8 @@ def bench_dp(eng, torch, dist, world, rank, steps, warmup, l2_flush, stream, wan
         alg = sum((j[0].shape[0]) * (j[3].shape[0]) + 2 * (j[0].shape[0] + j[3].shape[0] - 2)
                   + 160 * j[0].shape[0] + 384 * j[3].shape[0] for j in jobs)
         achieved = alg / (kern_ms / 1e3) / 1e9
+        tprof = os.path.join(ROOT, "profiles", "dp_fill_traffic.json")
+        dp_traffic = json.load(open(tprof)).get("dram_bytes_per_launch") if os.path.exists(tprof) else None
         out = {"metric": "profile DP cells/sec", "unit": "cells/s", "value": cells * world * steps / (dev_ms / 1e3),
                "ms_per_step": dev_ms / steps,
                "config": {"workload": f"{n} independent profile-profile merges per GPU, {DP_CARD[0]}-{DP_CARD[1]} sequences x "
@@ -251,9 +253,11 @@ def bench_dp(eng, torch, dist, world, rank, steps, warmup, l2_flush, stream, wan
                                         "level), merged tables built on the device, only results + paths return"},
                "gpu_launches": int(launches),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": None, "peak_source": peak_src, "kernel": "fb::k_dp_prep + k_dp_t + k_dp_fill<8>",
+                            "traffic": dp_traffic, "peak_source": peak_src, "kernel": "fb::k_dp_prep + k_dp_t + k_dp_fill<8,1>",
                             "kernel_ms": kern_ms,
-                            "note": "latency-bound wavefront (int64 recurrence), not HBM-bound: see DESIGN.md section 4"}}
+                            "note": "achieved = SURVEY 8d algorithmic bytes / time of the three kernels; traffic = DRAM bytes of "
+                                    "k_dp_fill alone (it reads the 8 B/cell T that k_dp_t wrote); the int64 recurrence is bound "
+                                    "by issue slots and the staircase's idle slots, not by HBM: see DESIGN.md section 4"}}
         if want_cpu:
             from oracle import pyoracle
             if pyoracle.have_ref():

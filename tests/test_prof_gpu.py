@@ -150,3 +150,19 @@ def test_prof_errors(engine):
     with pytest.raises(FamsaError, match="not a resident profile"):
         engine.prof_drop(ids2)
     assert engine.prof_stats() == (0, 0)
+
+
+@needs_ref
+@pytest.mark.parametrize("env", [{"FAMSA_DP_MAX_CELLS": "60000"}, {"FAMSA_DP_CLUSTER_MIN": "40", "FAMSA_DP_TEAM_MIN": "32"},
+                                 {"FAMSA_DP_TEAM_MIN": "100000"}])
+def test_resident_launch_shapes(engine, monkeypatch, env):
+    """The resident path through sub-batches of a few merges, through the thread-block-cluster fill kernel, and
+    through the one-warp-per-merge kernel (development knobs of dp.cu force each shape on an ordinary family)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(41)
+    codes, off, lens = seqio.synth_family(36, 150, 41, sort_desc=False)
+    seqs = [seqio.decode(codes[int(o):int(o) + int(l)]) for o, l in zip(off, lens)]
+    merges = random_tree(36, rng, caterpillar=0.4)
+    g, recs = reference_merges(seqs, merges, threads=(1,), rng=rng, want_merged=True)
+    _run_and_check(engine, seqs, merges, g, recs, _score_matrix(36))
