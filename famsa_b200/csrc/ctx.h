@@ -126,6 +126,7 @@ int lcs_assign(famsa_ctx* ctx, const uint32_t* h_seed_ids, uint32_t n_seeds, int
 // dp.cu
 int dp_run_host(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int64_t gaps[4], famsa_dp_result* results,
                 uint8_t* path_buf, uint8_t* dirs_buf);
+int dp_check_results(const famsa_dp_result* results, uint32_t n);
 int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int64_t gaps[4],
                   famsa_dp_result* d_results, uint8_t* d_path, uint8_t* d_dirs, cudaStream_t st);
 // prof.cu

@@ -58,6 +58,7 @@ struct DpMeta {            // written by k_dp_prep
     const long long* SC; const int* CC;
     uint32_t WR, WC;
     int nR, nC, var, sw;
+    int bad;               // a gap / residue count of the ProfProf tables is negative: not a profile CProfile can build
 };
 
 // per column j of the column profile, 64 bytes, meaning depends on the variant:
@@ -122,6 +123,11 @@ struct Scratch {
 __device__ __forceinline__ long long pack2(int lo, int hi) { return (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo); }
 __device__ __forceinline__ int lo32(long long v) { return (int)(unsigned long long)v; }
 __device__ __forceinline__ int hi32(long long v) { return (int)((unsigned long long)v >> 32); }
+// The counts that weight the gap scores (how many sequences open / extend a gap, how many hold a residue) are
+// non-negative for every profile CProfile can build; k_dp_prep verifies that (DpMeta::bad) so that the cell loop may
+// multiply  int64 score x uint32 count  with two instructions (IMAD.WIDE.U32 + IMAD) instead of the signed 64 x 64 form.
+__device__ __forceinline__ unsigned ulo32(long long v) { return (unsigned)(unsigned long long)v; }
+__device__ __forceinline__ unsigned uhi32(long long v) { return (unsigned)((unsigned long long)v >> 32); }
 
 __device__ __forceinline__ long long shfl_up_ll(long long v)
 {
@@ -243,9 +249,33 @@ __global__ void __launch_bounds__(128) k_dp_prep(const DpParams P)
     const long long* SC = sw ? J.s1 : J.s2;  const int* CC = sw ? J.c1 : J.c2;
     const uint32_t WR = sw ? J.w2 : J.w1, WC = sw ? J.w1 : J.w2;
     const int nR = (int)(sw ? J.card2 : J.card1), nC = (int)(sw ? J.card1 : J.card2);
+    // ProfProf: every count the cell loop multiplies with must be >= 0 (see ulo32)
+    __shared__ int sm_bad;
+    if (tid == 0) sm_bad = 0;
+    __syncthreads();
+    if (var == 2) {
+        int bad = 0;
+        for (int side = 0; side < 2; ++side) {
+            const int* cnt = side ? CC : CR;
+            const uint32_t w = side ? WC : WR;
+            const int card = side ? nC : nR;
+            for (uint32_t c = 1 + tid; c <= w; c += nthr) {
+                int a, b, d, e, f, g;
+                solve_gaps(cnt, c, w, card, a, b, d, e, f, g);
+                bad |= (a | b | d | e | f | g) < 0;
+                const int* cc = cnt + (size_t)c * 32;
+                int neg = 0;
+                for (int k = 0; k < 30; ++k) neg |= cc[k];
+                bad |= neg < 0;
+            }
+        }
+        if (bad) sm_bad = 1;
+    }
+    __syncthreads();
     if (tid == 0) {
         DpMeta m;
         m.SR = SR; m.CR = CR; m.SC = SC; m.CC = CC; m.WR = WR; m.WC = WC; m.nR = nR; m.nC = nC; m.var = var; m.sw = sw;
+        m.bad = sm_bad;
         P.meta[jid] = m;
     }
     const Scratch L(J.w1, J.w2);
@@ -477,8 +507,8 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
     // per-stripe state, live across macro steps
     uint32_t i = 0;
     bool valid = false, last_row = false;
-    int s_o = 0, s_e = 0, s_to = 0, s_te = 0, k_e = 0, k_te = 0, g1o = 0, g1t = 0;
-    long long nongap1 = 0, srgo = 0, srge = 0, srto = 0, srte = 0, col0cost = 0;
+    unsigned s_o = 0, s_e = 0, s_to = 0, s_te = 0, k_e = 0, k_te = 0, g1o = 0, g1t = 0, nongap1 = 0;
+    long long srgo = 0, srge = 0, srto = 0, srte = 0, col0cost = 0;
     Cell cur = {kNeg, kNeg, kNeg, 0}, up = {kNeg, kNeg, kNeg, 0};
     long long t_next = 0;
     unsigned char* dk = dirs;          // this stripe's skewed directions / T: element (s, lane) at [s * 32 + lane]
@@ -508,14 +538,16 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
                 i = k * 32 + 1 + lane;
                 valid = i <= WR;
                 last_row = i == WR;
-                s_o = s_e = s_to = s_te = k_e = k_te = g1o = g1t = 0;
-                nongap1 = srgo = srge = srto = srte = col0cost = 0;
+                s_o = s_e = s_to = s_te = k_e = k_te = g1o = g1t = nongap1 = 0;
+                srgo = srge = srto = srte = col0cost = 0;
                 if (valid) {
                     if (VAR == 2) {
                         const int* rc = M.CR + (size_t)i * 32;
-                        solve_gaps(M.CR, i, WR, M.nR, s_o, s_e, s_to, s_te, k_e, k_te);
-                        g1o = rc[kGO]; g1t = rc[kTO];
-                        for (int q = 0; q < 24; ++q) nongap1 += rc[q];
+                        int a, b, c, d, e, f;
+                        solve_gaps(M.CR, i, WR, M.nR, a, b, c, d, e, f);
+                        s_o = (unsigned)a; s_e = (unsigned)b; s_to = (unsigned)c; s_te = (unsigned)d; k_e = (unsigned)e; k_te = (unsigned)f;
+                        g1o = (unsigned)rc[kGO]; g1t = (unsigned)rc[kTO];
+                        for (int q = 0; q < 24; ++q) nongap1 += (unsigned)rc[q];
                         const long long* sr = M.SR + (size_t)i * 32;
                         srgo = sr[kGO]; srge = sr[kGE]; srto = sr[kTO]; srte = sr[kTE];
                         col0cost = (i == 1 ? srto : srte) * M.nC;
@@ -543,7 +575,7 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
             }
             const Cell* chunk = sb[off & 1];
             const uint32_t s_begin = (uint32_t)off * kChunk;
-#pragma unroll 1
+#pragma unroll 2
             for (uint32_t u = 0; u < (uint32_t)kChunk; ++u) {
                 const uint32_t s = s_begin + u;
                 if (s >= steps) break;                                   // warp-uniform
@@ -606,16 +638,16 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
                     // profile_par.cpp:679-886
                     long long tD = Pd.D + t;
                     long long tH = Pd.H + t;
-                    tH += (long long)g1o * (ci.cge - ci.cgo) + (long long)g1t * (ci.cte - ci.cto);   // == 0 when both counts are 0
+                    tH += (ci.cge - ci.cgo) * g1o + (ci.cte - ci.cto) * g1t;       // == 0 when both counts are 0
                     long long tV = Pd.V + t + ci.chg * nongap1;
                     dD = pick3(tD, tH, tV, 0, 1, 2, out.D);
                     const long long gcH = ci.cgo * s_o + ci.cge * s_e + ci.cto * s_to + ci.cte * s_te;
                     tD = L.D + gcH;
                     tH = L.H + ci.cge * k_e + ci.cte * k_te;
                     dH = pick3(tD, three ? L.V + gcH : kNever, tH, 0, 2, 1, out.H);
-                    const long long gcV = srgo * lo32(ci.b0) + srge * hi32(ci.b0) + srto * lo32(ci.b1) + srte * hi32(ci.b1);
+                    const long long gcV = srgo * ulo32(ci.b0) + srge * uhi32(ci.b0) + srto * ulo32(ci.b1) + srte * uhi32(ci.b1);
                     tD = U.D + gcV;
-                    tV = U.V + srge * lo32(ci.b2) + srte * hi32(ci.b2);
+                    tV = U.V + srge * ulo32(ci.b2) + srte * uhi32(ci.b2);
                     dV = pick3(tD, three ? U.H + gcV : kNever, tV, 0, 1, 2, out.V);
                 }
                 unsigned char db = (unsigned char)(dD | dH << 2 | dV << 4);
@@ -748,7 +780,7 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_fill(cons
         r.last[0] = last[0]; r.last[1] = last[1]; r.last[2] = last[2];
         r.path_offset = J.path_off; r.dirs_offset = J.dirs_off;
         r.path_len = n; r.rows_width = WR; r.cols_width = WC;
-        r.swapped = (uint8_t)M.sw; r.variant = (uint8_t)M.var; r.pad[0] = r.pad[1] = 0;
+        r.swapped = (uint8_t)M.sw; r.variant = M.bad ? (uint8_t)0xFF : (uint8_t)M.var; r.pad[0] = r.pad[1] = 0;
         P.results[jid] = r;
     }
 }
@@ -926,6 +958,18 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
     return FAMSA_OK;
 }
 
+// variant 0xFF: k_dp_prep found a negative count in the tables (see ulo32) -- fail loudly rather than return a
+// result that could differ from the reference's signed arithmetic
+int dp_check_results(const famsa_dp_result* results, uint32_t n)
+{
+    for (uint32_t k = 0; k < n; ++k)
+        if (results[k].variant == 0xFF) {
+            set_error("dp job " + std::to_string(k) + ": a profile holds negative residue / gap counts");
+            return FAMSA_E_INVALID;
+        }
+    return FAMSA_OK;
+}
+
 int dp_run_host(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int64_t gaps[4], famsa_dp_result* results,
                 uint8_t* path_buf, uint8_t* dirs_buf)
 {
@@ -1009,7 +1053,7 @@ int dp_run_host(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int6
     if (path_total) FB_CUDA(cudaMemcpyAsync(path_buf, S.d_path.p, path_total, cudaMemcpyDeviceToHost, st));
     if (dirs_buf && dirs_total) FB_CUDA(cudaMemcpyAsync(dirs_buf, d_dirs, dirs_total, cudaMemcpyDeviceToHost, st));
     FB_CUDA(cudaStreamSynchronize(st));
-    return FAMSA_OK;
+    return dp_check_results(results, n);
 }
 
 } // namespace fb

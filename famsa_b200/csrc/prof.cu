@@ -388,6 +388,7 @@ int prof_merge_batch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t n,
     FB_CUDA(cudaMemcpyAsync(results, P.d_results.p, sizeof(famsa_dp_result) * n, cudaMemcpyDeviceToHost, st));
     FB_CUDA(cudaMemcpyAsync(path_buf, P.d_path.p, path_need, cudaMemcpyDeviceToHost, st));
     FB_CUDA(cudaStreamSynchronize(st));                             // the merged widths size the new tables
+    FB_TRY(dp_check_results(results, n));
 
     // merged tables: one slab per call
     size_t bytes = 0;

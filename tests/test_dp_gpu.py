@@ -159,3 +159,20 @@ def test_tiny_and_degenerate(engine):
     assert engine.dp_align_batch([], gaps) == []
     with pytest.raises(Exception):
         engine.dp_align_batch([(jobs[0][0][:1], jobs[0][1][:1], 1, jobs[0][3], jobs[0][4], 1)], gaps)
+
+
+def test_inconsistent_profile_is_rejected(engine):
+    """The cell loop multiplies scores with gap / residue counts as unsigned 32-bit values; a table whose counts are
+    negative (more gaps than members -- nothing CProfile can build) must fail loudly instead of diverging silently."""
+    from famsa_b200 import profiles
+    from famsa_b200.binding import FamsaError
+    rng = np.random.default_rng(2)
+    sm = profiles.synth_score_matrix(rng)
+    gaps = np.array([-14850, -1250, -660, -660], dtype=np.int64)
+    a = profiles.tables_from_rows(profiles.synth_alignment(5, 40, rng), sm, gaps)
+    b = profiles.tables_from_rows(profiles.synth_alignment(4, 35, rng), sm, gaps)
+    engine.dp_align_batch([(a[0], a[1], a[2], b[0], b[1], b[2])], gaps)          # consistent: fine
+    c = b[1].copy()
+    c[7, 25] = 9                                                                  # 9 gap-opens in a 4-member profile
+    with pytest.raises(FamsaError, match="negative"):
+        engine.dp_align_batch([(a[0], a[1], a[2], b[0], c, b[2])], gaps)
