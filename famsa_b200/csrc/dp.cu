@@ -137,6 +137,14 @@ __device__ __forceinline__ long long shfl_up_ll(long long v)
     return pack2(lo, hi);
 }
 
+__device__ __forceinline__ long long shfl_up_ll_by(long long v, int delta)
+{
+    int lo = lo32(v), hi = hi32(v);
+    lo = __shfl_up_sync(0xffffffffu, lo, delta);
+    hi = __shfl_up_sync(0xffffffffu, hi, delta);
+    return pack2(lo, hi);
+}
+
 // boundary-row traffic goes through L2 (.cg): written by lane 31 of one stripe, read by lane 0 of the next
 __device__ __forceinline__ void store_cell(Cell* p, const Cell& c)
 {
@@ -575,14 +583,31 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
             }
             const Cell* chunk = sb[off & 1];
             const uint32_t s_begin = (uint32_t)off * kChunk;
+            if (off == 0) {
+                // Column 0 of the stripe (profile_par.cpp:625-640) in closed form, so that the step below never sees
+                // j == 0:  D = H = NEG and V(i, 0) = max(D, V)(i-1, 0) + cost_i, a running sum down the rows (D(i-1, 0)
+                // is NEG below row 0).  `cur` starts as that cell, its direction byte (all-V) and, for the stripe's
+                // last row, its boundary-row copy are written here -- after this stripe has read the old brow[0].
+                const Cell B = chunk[0];
+                long long pre = col0cost;                               // 0 in lanes past the last row
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const long long v = shfl_up_ll_by(pre, o);
+                    if ((int)lane >= o) pre += v;
+                }
+                cur = Cell{kNeg, kNeg, last_row ? kNeg : (B.D > B.V ? B.D : B.V) + pre, 0};
+                if (valid) {
+                    dk[(size_t)lane * 32 + lane] = (unsigned char)(2 | 2 << 2 | 2 << 4);
+                    if (lane == 31 && !last_row) store_cell(brow, cur);
+                }
+            }
 #pragma unroll 2
             for (uint32_t u = 0; u < (uint32_t)kChunk; ++u) {
                 const uint32_t s = s_begin + u;
-                if (s >= steps) break;                                   // warp-uniform
                 // The whole body is executed by all 32 lanes (results are committed under `active`), so the warp
-                // never diverges around the shuffles.
+                // never diverges around the shuffles; steps past the end of the stripe (the last chunk) commit nothing.
                 const int j = (int)s - (int)lane;                        // column handled now
-                const bool active = valid && j >= 0 && j <= (int)WC;
+                const bool active = valid && j >= 1 && j <= (int)WC;
                 const long long t = t_next;
                 // T of the next step: one coalesced 256-byte read per warp; the lines of the step after next few are
                 // pulled into L1 by two lanes
@@ -650,21 +675,14 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
                     tV = U.V + srge * ulo32(ci.b2) + srte * uhi32(ci.b2);
                     dV = pick3(tD, three ? U.H + gcV : kNever, tV, 0, 1, 2, out.V);
                 }
-                unsigned char db = (unsigned char)(dD | dH << 2 | dV << 4);
-                if (j == 0) {                                            // column 0 (profile_par.cpp:625-640)
-                    out.D = kNeg; out.H = kNeg;
-                    out.V = last_row ? kNeg : (U.D > U.V ? U.D : U.V) + col0cost;
-                    db = 2 | 2 << 2 | 2 << 4;
-                }
-                if (active) {
-                    dk[(size_t)s * 32 + lane] = db;
-                    cur = out;
-                    if (last_row) {
-                        if (j == (int)WC) { last_out[0] = out.D; last_out[1] = out.H; last_out[2] = out.V; }
-                    } else if (lane == 31) {
-                        store_cell(brow + j, out);                       // park the stripe's last row (L2)
-                    }
-                }
+                const unsigned char db = (unsigned char)(dD | dH << 2 | dV << 4);
+                // Commit as straight-line code (selects + predicated stores).  `cur` only has to be protected while the
+                // lane still waits for its first column; what it holds past the last column is never read.
+                const bool commit = j >= 1;
+                cur.D = commit ? out.D : cur.D; cur.H = commit ? out.H : cur.H; cur.V = commit ? out.V : cur.V;
+                if (active) dk[(size_t)s * 32 + lane] = db;
+                if (active && lane == 31 && !last_row) store_cell(brow + j, out);   // park the stripe's last row (L2)
+                if (active && last_row && j == (int)WC) { last_out[0] = out.D; last_out[1] = out.H; last_out[2] = out.V; }
             }
         }
         // hand-over point: parked columns become visible to the next stripe
