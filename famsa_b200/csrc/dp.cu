@@ -82,7 +82,7 @@ static_assert(sizeof(RowNz) == 160, "RowNz layout");
 
 struct Cell { long long D, H, V, pad; };   // 32 bytes: two 16-byte cp.async / st.cg.v2 transfers
 static_assert(sizeof(Cell) == 32, "Cell layout");
-constexpr int kChunk = 16;                  // boundary-row columns handed over per cp.async batch / progress publish
+constexpr int kChunk = 8;                   // boundary-row columns handed over per cp.async batch (one macro step)
 
 __host__ __device__ inline unsigned long long align_up(unsigned long long v, unsigned long long a) { return (v + a - 1) / a * a; }
 
@@ -488,8 +488,8 @@ __global__ void __launch_bounds__(kTThreads) k_dp_unskew(const DpParams P)
 // Macro steps between consecutive stripes for a chunk of CH columns.  The consumer requests chunk `off` right after
 // the barrier that opens its macro step off-1; by then the producer (kLag macro steps ahead) must have parked column
 // off*CH + CH-1, which its lane 31 computes at wavefront step off*CH + CH-1 + 31:  kLag >= 3 + floor(30 / CH).
-// Block teams use CH = 16 (64 columns of lag, fewer barriers); clusters, which exist to shorten the critical path of
-// one very wide merge, use CH = 8 (48 columns of lag).
+// CH = 8 (48 columns of lag) for every team size: the time of a wide merge is stripes x lag x step time, and the extra
+// barriers cost less than the 16 columns of lag that CH = 16 would add (measured on the bench batch and on whole trees).
 __host__ __device__ constexpr int lag_of(int ch) { return 3 + 30 / ch; }
 
 template <int VAR, int NW, int CL, int CH>
@@ -701,7 +701,7 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32) k_dp_fill(cons
 {
     constexpr int kBlockWarps = NW == 1 ? kDpWarps : NW;
     __shared__ long long sm_last[kBlockWarps][3];
-    constexpr int CH = CL > 1 ? 8 : kChunk;
+    constexpr int CH = kChunk;
     __shared__ __align__(16) Cell sm_brow[kBlockWarps][2][CH];
     __shared__ unsigned char sm_tile[NW == 1 ? kDpWarps : 1][32 * 32];
     __shared__ __align__(16) long long sm_ring[kBlockWarps][kColFields][kRing];
@@ -1033,7 +1033,8 @@ int dp_run_host(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int6
         job_at[k + 1] = at;
     }
     {
-        const unsigned n_thr = bytes > (16u << 20) ? 4 : 1;
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned n_thr = bytes > (16u << 20) ? std::min(8u, hw) : 1;
         std::vector<std::thread> workers;
         std::vector<cudaError_t> errs(n_thr, cudaSuccess);
         for (unsigned t = 0; t < n_thr; ++t)
