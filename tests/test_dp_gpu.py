@@ -176,3 +176,21 @@ def test_inconsistent_profile_is_rejected(engine):
     c[7, 25] = 9                                                                  # 9 gap-opens in a 4-member profile
     with pytest.raises(FamsaError, match="negative"):
         engine.dp_align_batch([(a[0], a[1], a[2], b[0], c, b[2])], gaps)
+
+
+def test_scores_beyond_32_bits(engine):
+    """k_dp_t has a 32 x 32 -> 64 bit path for tables whose scores fit in int32 (every realistic profile) and a
+    32 x 64 path otherwise; substitution scores of ~1e9 push the tables past 2^31 and exercise the latter."""
+    from famsa_b200 import profiles
+    rng = np.random.default_rng(9)
+    sm = profiles.synth_score_matrix(rng) * 300_000
+    gaps = np.array([-14850, -1250, -660, -660], dtype=np.int64) * 300_000
+    jobs = []
+    for _ in range(6):
+        a = profiles.tables_from_rows(profiles.synth_alignment(int(rng.integers(3, 9)), int(rng.integers(40, 140)), rng), sm, gaps)
+        b = profiles.tables_from_rows(profiles.synth_alignment(int(rng.integers(3, 9)), int(rng.integers(40, 140)), rng), sm, gaps)
+        jobs.append((a[0], a[1], a[2], b[0], b[1], b[2]))
+    assert max(int(np.abs(j[3]).max()) for j in jobs) > 2 ** 31
+    got = engine.dp_align_batch(jobs, gaps, want_dirs=True)
+    for r, j in zip(got, jobs):
+        assert_same(r, pyoracle.dp_align(*j, gaps))
