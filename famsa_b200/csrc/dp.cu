@@ -377,6 +377,80 @@ __host__ __device__ inline unsigned long long t_blocks(uint32_t w1, uint32_t w2)
     return a > b ? a : b;
 }
 
+// The usual ProfProf case -- every score fits in int32 and the row profile has at most 127 (NDA = 1) or 32767
+// (NDA = 2) members, so every counter is one or two byte digits: T = C x S^T is an exact integer GEMM with K = 32
+// symbols, done on the tensor cores.  Scores are split into four byte digits (three unsigned, the top one signed);
+// IMMA.16832 accumulates each digit plane in int32 (30 x 255 x 255 < 2^21) and the planes are recombined with shifts in
+// 64 bits.  Warp w owns columns j0 + 32w .. +31 (four 8-column tiles) and both 16-row tiles of the stripe.
+template <int NDA>
+__device__ __forceinline__ void t_tile_mma(const DpMeta& M, uint32_t i0, uint32_t nrows, uint32_t j0, uint32_t WC,
+                                           long long (*tile)[kTCols + 2])
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
+    unsigned afrag[NDA][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {                              // h&1: row +8, h>>1: symbols 16..31
+            const uint32_t row = (uint32_t)mt * 16 + g + (h & 1) * 8, k = (h >> 1) * 16 + t4 * 4;
+            unsigned lo = 0, hi = 0;
+            if (row < nrows) {
+                const int4 c = *reinterpret_cast<const int4*>(M.CR + (size_t)(i0 + row) * 32 + k);
+                const unsigned x = (unsigned)c.x, y = (unsigned)c.y, z = (unsigned)c.z, w = (unsigned)c.w;
+                lo = (x & 0xffu) | (y & 0xffu) << 8 | (z & 0xffu) << 16 | (w & 0xffu) << 24;
+                hi = (x >> 8 & 0xffu) | (y >> 8 & 0xffu) << 8 | (z >> 8 & 0xffu) << 16 | (w >> 8 & 0xffu) << 24;
+                if (k == 28) { lo &= 0xffffu; hi &= 0xffffu; }     // rows 30 (GAP) and 31 (GUARD) are not part of the sum
+            }
+            afrag[0][mt][h] = lo;
+            if (NDA == 2) afrag[NDA - 1][mt][h] = hi;
+        }
+#pragma unroll 1
+    for (int nt = 0; nt < 4; ++nt) {
+        const uint32_t cb = warp * 32 + (uint32_t)nt * 8;           // tile-local column of this 8-column tile
+        const uint32_t jc = j0 + cb + g;                            // the column whose scores this lane supplies
+        const long long* sc = M.SC + (size_t)(jc <= WC ? jc : 1) * 32;
+        unsigned bfrag[4][2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const longlong2 p = *reinterpret_cast<const longlong2*>(sc + h * 16 + t4 * 4);
+            const longlong2 q = *reinterpret_cast<const longlong2*>(sc + h * 16 + t4 * 4 + 2);
+            const unsigned v0 = (unsigned)p.x, v1 = (unsigned)p.y, v2 = (unsigned)q.x, v3 = (unsigned)q.y;
+            const unsigned t01 = __byte_perm(v0, v1, 0x5140), t23 = __byte_perm(v2, v3, 0x5140);   // bytes 0,1 interleaved
+            const unsigned u01 = __byte_perm(v0, v1, 0x7362), u23 = __byte_perm(v2, v3, 0x7362);   // bytes 2,3 interleaved
+            bfrag[0][h] = __byte_perm(t01, t23, 0x5410); bfrag[1][h] = __byte_perm(t01, t23, 0x7632);
+            bfrag[2][h] = __byte_perm(u01, u23, 0x5410); bfrag[3][h] = __byte_perm(u01, u23, 0x7632);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            long long out[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int da = 0; da < NDA; ++da) {
+                int acc[4][4];
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    acc[d][0] = acc[d][1] = acc[d][2] = acc[d][3] = 0;
+                    if (d < 3)
+                        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                     : "+r"(acc[d][0]), "+r"(acc[d][1]), "+r"(acc[d][2]), "+r"(acc[d][3])
+                                     : "r"(afrag[da][mt][0]), "r"(afrag[da][mt][1]), "r"(afrag[da][mt][2]), "r"(afrag[da][mt][3]),
+                                       "r"(bfrag[d][0]), "r"(bfrag[d][1]));
+                    else
+                        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                     : "+r"(acc[d][0]), "+r"(acc[d][1]), "+r"(acc[d][2]), "+r"(acc[d][3])
+                                     : "r"(afrag[da][mt][0]), "r"(afrag[da][mt][1]), "r"(afrag[da][mt][2]), "r"(afrag[da][mt][3]),
+                                       "r"(bfrag[d][0]), "r"(bfrag[d][1]));
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    out[c] += ((long long)acc[0][c] + ((long long)acc[1][c] << 8) + ((long long)acc[2][c] << 16) + ((long long)acc[3][c] << 24)) << (8 * da);
+            }
+            // c0,c1: row g, columns 2*t4, 2*t4+1;  c2,c3: row g+8
+            *reinterpret_cast<longlong2*>(&tile[mt * 16 + g][cb + t4 * 2]) = make_longlong2(out[0], out[1]);
+            *reinterpret_cast<longlong2*>(&tile[mt * 16 + g + 8][cb + t4 * 2]) = make_longlong2(out[2], out[3]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kTCols) k_dp_t(const DpParams P)
 {
     __shared__ __align__(16) long long tile[32][kTCols + 2];     // +2: rows 16 bytes apart in the banks
@@ -401,66 +475,9 @@ __global__ void __launch_bounds__(kTCols) k_dp_t(const DpParams P)
     const uint32_t nrows = WR - i0 + 1 < 32 ? WR - i0 + 1 : 32;
     const bool ok = j <= WC;
     if (M.var == 2 && M.narrow && M.nR <= 127) {
-        // The usual case -- every score fits in int32 and the row profile has at most 127 members, so every counter is
-        // an int8: T = C x S^T is an exact integer GEMM with K = 32 symbols, done on the tensor cores.  Scores are
-        // split into four byte digits (three unsigned, the top one signed); IMMA.16832 accumulates each digit plane in
-        // int32 (30 x 127 x 255 < 2^20) and the planes are recombined with shifts in 64 bits.  Warp w owns columns
-        // j0 + 32w .. +31 (four 8-column tiles), both 16-row tiles of the stripe.
-        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t4 = lane & 3;
-        unsigned afrag[2][4];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {                          // h&1: row +8, h>>1: symbols 16..31
-                const uint32_t row = (uint32_t)mt * 16 + g + (h & 1) * 8, k = (h >> 1) * 16 + t4 * 4;
-                unsigned v = 0;
-                if (row < nrows) {
-                    const int4 c = *reinterpret_cast<const int4*>(M.CR + (size_t)(i0 + row) * 32 + k);
-                    v = (unsigned)c.x | (unsigned)c.y << 8 | (unsigned)c.z << 16 | (unsigned)c.w << 24;
-                    if (k == 28) v &= 0xffffu;                      // rows 30 (GAP) and 31 (GUARD) are not part of the sum
-                }
-                afrag[mt][h] = v;
-            }
-#pragma unroll 1
-        for (int nt = 0; nt < 4; ++nt) {
-            const uint32_t cb = warp * 32 + (uint32_t)nt * 8;       // tile-local column of this 8-column tile
-            const uint32_t jc = j0 + cb + g;                        // the column whose scores this lane supplies
-            const long long* sc = M.SC + (size_t)(jc <= WC ? jc : 1) * 32;
-            unsigned bfrag[4][2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const longlong2 p = *reinterpret_cast<const longlong2*>(sc + h * 16 + t4 * 4);
-                const longlong2 q = *reinterpret_cast<const longlong2*>(sc + h * 16 + t4 * 4 + 2);
-                const unsigned v0 = (unsigned)p.x, v1 = (unsigned)p.y, v2 = (unsigned)q.x, v3 = (unsigned)q.y;
-                const unsigned t01 = __byte_perm(v0, v1, 0x5140), t23 = __byte_perm(v2, v3, 0x5140);   // bytes 0,1 interleaved
-                const unsigned u01 = __byte_perm(v0, v1, 0x7362), u23 = __byte_perm(v2, v3, 0x7362);   // bytes 2,3 interleaved
-                bfrag[0][h] = __byte_perm(t01, t23, 0x5410); bfrag[1][h] = __byte_perm(t01, t23, 0x7632);
-                bfrag[2][h] = __byte_perm(u01, u23, 0x5410); bfrag[3][h] = __byte_perm(u01, u23, 0x7632);
-            }
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                int acc[4][4];
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    acc[d][0] = acc[d][1] = acc[d][2] = acc[d][3] = 0;
-                    if (d < 3)
-                        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                     : "+r"(acc[d][0]), "+r"(acc[d][1]), "+r"(acc[d][2]), "+r"(acc[d][3])
-                                     : "r"(afrag[mt][0]), "r"(afrag[mt][1]), "r"(afrag[mt][2]), "r"(afrag[mt][3]), "r"(bfrag[d][0]), "r"(bfrag[d][1]));
-                    else
-                        asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                                     : "+r"(acc[d][0]), "+r"(acc[d][1]), "+r"(acc[d][2]), "+r"(acc[d][3])
-                                     : "r"(afrag[mt][0]), "r"(afrag[mt][1]), "r"(afrag[mt][2]), "r"(afrag[mt][3]), "r"(bfrag[d][0]), "r"(bfrag[d][1]));
-                }
-                long long out[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    out[c] = (long long)acc[0][c] + ((long long)acc[1][c] << 8) + ((long long)acc[2][c] << 16) + ((long long)acc[3][c] << 24);
-                // c0,c1: row g, columns 2*t4, 2*t4+1;  c2,c3: row g+8
-                *reinterpret_cast<longlong2*>(&tile[mt * 16 + g][cb + t4 * 2]) = make_longlong2(out[0], out[1]);
-                *reinterpret_cast<longlong2*>(&tile[mt * 16 + g + 8][cb + t4 * 2]) = make_longlong2(out[2], out[3]);
-            }
-        }
+        t_tile_mma<1>(M, i0, nrows, j0, WC, tile);
+    } else if (M.var == 2 && M.narrow && M.nR <= 32767) {
+        t_tile_mma<2>(M, i0, nrows, j0, WC, tile);
     } else if (M.var == 2) {
         unsigned slo[30], shi[30];
         {
