@@ -227,7 +227,8 @@ struct DpParams {
 // ------------------------------------------------------------------------------------------------
 // k_dp_prep: one block per job
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_dp_prep(const DpParams P)
+constexpr int kPrepThreads = 512;
+__global__ void __launch_bounds__(kPrepThreads) k_dp_prep(const DpParams P)
 {
     __shared__ unsigned long long sm_nz[2];
     const uint32_t jid = P.job_base + blockIdx.x;
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(128) k_dp_prep(const DpParams P)
     // row 0 (profile_par.cpp:531-555; SeqSeq profile_seq.cpp:48-69): H(0, j) is a running sum over the columns --
     // every thread sums a contiguous segment, the segment totals are combined through shared memory
     {
-        __shared__ long long sm_seg[128];
+        __shared__ long long sm_seg[kPrepThreads];
         auto term = [&](uint32_t j) -> long long {
             const long long* sc = SC + (size_t)j * 32;
             if (var == 0) return j == 1 ? to : te;             // max(H, D = NEG) + te
@@ -1004,7 +1005,7 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
         P.tblock = S.d_tblock.as<unsigned long long>();
         P.t2block = P.tblock + (m + 1);
         P.results = d_results;
-        k_dp_prep<<<m, 128, 0, st>>>(P);
+        k_dp_prep<<<m, kPrepThreads, 0, st>>>(P);
         FB_CUDA(cudaGetLastError());
         k_dp_t<<<(unsigned)t2block[m], kTCols, 0, st>>>(P);
         FB_CUDA(cudaGetLastError());

@@ -188,7 +188,7 @@ int famsa_dp_align_batch(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n_jo
                          famsa_dp_result* results, uint8_t* path_buf, uint8_t* dirs_buf);
 
 /* Same, but with the profile tables already resident in HBM (famsa_dp_profile pointers are DEVICE
- * pointers; results/path/dirs are DEVICE buffers); used to time the kernels without PCIe.
+ * pointers, 16-byte aligned; results/path/dirs are DEVICE buffers); used to time the kernels without PCIe.
  * Variant/orientation are then decided on the device too.  stream: cudaStream_t or NULL. */
 int famsa_dp_align_batch_device(famsa_ctx* ctx, const famsa_dp_job* h_jobs_with_device_ptrs, uint32_t n_jobs,
                                 const int64_t gaps[4], famsa_dp_result* d_results, uint8_t* d_path_buf,
