@@ -220,6 +220,30 @@ class Engine:
             out.append(d)
         return out
 
+    def dp_jobs(self, jobs):
+        """ctypes job array for dp_align_batch_raw (keeps the numpy tables alive): build once, call many times."""
+        n = len(jobs)
+        arr = (DpJob * max(n, 1))()
+        keep = []
+        path_total = 0
+        for k, (s1, c1, k1, s2, c2, k2) in enumerate(jobs):
+            s1 = np.ascontiguousarray(s1, dtype=np.int64); c1 = np.ascontiguousarray(c1, dtype=np.int32)
+            s2 = np.ascontiguousarray(s2, dtype=np.int64); c2 = np.ascontiguousarray(c2, dtype=np.int32)
+            keep += [s1, c1, s2, c2]
+            arr[k].p1 = DpProfile(s1.ctypes.data, c1.ctypes.data, s1.shape[0] - 1, k1)
+            arr[k].p2 = DpProfile(s2.ctypes.data, c2.ctypes.data, s2.shape[0] - 1, k2)
+            path_total += s1.shape[0] + s2.shape[0] - 2
+        return arr, keep, path_total
+
+    def dp_align_batch_raw(self, arr, n: int, gaps, res, path):
+        """famsa_dp_align_batch on prebuilt arrays (res: (DpResult * n)(), path: uint8 numpy buffer) -- the call a C
+        caller makes, without this binding's per-job Python work."""
+        self._check(self.lib.famsa_dp_align_batch(self.h, C.byref(arr), n, _ptr(gaps), C.byref(res), _ptr(path), None))
+
+    def prof_merge_batch_raw(self, arr, n: int, gaps, ids, res, path):
+        """famsa_prof_merge_batch on prebuilt arrays (arr: (ProfMerge * n)(), ids: uint32 numpy, res: (DpResult * n)())."""
+        self._check(self.lib.famsa_prof_merge_batch(self.h, C.byref(arr), n, _ptr(gaps), _ptr(ids), C.byref(res), _ptr(path), path.size))
+
     def dp_align_batch_device(self, job_array, n: int, gaps, d_results: int, d_path: int, d_dirs: int = 0, stream: int = 0):
         """job_array: ctypes (DpJob * n) whose table pointers are DEVICE pointers; d_* are device pointers."""
         g = np.ascontiguousarray(gaps, dtype=np.int64)
