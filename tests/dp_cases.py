@@ -128,3 +128,71 @@ def resident_progressive_alignment(engine, seqs, merges, gaps, score_matrix, on_
             on_level(lvl, ids, res)
     root = n + len(merges) - 1
     return {no: row.tobytes().decode() for no, row in rows[root].items()}, results, node[root]
+
+
+def assemble_rows(seqs, merges, results):
+    """Final alignment {seq_no: gapped string} from the per-merge paths (what FinalizeGaps does on the host):
+    H steps are gap columns in the members of the DP's row profile, V steps in those of the column profile."""
+    n = len(seqs)
+    rows = {i: {i: np.frombuffer(seqs[i].encode(), dtype=np.uint8)} for i in range(n)}
+    for k, (a, b) in enumerate(merges):
+        r = results[k]
+        ra, rb = rows.pop(a), rows.pop(b)
+        rrows, crows = (rb, ra) if r["swapped"] else (ra, rb)
+        out = {}
+        for members, gapdir in ((rrows, 1), (crows, 2)):
+            keep = r["path"] != gapdir
+            for no, row in members.items():
+                g = np.full(len(r["path"]), ord("-"), dtype=np.uint8)
+                g[keep] = row
+                out[no] = g
+        rows[n + k] = out
+    return {no: row.tobytes().decode() for no, row in rows[n + len(merges) - 1].items()}
+
+
+class OracleEngine:
+    """CPU stand-in for Engine's resident-profile calls, built on the oracle (tests of the multi-rank host logic run
+    without a GPU): same ids / leaf handles / consume-on-merge semantics as famsa_prof_*."""
+    def __init__(self):
+        self.tab = {}
+        self.next = 0
+
+    def upload(self, codes, off, lens):
+        self.seqs = [np.asarray(codes[int(o):int(o) + int(l)]) for o, l in zip(off, lens)]
+
+    def prof_set_scoring(self, sm):
+        self.sm = np.asarray(sm, dtype=np.int64)
+
+    def _tables(self, h, gaps):
+        from famsa_b200 import profiles
+        from famsa_b200.binding import PROF_LEAF
+        if h & PROF_LEAF:
+            return profiles.tables_from_rows(self.seqs[h & ~PROF_LEAF][None, :], self.sm, gaps)
+        return self.tab.pop(h)
+
+    def prof_merge_batch(self, pairs, gaps, widths):
+        ids, out = [], []
+        for a, b in pairs:
+            ta, tb = self._tables(a, gaps), self._tables(b, gaps)
+            r = pyoracle.dp_align(*ta, *tb, gaps)
+            rp, cp = (tb, ta) if r["swapped"] else (ta, tb)
+            s, c, _, _ = pyoracle.dp_construct(rp, cp, r["path"], gaps)
+            self.tab[self.next] = (s, c, ta[2] + tb[2])
+            ids.append(self.next); self.next += 1
+            out.append(dict(path=r["path"], total=r["total"], last=r["last"], swapped=r["swapped"], variant=r["variant"]))
+        return ids, out
+
+    def prof_get(self, pid, tables=True):
+        s, c, k = self.tab[pid]
+        return (s, c, k) if tables else (s.shape[0] - 1, k)
+
+    def prof_put(self, profs):
+        ids = []
+        for p in profs:
+            self.tab[self.next] = p
+            ids.append(self.next); self.next += 1
+        return ids
+
+    def prof_drop(self, ids):
+        for i in ids:
+            del self.tab[int(i)]

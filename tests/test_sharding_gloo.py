@@ -56,3 +56,62 @@ def test_schedule_levels_and_shards():
     assert lv == [[0, 1, 2], [3], [4]]
     parts = shard_level([0, 1, 2, 3], [10, 7, 5, 4], 2)
     assert sorted(sum(parts, [])) == [0, 1, 2, 3] and abs(sum([10, 7, 5, 4][k] for k in parts[0]) - 13) <= 3
+
+
+def _tree_worker(rank, world, port, n, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from dp_cases import OracleEngine, random_tree
+    from famsa_b200 import schedule
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    z = np.load(os.path.join(out_dir, "case.npz"))
+    seqs = [str(s) for s in z["seqs"]]
+    merges = [tuple(int(x) for x in m) for m in z["merges"]]
+    codes, off, lens = seqio.pack([seqio.encode(s) for s in seqs])
+    eng = OracleEngine()
+    eng.upload(codes, off, lens)
+    eng.prof_set_scoring(z["sm"])
+    results, root = schedule.sharded_resident_alignment(eng, dist, rank, world, len(seqs), lens, merges, z["gaps"])
+    everything = [None] * world
+    dist.all_gather_object(everything, {k: (r["path"], r["swapped"], r["total"]) for k, r in results.items()})
+    if rank == 0:
+        merged = {}
+        for part in everything:
+            assert not (set(part) & set(merged)), "a merge ran on two ranks"
+            merged.update(part)
+        np.savez(os.path.join(out_dir, "out.npz"), keys=np.array(sorted(merged)),
+                 **{f"p{k}": merged[k][0] for k in merged}, sw=np.array([merged[k][1] for k in sorted(merged)]),
+                 tot=np.array([merged[k][2] for k in sorted(merged)]), n_ranks_with_work=sum(1 for p in everything if p),
+                 live=len(eng.tab), root=root)
+    else:
+        assert root is None and not eng.tab, "non-root ranks must hand everything over"
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("world", [2, 3])
+def test_subtree_sharded_resident_alignment(tmp_path, world):
+    """HP-2 on several ranks with resident profiles: whole subtrees per rank (no communication), subtree roots handed
+    to rank 0, top merges there.  Every merge runs exactly once and the assembled alignment is the reference's."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from dp_cases import assemble_rows, random_tree, reference_merges
+    n = 26
+    rng = np.random.default_rng(8)
+    codes, off, lens = seqio.synth_family(n, 45, 8, sort_desc=False)
+    seqs = [seqio.decode(codes[int(o):int(o) + int(l)]) for o, l in zip(off, lens)]
+    merges = random_tree(n, rng, 0.3)
+    g, recs = reference_merges(seqs, merges, threads=(1,))
+    dp = pyoracle.RefDp(n); sm = dp.score_matrix(); dp.close()
+    np.savez(tmp_path / "case.npz", seqs=np.array(seqs), merges=np.array(merges), sm=sm, gaps=g)
+    port = 29640 + world
+    mp.spawn(_tree_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+    z = np.load(tmp_path / "out.npz")
+    assert list(z["keys"]) == list(range(len(merges))) and int(z["n_ranks_with_work"]) == world
+    assert int(z["live"]) == 1
+    results = {int(k): dict(path=z[f"p{k}"], swapped=bool(s), total=int(t)) for k, s, t in zip(z["keys"], z["sw"], z["tot"])}
+    assert [results[k]["total"] for k in range(len(merges))] == [r["total"] for r in recs]
+    assert assemble_rows(seqs, merges, results) == recs[-1]["rows"]
