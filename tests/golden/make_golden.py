@@ -52,8 +52,9 @@ def make_dp():
                             costs, and the reference outcome (traceback path, total score); generation asserts that
                             the reference run reproduces upgma.pp.fasta byte for byte.
     adeno_upgma_merges.npz  all 241 merges of test/adeno_fiber/upgma.dnd (refinement off): sequences, merge list and
-                            per-merge reference outcome; generation asserts the final alignment equals
-                            upgma.no_refine.fasta.  Inputs of each merge are rebuilt by the tests with oracle/_ref.
+                            per-merge reference outcome (total, path, CRC32 of the merged profile's scores and
+                            counters as the reference's ConstructProfile built them) and the score matrix;
+                            generation asserts the final alignment equals upgma.no_refine.fasta.
     """
     sys.path.insert(0, os.path.join(HERE, ".."))
     from oracle import pyoracle
@@ -89,17 +90,23 @@ def make_dp():
     lseqs = [name2seq[n].upper() for n in leaves]
     sys.path.insert(0, os.path.join(HERE, ".."))
     from dp_cases import reference_merges
-    g, recs = reference_merges(lseqs, merges, threads=(1,))
+    import zlib
+    g, recs = reference_merges(lseqs, merges, threads=(1,), want_merged=True)
     final = recs[-1]["rows"]
     assert all(final[i] == gold[leaves[i]].upper() for i in range(len(leaves))), "does not reproduce upgma.no_refine.fasta"
-    totals, paths, plen, swapped = [], [], [], []
+    totals, paths, plen, swapped, tcrc = [], [], [], [], []
     for r in recs:
         o = pyoracle.dp_align(*r["job"], g)
         pth = pyoracle.path_from_rows(r["rows"], r["m1"], r["m2"], o["swapped"])
         totals.append(r["total"]); paths.append(pth); plen.append(len(pth)); swapped.append(o["swapped"])
+        # the scores/counters ConstructProfile built for the merged profile, as CRC32 of the raw tables
+        ms, mc, _ = r["merged"]
+        tcrc.append((zlib.crc32(np.ascontiguousarray(ms).tobytes()), zlib.crc32(np.ascontiguousarray(mc).tobytes())))
+    dp2 = pyoracle.RefDp(len(lseqs)); sm = dp2.score_matrix(); dp2.close()
     np.savez_compressed(os.path.join(HERE, "adeno_upgma_merges.npz"), seqs=np.array(lseqs), merges=np.array(merges),
                         gaps=g, totals=np.array(totals, dtype=np.int64), path=np.concatenate(paths),
-                        path_len=np.array(plen), swapped=np.array(swapped))
+                        path_len=np.array(plen), swapped=np.array(swapped), merged_crc=np.array(tcrc, dtype=np.uint32),
+                        score_matrix=sm)
     print("adeno_upgma_merges.npz:", len(recs), "merges, sum path", sum(plen))
 
 

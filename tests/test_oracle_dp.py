@@ -139,3 +139,27 @@ def test_oracle_construct_random_families(seed, n, length, gaps):
     g, recs = reference_merges(seqs, merges, threads=(1, 2), rng=rng, gaps=gaps, want_merged=True)
     res = [pyoracle.dp_align(*r["job"], g) for r in recs]
     _check_construct(res, recs, g)
+
+
+def test_oracle_progressive_alignment_from_fixture_alone():
+    """No oracle/_ref needed: leaves from the host mirror of CalculateCountersScores, DP + merged tables from the
+    restatement, level by level over the 241 merges behind upgma.no_refine.fasta; totals, paths and the CRC32 of every
+    merged profile's scores/counters must equal what the reference produced when the fixture was generated."""
+    from famsa_b200 import profiles
+    z = np.load(os.path.join(GOLDEN, "adeno_upgma_merges.npz"))
+    seqs = [str(s) for s in z["seqs"]]
+    merges = [tuple(int(x) for x in m) for m in z["merges"]]
+    g, sm = z["gaps"], z["score_matrix"]
+    n = len(seqs)
+    node = {i: profiles.tables_from_rows(seqio.encode(seqs[i])[None, :], sm, g) for i in range(n)}
+    at = 0
+    for k, (a, b) in enumerate(merges):
+        ta, tb = node.pop(a), node.pop(b)
+        r = pyoracle.dp_align(*ta, *tb, g)
+        assert r["total"] == int(z["totals"][k]) and r["swapped"] == bool(z["swapped"][k])
+        assert np.array_equal(r["path"], z["path"][at:at + int(z["path_len"][k])])
+        at += int(z["path_len"][k])
+        rp, cp = (tb, ta) if r["swapped"] else (ta, tb)
+        s, c, _, _ = pyoracle.dp_construct(rp, cp, r["path"], g)
+        assert (zlib.crc32(s.tobytes()), zlib.crc32(c.tobytes())) == tuple(int(x) for x in z["merged_crc"][k]), f"merge {k}"
+        node[n + k] = (s, c, ta[2] + tb[2])

@@ -166,3 +166,23 @@ def test_resident_launch_shapes(engine, monkeypatch, env):
     merges = random_tree(36, rng, caterpillar=0.4)
     g, recs = reference_merges(seqs, merges, threads=(1,), rng=rng, want_merged=True)
     _run_and_check(engine, seqs, merges, g, recs, _score_matrix(36))
+
+
+def test_resident_golden_tables_without_reference(engine):
+    """Needs only the committed fixture: the resident path over all 241 merges behind upgma.no_refine.fasta; totals,
+    paths and the CRC32 of every merged profile's scores/counters equal the reference's (recorded at generation)."""
+    import zlib
+    z = np.load(os.path.join(GOLDEN, "adeno_upgma_merges.npz"))
+    seqs = [str(s) for s in z["seqs"]]
+    merges = [tuple(int(x) for x in m) for m in z["merges"]]
+    crcs = {}
+
+    def on_level(lvl, ids, res):
+        for k, pid in zip(lvl, ids):
+            s, c, _ = engine.prof_get(pid)
+            crcs[k] = (zlib.crc32(s.tobytes()), zlib.crc32(c.tobytes()))
+    rows, res, root = resident_progressive_alignment(engine, seqs, merges, z["gaps"], z["score_matrix"], on_level)
+    engine.prof_drop([root])
+    assert [r["total"] for r in res] == [int(t) for t in z["totals"]]
+    assert np.array_equal(np.concatenate([r["path"] for r in res]), z["path"])
+    assert [crcs[k] for k in range(len(merges))] == [tuple(int(x) for x in row) for row in z["merged_crc"]]
