@@ -931,8 +931,8 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
     if (const char* e = getenv("FAMSA_DP_MAX_CELLS")) max_cells = strtoull(e, nullptr, 10);     // development knob
     uint32_t team_min = kDpTeamMinWidth;
     if (const char* e = getenv("FAMSA_DP_TEAM_MIN")) team_min = (uint32_t)atoi(e);               // development knob
-    int nw = kDpTeamWarps;
-    if (const char* e = getenv("FAMSA_DP_TEAM_WARPS")) nw = atoi(e);                             // development knob
+    int nw_forced = 0;
+    if (const char* e = getenv("FAMSA_DP_TEAM_WARPS")) nw_forced = atoi(e);                      // development knob
     uint32_t cluster_min = kDpClusterMinWidth;
     if (const char* e = getenv("FAMSA_DP_CLUSTER_MIN")) cluster_min = (uint32_t)atoi(e);         // development knob
 
@@ -1032,6 +1032,13 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const in
             DpParams Q = P;
             Q.order = P.order + n_huge;
             Q.n_jobs = n_big - n_huge;
+            // Team size by how many merges there are: a team's ramp-up / ramp-down (stripes start 6 macro steps apart)
+            // idles a third of an 8-warp team on ~14-stripe merges, so when the level is large enough to fill the SMs with
+            // smaller teams (16 warps per SM either way) those waste less -- 4 warps from 4 merges per SM on, 2 from 8.
+            int nw = kDpTeamWarps;
+            if (Q.n_jobs >= 8u * (uint32_t)ctx->sm_count) nw = 2;
+            else if (Q.n_jobs >= 4u * (uint32_t)ctx->sm_count) nw = 4;
+            if (nw_forced) nw = nw_forced;
             switch (nw) {
             case 2: k_dp_fill<2, 1><<<Q.n_jobs, 2 * 32, 0, st>>>(Q); break;
             case 4: k_dp_fill<4, 1><<<Q.n_jobs, 4 * 32, 0, st>>>(Q); break;
