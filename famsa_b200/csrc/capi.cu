@@ -65,7 +65,7 @@ void famsa_destroy(famsa_ctx* ctx)
     fb::LcsState& S = ctx->lcs;
     for (fb::DevBuf* b : {&S.d_perm, &S.d_invperm, &S.d_len_sorted, &S.d_code_off, &S.d_codes, &S.d_blob,
                           &S.d_group_blob, &S.d_raw_codes, &S.d_raw_off, &S.d_raw_len, &S.d_flags, &S.d_pow075, &S.d_assign_lcs, &S.d_pow075_f64, &S.d_prim_tri, &S.d_prim_side, &S.d_prim_state,
-                          &S.d_prim_out, &S.d_prim_sideidx, &S.d_prim_cand,
+                          &S.d_prim_out, &S.d_prim_sideidx, &S.d_prim_cand, &S.d_prim_dtri, &S.d_prim_comp, &S.d_prim_best, &S.d_prim_part,
                           &S.d_assign, &S.d_mind, &S.d_tiles,
                           &S.d_res, &S.d_refpos, &S.d_ids_a, &S.d_ids_b, &S.d_out_stage, &S.d_masks64, &S.d_x64})
         b->release();

@@ -52,7 +52,8 @@ struct LcsState {
     std::vector<uint32_t> h_long;      // caller ids longer than the tile kernel handles as mask side
     DevBuf d_perm, d_invperm, d_len_sorted, d_code_off, d_codes, d_blob, d_group_blob;
     DevBuf d_raw_codes, d_raw_off, d_raw_len, d_flags, d_pow075, d_assign_lcs, d_assign, d_mind,
-        d_pow075_f64, d_prim_tri, d_prim_side, d_prim_state, d_prim_out, d_prim_sideidx, d_prim_cand;
+        d_pow075_f64, d_prim_tri, d_prim_side, d_prim_state, d_prim_out, d_prim_sideidx, d_prim_cand,
+        d_prim_dtri, d_prim_comp, d_prim_best, d_prim_part;
     // per-call scratch
     DevBuf d_tiles, d_res, d_refpos, d_ids_a, d_ids_b, d_out_stage, d_masks64, d_x64;
     // last-call timing

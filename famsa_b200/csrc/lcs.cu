@@ -26,6 +26,8 @@
 #include <cmath>
 #include <cstring>
 #include <numeric>
+#include <queue>
+#include <tuple>
 
 #include <cooperative_groups.h>
 
@@ -549,6 +551,134 @@ __global__ void __launch_bounds__(1024) k_prim(const void* __restrict__ tri, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// Parallel MST (Boruvka rounds) under MSTPrim's edge order.
+//
+// MSTPrim relaxes and elects with the pair (distance, ~ids_to_uint64(min id, max id)) compared lexicographically
+// (MSTPrim.cpp:366-386, 492-503).  The key is unique per edge, so the pairs are a strict total order and the minimum
+// spanning tree under it is unique: any algorithm finds the edges Prim finds.  What Prim adds is the visiting order
+// from vertex 0, and that can be replayed on the n-1 tree edges alone (at every step Prim takes the smallest edge
+// leaving the visited set, which is a tree edge).  So: distances once into a float64 triangle, then log2(n) rounds in
+// which every vertex finds its smallest edge into another component -- two streaming passes over the triangle, rows
+// and columns, both coalesced -- while the host merges components (union-find over n entries) and finally replays
+// Prim's order with a heap.  Used when no sequence has orientation-dependent LCS values (the dropped-carry corner);
+// otherwise the sequential loop above runs.  famsa_b200/mst.py + tests/test_mst_host.py pin the argument on the CPU.
+// ------------------------------------------------------------------------------------------------
+struct EdgeMin {
+    double d;
+    unsigned long long k;
+};
+__device__ __forceinline__ bool edge_less(double d, unsigned long long k, double bd, unsigned long long bk) { return d < bd || (d == bd && k < bk); }
+__device__ __forceinline__ unsigned long long edge_key_dev(uint32_t a, uint32_t b)
+{
+    const unsigned long long lo = a < b ? a : b, hi = a < b ? b : a;
+    return ~((lo << 32) + hi);
+}
+constexpr double kEdgeNone = __builtin_huge_val();      // +inf: no candidate (distances are finite)
+
+// one block per row i: distances of (i, j), j < i  (Transform<double, Distance>, AbstractTreeGenerator.hpp:28-82)
+__global__ void __launch_bounds__(256) k_mst_dist(const void* __restrict__ tri, int eb, uint32_t n, const uint32_t* __restrict__ lens,
+                                                  const double* __restrict__ pow075, int kind, double never, double* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x + 1;
+    const size_t base = (size_t)i * (i - 1) / 2;
+    const uint32_t li = lens[i];
+    for (uint32_t j = threadIdx.x; j < i; j += blockDim.x) {
+        const uint32_t l = eb == 2 ? static_cast<const uint16_t*>(tri)[base + j] : static_cast<const uint32_t*>(tri)[base + j];
+        out[base + j] = transform_f64(kind, l, li, lens[j], pow075, never);
+    }
+}
+
+__device__ __forceinline__ void block_edge_min(double& d, unsigned long long& k)
+{
+    __shared__ double sd[32];
+    __shared__ unsigned long long sk[32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 16; o; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, d, o);
+        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, k, o);
+        if (edge_less(od, ok, d, k)) { d = od; k = ok; }
+    }
+    if (lane == 0) { sd[warp] = d; sk[warp] = k; }
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t nw = blockDim.x / 32;
+        d = lane < nw ? sd[lane] : kEdgeNone; k = lane < nw ? sk[lane] : 0;
+        for (int o = 16; o; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, d, o);
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, k, o);
+            if (edge_less(od, ok, d, k)) { d = od; k = ok; }
+        }
+    }
+}
+
+// row pass: vertex i against its lower neighbours j < i in other components
+__global__ void __launch_bounds__(256) k_mst_rows(const double* __restrict__ dtri, uint32_t n, const uint32_t* __restrict__ comp,
+                                                  EdgeMin* __restrict__ best)
+{
+    const uint32_t i = blockIdx.x;
+    const size_t base = (size_t)i * (i ? i - 1 : 0) / 2;
+    const uint32_t ci = comp[i];
+    double d = kEdgeNone;
+    unsigned long long k = 0;
+    for (uint32_t j = threadIdx.x; j < i; j += blockDim.x) {
+        if (comp[j] == ci) continue;
+        const double dj = dtri[base + j];
+        const unsigned long long kj = edge_key_dev(i, j);
+        if (edge_less(dj, kj, d, k)) { d = dj; k = kj; }
+    }
+    block_edge_min(d, k);
+    if (threadIdx.x == 0) { best[i].d = d; best[i].k = k; }
+}
+
+// column pass: vertex j against its upper neighbours i > j; block = 32 columns x a chunk of kMstChunk rows, every row
+// contributes a coalesced 256-byte segment.  part[chunk][j] receives the chunk's minimum.
+constexpr uint32_t kMstChunk = 1024;
+__global__ void __launch_bounds__(256) k_mst_cols(const double* __restrict__ dtri, uint32_t n, const uint32_t* __restrict__ comp,
+                                                  EdgeMin* __restrict__ part)
+{
+    __shared__ double sd[8][32];
+    __shared__ unsigned long long sk[8][32];
+    const uint32_t x = threadIdx.x & 31, y = threadIdx.x >> 5;
+    const uint32_t j = blockIdx.x * 32 + x;
+    const uint32_t r0 = blockIdx.y * kMstChunk, r1 = r0 + kMstChunk < n ? r0 + kMstChunk : n;
+    double d = kEdgeNone;
+    unsigned long long k = 0;
+    if (j < n) {
+        const uint32_t cj = comp[j];
+        uint32_t i = r0 + y;
+        if (i <= j) i += ((j + 1 - i) + 7) / 8 * 8;                 // first row of this thread's residue class above j
+        for (; i < r1; i += 8) {
+            if (comp[i] == cj) continue;
+            const double di = dtri[(size_t)i * (i - 1) / 2 + j];
+            const unsigned long long ki = edge_key_dev(i, j);
+            if (edge_less(di, ki, d, k)) { d = di; k = ki; }
+        }
+    }
+    sd[y][x] = d; sk[y][x] = k;
+    __syncthreads();
+    if (y == 0 && j < n) {
+        for (int q = 1; q < 8; ++q)
+            if (edge_less(sd[q][x], sk[q][x], d, k)) { d = sd[q][x]; k = sk[q][x]; }
+        part[(size_t)blockIdx.y * n + j].d = d;
+        part[(size_t)blockIdx.y * n + j].k = k;
+    }
+}
+
+// best[j] = min(best[j] (row pass), part[*][j])
+__global__ void __launch_bounds__(256) k_mst_combine(uint32_t n, uint32_t n_chunks, const EdgeMin* __restrict__ part, EdgeMin* __restrict__ best)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double d = best[j].d;
+    unsigned long long k = best[j].k;
+    for (uint32_t c = j / kMstChunk; c < n_chunks; ++c) {            // chunks that end at or below row j hold nothing for j
+        const EdgeMin e = part[(size_t)c * n + j];
+        if (edge_less(e.d, e.k, d, k)) { d = e.d; k = e.k; }
+    }
+    best[j].d = d; best[j].k = k;
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 
@@ -900,6 +1030,104 @@ int lcs_rows(famsa_ctx* ctx, const uint32_t* d_ref_ids, const uint32_t* h_ref_id
     return FAMSA_OK;
 }
 
+// Parallel MST + host replay of Prim's visiting order (see the kernels above).  Expects the true-LCS triangle in
+// d_prim_tri and the pow table in d_pow075_f64.
+static int prim_boruvka(famsa_ctx* ctx, int kind, int eb, int32_t* h_from, int32_t* h_to, double* h_dist, int32_t* h_order)
+{
+    LcsState& S = ctx->lcs;
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = S.n;
+    const size_t pairs = (size_t)n * (n - 1) / 2;
+    const uint32_t n_chunks = (n + kMstChunk - 1) / kMstChunk;
+    FB_TRY(S.d_prim_dtri.reserve(pairs * sizeof(double)));
+    FB_TRY(S.d_prim_comp.reserve(sizeof(uint32_t) * n));
+    FB_TRY(S.d_prim_best.reserve(sizeof(EdgeMin) * n));
+    FB_TRY(S.d_prim_part.reserve(sizeof(EdgeMin) * (size_t)n_chunks * n));
+    double* d_dtri = S.d_prim_dtri.as<double>();
+    uint32_t* d_comp = S.d_prim_comp.as<uint32_t>();
+    EdgeMin* d_best = S.d_prim_best.as<EdgeMin>();
+    EdgeMin* d_part = S.d_prim_part.as<EdgeMin>();
+    k_mst_dist<<<n - 1, 256, 0, st>>>(S.d_prim_tri.p, eb, n, S.d_raw_len.as<uint32_t>(), S.d_pow075_f64.as<double>(), kind,
+                                      nextafter(DBL_MAX, 0.0), d_dtri);
+    FB_CUDA(cudaGetLastError());
+    ctx->launches++;
+
+    std::vector<uint32_t> parent(n), comp(n);
+    std::iota(parent.begin(), parent.end(), 0u);
+    std::iota(comp.begin(), comp.end(), 0u);
+    auto find = [&](uint32_t x) {
+        while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+        return x;
+    };
+    struct HostEdge { uint32_t a, b; double d; };
+    std::vector<HostEdge> edges;
+    edges.reserve(n - 1);
+    std::vector<EdgeMin> best(n), cbest(n);
+    const double none = kEdgeNone;
+    uint32_t n_comp = n;
+    while (n_comp > 1) {
+        FB_CUDA(cudaMemcpyAsync(d_comp, comp.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+        k_mst_rows<<<n, 256, 0, st>>>(d_dtri, n, d_comp, d_best);
+        k_mst_cols<<<dim3((n + 31) / 32, n_chunks), 256, 0, st>>>(d_dtri, n, d_comp, d_part);
+        k_mst_combine<<<(n + 255) / 256, 256, 0, st>>>(n, n_chunks, d_part, d_best);
+        FB_CUDA(cudaGetLastError());
+        ctx->launches += 3;
+        FB_CUDA(cudaMemcpyAsync(best.data(), d_best, sizeof(EdgeMin) * n, cudaMemcpyDeviceToHost, st));
+        FB_CUDA(cudaStreamSynchronize(st));
+        // every component's smallest outgoing edge ...
+        for (uint32_t v = 0; v < n; ++v) cbest[v].d = none;
+        for (uint32_t v = 0; v < n; ++v) {
+            if (!(best[v].d < none)) continue;
+            EdgeMin& c = cbest[comp[v]];
+            if (best[v].d < c.d || (best[v].d == c.d && best[v].k < c.k)) c = best[v];
+        }
+        // ... joins two components (the edge order is strict, so no cycle can close)
+        const uint32_t before = n_comp;
+        for (uint32_t c = 0; c < n; ++c) {
+            if (!(cbest[c].d < none)) continue;
+            const unsigned long long packed = ~cbest[c].k;         // uint64_to_id (MSTPrim.h:441-450)
+            const uint32_t a = (uint32_t)(packed >> 32), b = (uint32_t)(packed & 0xffffffffull);
+            const uint32_t ra = find(a), rb = find(b);
+            if (ra == rb) continue;                                 // both sides elected the same edge
+            parent[ra] = rb;
+            edges.push_back(HostEdge{a, b, cbest[c].d});
+            --n_comp;
+        }
+        if (n_comp == before) { set_error("famsa_lcs_prim: no progress in a Boruvka round"); return FAMSA_E_CUDA; }
+        for (uint32_t v = 0; v < n; ++v) comp[v] = find(v);
+    }
+    FB_CUDA(cudaEventRecord(ctx->ev[3], st));
+    // Prim's visiting order from vertex 0, replayed on the tree (MSTPrim.cpp:366-386 restricted to tree edges)
+    std::vector<std::vector<std::tuple<double, unsigned long long, uint32_t>>> adj(n);
+    for (const HostEdge& e : edges) {
+        const unsigned long long lo = std::min(e.a, e.b), hi = std::max(e.a, e.b);
+        const unsigned long long key = ~((lo << 32) + hi);
+        adj[e.a].emplace_back(e.d, key, e.b);
+        adj[e.b].emplace_back(e.d, key, e.a);
+    }
+    using Item = std::tuple<double, unsigned long long, uint32_t>;
+    std::priority_queue<Item, std::vector<Item>, std::greater<Item>> heap;
+    for (uint32_t v = 0; v < n; ++v) h_order[v] = (int32_t)n;
+    h_order[0] = 0;
+    for (const Item& it : adj[0]) heap.push(it);
+    uint32_t step = 0;
+    while (!heap.empty()) {
+        const Item it = heap.top();
+        heap.pop();
+        const uint32_t v = std::get<2>(it);
+        if (h_order[v] != (int32_t)n) continue;
+        const unsigned long long packed = ~std::get<1>(it);
+        h_from[step] = (int32_t)(packed >> 32);
+        h_to[step] = (int32_t)(packed & 0xffffffffull);
+        h_dist[step] = std::get<0>(it);
+        h_order[v] = (int32_t)++step;
+        for (const Item& nx : adj[v])
+            if (h_order[std::get<2>(nx)] == (int32_t)n) heap.push(nx);
+    }
+    if (step != n - 1) { set_error("famsa_lcs_prim: the replay did not reach every sequence"); return FAMSA_E_CUDA; }
+    return FAMSA_OK;
+}
+
 int lcs_prim(famsa_ctx* ctx, int kind, int32_t* h_from, int32_t* h_to, double* h_dist, int32_t* h_order)
 {
     LcsState& S = ctx->lcs;
@@ -929,6 +1157,8 @@ int lcs_prim(famsa_ctx* ctx, int kind, int32_t* h_from, int32_t* h_to, double* h
         FB_CUDA(cudaMemcpyAsync(S.d_pow075_f64.p, pw.data(), sizeof(double) * pw.size(), cudaMemcpyHostToDevice, st));
         FB_CUDA(cudaStreamSynchronize(st));
     }
+    if (S.h_quirky.empty() && n >= 2 && !getenv("FAMSA_PRIM_SEQUENTIAL"))
+        return prim_boruvka(ctx, kind, eb, h_from, h_to, h_dist, h_order);
     FB_TRY(S.d_prim_state.reserve((sizeof(PrimState) + 1) * (size_t)n + 64));
     FB_TRY(S.d_prim_out.reserve((sizeof(int) * 3 + sizeof(double)) * (size_t)n + 64));
     PrimState* d_state = S.d_prim_state.as<PrimState>();

@@ -316,7 +316,12 @@ def test_gpu_prim_tree(engine, adeno, case):
     assert sorted(order.tolist()) == list(range(n))
 
 
-def test_gpu_prim_edges_match_restatement(engine):
+@pytest.mark.parametrize("sequential", [False, True])
+def test_gpu_prim_edges_match_restatement(engine, monkeypatch, sequential):
+    """Both device implementations -- Boruvka rounds + host replay of the visiting order (default when no sequence has
+    orientation-dependent LCS values) and the sequential vertex loop -- against the restated Prim, edge for edge."""
+    if sequential:
+        monkeypatch.setenv("FAMSA_PRIM_SEQUENTIAL", "1")
     codes, offsets, lens = seqio.synth_family(90, 70, seed=43)
     engine.upload(codes, offsets, lens)
     for kind in (0, 1):
