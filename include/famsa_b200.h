@@ -116,6 +116,10 @@ int famsa_lcs_assign(famsa_ctx* ctx, const uint32_t* seed_ids, uint32_t n_seeds,
  * Transform<double, distance>, the relaxation  s = {d, ~ids_to_uint64(v, j)};  if (d <= best[j].first && s < best[j])
  * best[j] = s  (MSTPrim.cpp:492-503), and the election of the unvisited vertex with the smallest pair
  * (:366-386); the reference's lower-bound pruning (:450-467) does not change results and is not needed.
+ * Because the pair is a strict total order on the edges, the tree is the unique MST under it: the library finds it with
+ * parallel Boruvka rounds over a float64 distance triangle and replays Prim's visiting order on the n-1 tree edges
+ * (the sequential loop itself runs when a sequence has orientation-dependent LCS values, the dropped-carry corner of
+ * lcsbp_classic.h:85-92, or when FAMSA_PRIM_SEQUENTIAL is set).
  * Runs on the LCS triangle kept in HBM, so no n^2 data leaves the device: the n-1 MST edges come back in Prim
  * order -- edge k joins edge_from[k] < edge_to[k] at distance edge_dist[k] (positive; the reference stores the
  * negated value) and was added with the (k+1)-th vertex -- plus prim_order[i], the visiting position of every
