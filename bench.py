@@ -505,6 +505,22 @@ def main():
     if rank == 0:
         line["dp"] = dp
         line["gpu_launches"] = int(launches) + (dp["gpu_launches"] if dp else 0)
+        if world == 1:
+            # informational: the default guide tree (-gt sl) end to end on the same set -- famsa_lcs_prim =
+            # LCS triangle + Transform + MST (Boruvka rounds under MSTPrim's edge order) + Prim-order replay
+            try:
+                eng.upload(codes, offsets, lens)
+                eng.prim(0)
+                t0 = time.time()
+                ef, _, ed, _ = eng.prim(0)
+                wall = time.time() - t0
+                tot, lcs_ms, _ = eng.last_timing()
+                line["guide_tree_sl"] = {"ms": 1e3 * wall, "device_ms": tot, "lcs_kernels_ms": lcs_ms, "n_seqs": int(n),
+                                         "edges": int(len(ef)), "sum_dist": float(ed.sum()),
+                                         "note": "MSTPrim<indel075_div_lcs> tree of the bench set through famsa_lcs_prim; "
+                                                 "the reference builds it in cpu_baseline's LCS time plus its Prim loop"}
+            except Exception as e:                     # never let the extra leg break the contract line
+                line["guide_tree_sl"] = {"error": str(e)}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

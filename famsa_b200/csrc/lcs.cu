@@ -1157,8 +1157,10 @@ int lcs_prim(famsa_ctx* ctx, int kind, int32_t* h_from, int32_t* h_to, double* h
         FB_CUDA(cudaMemcpyAsync(S.d_pow075_f64.p, pw.data(), sizeof(double) * pw.size(), cudaMemcpyHostToDevice, st));
         FB_CUDA(cudaStreamSynchronize(st));
     }
-    if (S.h_quirky.empty() && n >= 2 && !getenv("FAMSA_PRIM_SEQUENTIAL"))
-        return prim_boruvka(ctx, kind, eb, h_from, h_to, h_dist, h_order);
+    if (S.h_quirky.empty() && n >= 2 && !getenv("FAMSA_PRIM_SEQUENTIAL")) {
+        const int rc = prim_boruvka(ctx, kind, eb, h_from, h_to, h_dist, h_order);
+        if (rc != FAMSA_E_NOMEM) return rc;                         // no room for the float64 triangle: sequential loop
+    }
     FB_TRY(S.d_prim_state.reserve((sizeof(PrimState) + 1) * (size_t)n + 64));
     FB_TRY(S.d_prim_out.reserve((sizeof(int) * 3 + sizeof(double)) * (size_t)n + 64));
     PrimState* d_state = S.d_prim_state.as<PrimState>();
