@@ -73,7 +73,7 @@ struct ColInfo {
 };
 static_assert(sizeof(ColInfo) == 64, "ColInfo layout");
 
-struct RowNz {             // compact non-zero list of one counters column (rows 0..29), 160 bytes
+struct RowNz {             // per row of a Seq* merge: k[0] = its residue (the list form served an earlier sparse k_dp_t), 160 bytes
     int n;
     int c[30];
     unsigned char k[30];
