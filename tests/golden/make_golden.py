@@ -143,3 +143,46 @@ if __name__ == "__main__":
     main()
     make_dp()
     make_hemopexin()
+    make_sl_tree()
+
+
+def make_sl_tree():
+    """adeno_sl_tree.npz -- the reference's DEFAULT guide tree golden, test/adeno_fiber/sl.dnd.
+    Holds the set in FAMSA's own order (length-descending, msa.cpp:245-256), the MST edges in Prim order and the
+    visiting order (what famsa_lcs_prim returns) and the resulting tree_structure.  Generation asserts that
+      (1) the reference's own MSTPrim run on this set,
+      (2) the reference's mst_to_dendogram fed with the restated Prim's edges,
+      (3) the same fed with famsa_b200.mst (Kruskal under MSTPrim's edge order + visiting-order replay)
+    all give one tree, and that its clades are exactly those of sl.dnd.  Needs oracle/_ref."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from famsa_b200 import mst
+    from oracle import pyoracle
+    from treeutil import parse_newick
+    T = os.path.join(REF, "adeno_fiber")
+    ids, seqs = seqio.read_fasta(os.path.join(T, "adeno_fiber"))
+    code_list = [seqio.encode(s) for s in seqs]
+    order = sorted(range(len(seqs)), key=lambda i: (-len(code_list[i]), code_list[i].tobytes()))
+    names = [ids[i] for i in order]
+    codes, offsets, lens = seqio.pack([code_list[i] for i in order])
+    n = len(lens)
+    letters = [seqio.decode(codes[int(o):int(o) + int(l)]) for o, l in zip(offsets, lens)]
+    ref_tree = pyoracle.RefSeqSet(letters).mst_prim_tree(2)
+    # distances through the oracle, as MSTPrim's Transform<double, indel075_div_lcs> computes them
+    tri = pyoracle.lcs_triangle(codes, offsets, lens)
+    dist = np.array([pyoracle.transform(0, int(tri[i * (i - 1) // 2 + j]), int(lens[i]), int(lens[j]), True)
+                     for i in range(1, n) for j in range(i)])
+    ef, et, ed, po = mst.prim_replay(n, mst.kruskal_total_order(n, dist))
+    tree = pyoracle.mst_to_dendogram(ef, et, ed, po)
+    assert np.array_equal(tree, ref_tree), "edges do not rebuild the reference's MSTPrim tree"
+
+    def clades(n_leaves, merges, leaf_names):
+        sets = [frozenset([nm]) for nm in leaf_names]
+        for a, b in merges:
+            sets.append(sets[a] | sets[b])
+        return set(sets[n_leaves:])
+    gl, gm = parse_newick(open(os.path.join(T, "sl.dnd")).read())
+    mine = clades(n, [tuple(int(x) for x in r) for r in tree[n:]], names)
+    assert mine == clades(len(gl), gm, gl), "tree differs from the golden sl.dnd"
+    np.savez_compressed(os.path.join(HERE, "adeno_sl_tree.npz"), names=np.array(names), seqs=np.array(letters),
+                        edge_from=ef, edge_to=et, edge_dist=ed, prim_order=po, tree=tree)
+    print("adeno_sl_tree.npz:", n, "sequences, clades equal to sl.dnd")

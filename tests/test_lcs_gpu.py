@@ -1,8 +1,10 @@
 """GPU parity tests for HP-1 (all go through the C ABI).  Bit-exact: LCS lengths are integers."""
+import os
+
 import numpy as np
 import pytest
 
-from conftest import QUIRK_LCS, QUIRK_SEQS, random_set
+from conftest import GOLDEN, QUIRK_LCS, QUIRK_SEQS, random_set
 from famsa_b200 import seqio
 from oracle import pyoracle
 
@@ -329,3 +331,18 @@ def test_gpu_prim_edges_match_restatement(engine, monkeypatch, sequential):
         want = _prim_restated(codes, offsets, lens, kind)
         for g, w in zip(got, want):
             assert np.array_equal(g, w)
+
+
+@pytest.mark.parametrize("sequential", [False, True])
+def test_gpu_prim_golden_sl_tree(engine, monkeypatch, sequential):
+    """The reference's default guide tree golden (test/adeno_fiber/sl.dnd) without oracle/_ref: the fixture's MST edges
+    were checked at generation to rebuild, through the reference's mst_to_dendogram, the reference's tree and the
+    clades of sl.dnd; famsa_lcs_prim (both device implementations) must return exactly those edges."""
+    if sequential:
+        monkeypatch.setenv("FAMSA_PRIM_SEQUENTIAL", "1")
+    z = np.load(os.path.join(GOLDEN, "adeno_sl_tree.npz"))
+    codes, offsets, lens = seqio.pack([seqio.encode(str(s)) for s in z["seqs"]])
+    engine.upload(codes, offsets, lens)
+    ef, et, ed, order = engine.prim(0)
+    assert np.array_equal(ef, z["edge_from"]) and np.array_equal(et, z["edge_to"])
+    assert np.array_equal(ed, z["edge_dist"]) and np.array_equal(order, z["prim_order"])

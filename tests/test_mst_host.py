@@ -72,3 +72,19 @@ def test_replayed_mst_gives_the_reference_tree():
     letters = [seqio.decode(codes[int(o):int(o) + int(ln)]) for o, ln in zip(offsets, lens)]
     want = pyoracle.RefSeqSet(letters).mst_prim_tree(2)
     assert np.array_equal(pyoracle.mst_to_dendogram(ef, et, ed, order), want)
+
+
+def test_golden_sl_tree_edges_without_reference():
+    """tests/golden/adeno_sl_tree.npz was generated with the assertion that these edges, through the reference's
+    mst_to_dendogram, give the reference's MSTPrim tree and exactly the clades of the golden test/adeno_fiber/sl.dnd.
+    Here (no oracle/_ref needed) the oracle's distances + Kruskal under MSTPrim's edge order + the visiting-order
+    replay must reproduce them."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "adeno_sl_tree.npz"))
+    codes, offsets, lens = seqio.pack([seqio.encode(str(s)) for s in z["seqs"]])
+    n = len(lens)
+    tri = _distances(codes, offsets, lens, 0)
+    ef, et, ed, po = mst.prim_replay(n, mst.kruskal_total_order(n, tri))
+    assert np.array_equal(ef, z["edge_from"]) and np.array_equal(et, z["edge_to"])
+    assert np.array_equal(ed, z["edge_dist"]) and np.array_equal(po, z["prim_order"])
