@@ -115,3 +115,48 @@ def test_subtree_sharded_resident_alignment(tmp_path, world):
     results = {int(k): dict(path=z[f"p{k}"], swapped=bool(s), total=int(t)) for k, s, t in zip(z["keys"], z["sw"], z["tot"])}
     assert [results[k]["total"] for k in range(len(merges))] == [r["total"] for r in recs]
     assert assemble_rows(seqs, merges, results) == recs[-1]["rows"]
+
+
+@pytest.mark.parametrize("n,world,cat", [(2, 2, 0.0), (3, 4, 0.0), (40, 2, 0.9), (333, 4, 0.3), (1000, 8, 0.05), (64, 3, 1.0)])
+def test_subtree_shards_properties(n, world, cat):
+    """Every merge has exactly one executor; a subtree below a frontier node stays on that node's rank (so both children
+    of every sharded merge are local); top merges only combine frontier nodes or other top merges; loads are balanced."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from dp_cases import random_tree
+    from famsa_b200.schedule import ready_levels_subset, subtree_shards
+    merges = random_tree(n, np.random.default_rng(n + world), cat)
+    owner, frontier = subtree_shards(n, merges, world)
+    assert len(owner) == len(merges) and all(-1 <= o < world for o in owner)
+    fr = dict(frontier)
+    node_rank = {}
+    for k, (a, b) in enumerate(merges):
+        v = n + k
+        if owner[k] >= 0:
+            for c in (a, b):                     # children are leaves or merges of the same rank
+                assert c < n or owner[c - n] == owner[k]
+            node_rank[v] = owner[k]
+        else:
+            assert v not in fr
+            for c in (a, b):                     # a top merge consumes frontier nodes or other top merges
+                assert c in fr or (c >= n and owner[c - n] == -1)
+    assert all((v < n) or owner[v - n] == r for v, r in frontier)
+    # the frontier partitions the leaves
+    leaves_under = {}
+    for i in range(n):
+        leaves_under[i] = {i}
+    for k, (a, b) in enumerate(merges):
+        leaves_under[n + k] = leaves_under[a] | leaves_under[b]
+    covered = [leaf for v, _ in frontier for leaf in leaves_under[v]]
+    assert sorted(covered) == list(range(n))
+    loads = [sum(1 for o in owner if o == r) for r in range(world)]
+    if n >= 50 * world:
+        assert max(loads) <= 1.25 * sum(loads) / world + 4       # LPT over ~4 pieces per rank
+    # levels of a rank's subset respect dependencies
+    for r in range(world):
+        done = set()
+        for lvl in ready_levels_subset(n, merges, [k for k in range(len(merges)) if owner[k] == r]):
+            for k in lvl:
+                for c in merges[k]:
+                    assert c < n or (c - n) in done
+            done.update(lvl)
