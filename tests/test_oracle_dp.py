@@ -74,12 +74,15 @@ def test_oracle_hemopexin_first_levels():
             keep.append(k)
     remap = {k: i for i, k in enumerate(keep)}
     sub = [tuple(x if x < n else n + remap[x - n] for x in merges[k]) for k in keep]
-    g, recs = reference_merges(seqs, sub, n_seqs_for_rescale=n, threads=(1,))
+    g, recs = reference_merges(seqs, sub, n_seqs_for_rescale=n, threads=(1,), want_merged=True)
     assert np.array_equal(g, z["gaps"])
+    res = []
     for k, r in zip(keep, recs):
         o = pyoracle.dp_align(*r["job"], g)
         assert o["total"] == int(z["totals"][k])
         assert zlib.crc32(o["path"].tobytes()) == int(z["path_crc"][k])
+        res.append(o)
+    _check_construct(res, recs, g)               # and the merged tables ConstructProfile builds from those paths
 
 
 @needs_ref
