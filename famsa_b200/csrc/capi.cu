@@ -10,6 +10,19 @@ namespace fb {
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 const char* get_error() { return g_error.c_str(); }
+
+int scratch_acquire(famsa_ctx* ctx, cudaStream_t st)
+{
+    if (ctx->busy) FB_CUDA(cudaStreamWaitEvent(st, ctx->ev_busy, 0));
+    return FAMSA_OK;
+}
+int scratch_release(famsa_ctx* ctx, cudaStream_t st, bool synced)
+{
+    if (synced) { ctx->busy = false; return FAMSA_OK; }
+    FB_CUDA(cudaEventRecord(ctx->ev_busy, st));
+    ctx->busy = true;
+    return FAMSA_OK;
+}
 } // namespace fb
 
 using fb::set_error;
@@ -51,8 +64,13 @@ int famsa_create(int device, famsa_ctx** out_ctx)
     if (!ctx) { set_error("out of host memory"); return FAMSA_E_NOMEM; }
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    FB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    for (auto& ev : ctx->ev) FB_CUDA(cudaEventCreate(&ev));
+    const int rc = [&]() -> int {
+        FB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        for (auto& ev : ctx->ev) FB_CUDA(cudaEventCreate(&ev));
+        FB_CUDA(cudaEventCreateWithFlags(&ctx->ev_busy, cudaEventDisableTiming));
+        return FAMSA_OK;
+    }();
+    if (rc) { famsa_destroy(ctx); return rc; }
     *out_ctx = ctx;
     return FAMSA_OK;
 }
@@ -80,6 +98,7 @@ void famsa_destroy(famsa_ctx* ctx)
         if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->ev_host)
         if (ev) cudaEventDestroy(ev);
+    if (ctx->ev_busy) cudaEventDestroy(ctx->ev_busy);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -96,6 +115,10 @@ int famsa_lcs_upload(famsa_ctx* ctx, const int8_t* codes, const uint64_t* offset
     if (n_seqs && (!codes || !offsets || !lens)) { set_error("NULL sequence arrays"); return FAMSA_E_INVALID; }
     std::lock_guard<std::mutex> lk(ctx->mu);
     FB_CUDA(cudaSetDevice(ctx->device));
+    int rc = fb::scratch_acquire(ctx, ctx->stream);                 // earlier *_device calls may still read the old set
+    if (rc) return rc;
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    fb::scratch_release(ctx, ctx->stream, true);
     return fb::lcs_upload(ctx, codes, offsets, lens, n_seqs);
 }
 
@@ -132,10 +155,11 @@ static int triangle_locked(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end,
     if (!d_out && row_end > row_begin && row_end > 1) { set_error("d_out is NULL"); return FAMSA_E_INVALID; }
     FB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    if ((rc = fb::scratch_acquire(ctx, st))) return rc;
     rc = fb::lcs_triangle(ctx, row_begin, row_end, d_out, elem_bytes, st);
     if (rc) return rc;
-    if (!stream) { FB_CUDA(cudaStreamSynchronize(st)); return finish_timing(ctx); }
-    return FAMSA_OK;
+    if (!stream) { FB_CUDA(cudaStreamSynchronize(st)); fb::scratch_release(ctx, st, true); return finish_timing(ctx); }
+    return fb::scratch_release(ctx, st, false);
 }
 
 int famsa_lcs_triangle_device(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_out, int elem_bytes,
@@ -183,6 +207,7 @@ int famsa_lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, voi
     if (ctx->lcs.n == 0 && row_end > 0) { set_error("famsa_lcs_upload has not been called"); return FAMSA_E_STATE; }
     rc = check_elem(ctx, elem_bytes);
     if (rc) return rc;
+    if ((rc = fb::scratch_acquire(ctx, ctx->stream))) return rc;
     FB_CUDA(cudaEventRecord(ctx->ev_host[0], ctx->stream));
     float main_ms = 0.f;
     rc = fb::lcs_triangle(ctx, row_begin, row_end, d_out, elem_bytes, ctx->stream, bounds, n_blocks, ctx->ev_block);
@@ -198,6 +223,7 @@ int famsa_lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, voi
     }
     FB_CUDA(cudaStreamSynchronize(ctx->stream));
     FB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    fb::scratch_release(ctx, ctx->stream, true);
     FB_CUDA(cudaEventElapsedTime(&main_ms, ctx->ev_host[0], ctx->ev_host[1]));
     ctx->lcs.last_total_ms = main_ms;
     ctx->lcs.last_main_ms = main_ms;
@@ -211,10 +237,12 @@ static int rows_common(famsa_ctx* ctx, const uint32_t* d_ref_ids, const uint32_t
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     for (uint32_t r = 0; r < n_ref; ++r)
         if (h_ref_ids[r] >= ctx->lcs.n) { set_error("ref id out of range"); return FAMSA_E_INVALID; }
-    int rc = fb::lcs_rows(ctx, d_ref_ids, h_ref_ids, n_ref, d_col_ids, n_col, d_out, elem_bytes, st);
+    int rc = fb::scratch_acquire(ctx, st);
     if (rc) return rc;
-    if (!stream) { FB_CUDA(cudaStreamSynchronize(st)); return finish_timing(ctx); }
-    return FAMSA_OK;
+    rc = fb::lcs_rows(ctx, d_ref_ids, h_ref_ids, n_ref, d_col_ids, n_col, d_out, elem_bytes, st);
+    if (rc) return rc;
+    if (!stream) { FB_CUDA(cudaStreamSynchronize(st)); fb::scratch_release(ctx, st, true); return finish_timing(ctx); }
+    return fb::scratch_release(ctx, st, false);
 }
 
 int famsa_lcs_rows_device(famsa_ctx* ctx, const uint32_t* d_ref_ids, uint32_t n_ref, const uint32_t* d_col_ids,
@@ -229,7 +257,11 @@ int famsa_lcs_rows_device(famsa_ctx* ctx, const uint32_t* d_ref_ids, uint32_t n_
     if (n_ref && !d_ref_ids) { set_error("d_ref_ids is NULL"); return FAMSA_E_INVALID; }
     FB_CUDA(cudaSetDevice(ctx->device));
     std::vector<uint32_t> h_ref(n_ref);
-    if (n_ref) FB_CUDA(cudaMemcpy(h_ref.data(), d_ref_ids, sizeof(uint32_t) * n_ref, cudaMemcpyDeviceToHost));
+    if (n_ref) {      // ordered on the caller's stream (a blocking copy on the legacy stream would not be)
+        cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+        FB_CUDA(cudaMemcpyAsync(h_ref.data(), d_ref_ids, sizeof(uint32_t) * n_ref, cudaMemcpyDeviceToHost, st));
+        FB_CUDA(cudaStreamSynchronize(st));
+    }
     return rows_common(ctx, d_ref_ids, h_ref.data(), n_ref, d_col_ids, n_col, d_out, elem_bytes, stream);
 }
 
@@ -277,8 +309,12 @@ int famsa_lcs_prim(famsa_ctx* ctx, int distance_kind, int32_t* edge_from, int32_
     if (!prim_order || (ctx->lcs.n > 1 && (!edge_from || !edge_to || !edge_dist))) { set_error("NULL argument"); return FAMSA_E_INVALID; }
     if (distance_kind != 0 && distance_kind != 1) { set_error("MSTPrim is instantiated for distance_kind 0 and 1 only"); return FAMSA_E_INVALID; }
     FB_CUDA(cudaSetDevice(ctx->device));
-    int rc = fb::lcs_prim(ctx, distance_kind, edge_from, edge_to, edge_dist, prim_order);
+    int rc = fb::scratch_acquire(ctx, ctx->stream);
     if (rc) return rc;
+    rc = fb::lcs_prim(ctx, distance_kind, edge_from, edge_to, edge_dist, prim_order);
+    if (rc) return rc;
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    fb::scratch_release(ctx, ctx->stream, true);
     return finish_timing(ctx);
 }
 
@@ -293,8 +329,12 @@ int famsa_lcs_assign(famsa_ctx* ctx, const uint32_t* seed_ids, uint32_t n_seeds,
     for (uint32_t k = 0; k < n_seeds; ++k)
         if (seed_ids[k] >= ctx->lcs.n) { set_error("seed id out of range"); return FAMSA_E_INVALID; }
     FB_CUDA(cudaSetDevice(ctx->device));
-    int rc = fb::lcs_assign(ctx, seed_ids, n_seeds, distance_kind, assignments, min_dist);
+    int rc = fb::scratch_acquire(ctx, ctx->stream);
     if (rc) return rc;
+    rc = fb::lcs_assign(ctx, seed_ids, n_seeds, distance_kind, assignments, min_dist);
+    if (rc) return rc;
+    FB_CUDA(cudaStreamSynchronize(ctx->stream));
+    fb::scratch_release(ctx, ctx->stream, true);
     return finish_timing(ctx);
 }
 
@@ -327,8 +367,11 @@ int famsa_dp_align_batch(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n_jo
     if (n_jobs && (!jobs || !gaps || !results || !path_buf)) { set_error("NULL argument"); return FAMSA_E_INVALID; }
     std::lock_guard<std::mutex> lk(ctx->mu);
     FB_CUDA(cudaSetDevice(ctx->device));
-    int rc = fb::dp_run_host(ctx, jobs, n_jobs, gaps, results, path_buf, dirs_buf);
+    int rc = fb::scratch_acquire(ctx, ctx->stream);
     if (rc) return rc;
+    rc = fb::dp_run_host(ctx, jobs, n_jobs, gaps, results, path_buf, dirs_buf);
+    if (rc) return rc;
+    fb::scratch_release(ctx, ctx->stream, true);
     return dp_finish_timing(ctx);
 }
 
@@ -340,10 +383,12 @@ int famsa_dp_align_batch_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32
     std::lock_guard<std::mutex> lk(ctx->mu);
     FB_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
-    int rc = fb::dp_run_device(ctx, jobs, n_jobs, gaps, d_results, d_path_buf, d_dirs_buf, st);
+    int rc = fb::scratch_acquire(ctx, st);
     if (rc) return rc;
-    if (!stream) { FB_CUDA(cudaStreamSynchronize(st)); return dp_finish_timing(ctx); }
-    return FAMSA_OK;
+    rc = fb::dp_run_device(ctx, jobs, n_jobs, gaps, d_results, d_path_buf, d_dirs_buf, st);
+    if (rc) return rc;
+    if (!stream) { FB_CUDA(cudaStreamSynchronize(st)); fb::scratch_release(ctx, st, true); return dp_finish_timing(ctx); }
+    return fb::scratch_release(ctx, st, false);
 }
 
 int famsa_dp_last_timing(const famsa_ctx* ctx, float* total_ms, float* kernel_ms, uint64_t* n_cells)
@@ -382,7 +427,9 @@ int famsa_prof_merge_batch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint3
     if (n && (!merges || !gaps || !merged_ids_out || !results || !path_buf)) { set_error("NULL argument"); return FAMSA_E_INVALID; }
     std::lock_guard<std::mutex> lk(ctx->mu);
     FB_CUDA(cudaSetDevice(ctx->device));
-    int rc = fb::prof_merge_batch(ctx, merges, n, gaps, merged_ids_out, results, path_buf, path_cap);
+    int rc = fb::scratch_acquire(ctx, ctx->stream);
+    if (rc) return rc;
+    rc = fb::prof_merge_batch(ctx, merges, n, gaps, merged_ids_out, results, path_buf, path_cap);
     if (rc || !n) return rc;
     return dp_finish_timing(ctx);
 }

@@ -103,6 +103,11 @@ struct famsa_ctx {
     cudaStream_t copy_stream = nullptr;                 // D2H of finished row blocks (famsa_lcs_triangle)
     cudaEvent_t ev_block[8] = {};
     cudaEvent_t ev_host[2] = {};
+    // The context-owned scratch (tile lists, DP scratch, ...) is shared by every call.  A *_device call on a caller
+    // stream returns while its kernels are still queued, so it leaves `ev_busy` recorded behind them and the next call
+    // (on whatever stream) waits for it before it touches the scratch again.
+    cudaEvent_t ev_busy = nullptr;
+    bool busy = false;
     std::mutex mu;
     uint64_t launches = 0;
     int sm_count = 0;
@@ -112,6 +117,9 @@ struct famsa_ctx {
 };
 
 namespace fb {
+// capi.cu: ordering of calls that share the context's scratch
+int scratch_acquire(famsa_ctx* ctx, cudaStream_t st);   // call before queueing work that uses the scratch on `st`
+int scratch_release(famsa_ctx* ctx, cudaStream_t st, bool synced);   // call after queueing (synced: the stream was synchronised)
 // lcs.cu
 int lcs_upload(famsa_ctx* ctx, const int8_t* codes, const uint64_t* offsets, const uint32_t* lens,
                uint32_t n);

@@ -22,6 +22,7 @@
 //     those rows -- and rows too long for the register-resident kernel -- are recomputed by
 //     k_lcs_exact, which follows the reference recurrence word for word.
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -712,11 +713,11 @@ void DevBuf::release()
 template <int NL>
 static int launch_tile(famsa_ctx* ctx, const TileParams& P, uint32_t n_tiles, cudaStream_t st)
 {
-    static bool configured[16] = {};
+    static std::atomic<bool> configured[64];       // per device ordinal; setting the attribute twice is harmless
     const size_t smem = (size_t)blob_words(NL) * 4;
-    if (!configured[ctx->device & 15]) {
+    if (!configured[ctx->device & 63].load(std::memory_order_acquire)) {
         FB_CUDA(cudaFuncSetAttribute(k_lcs_tile<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[ctx->device & 15] = true;
+        configured[ctx->device & 63].store(true, std::memory_order_release);
     }
     k_lcs_tile<NL><<<n_tiles, kTileWarps * 32, smem, st>>>(P);
     FB_CUDA(cudaGetLastError());
@@ -740,7 +741,22 @@ static int launch_tile_nl(famsa_ctx* ctx, uint32_t nl, const TileParams& P, uint
     }
 }
 
+static int lcs_upload_impl(famsa_ctx* ctx, const int8_t* codes, const uint64_t* offsets, const uint32_t* lens, uint32_t n);
+
+// A failed upload leaves the context without a sequence set (n = 0) rather than with a half-replaced one.
 int lcs_upload(famsa_ctx* ctx, const int8_t* codes, const uint64_t* offsets, const uint32_t* lens, uint32_t n)
+{
+    const int rc = lcs_upload_impl(ctx, codes, offsets, lens, n);
+    if (rc != FAMSA_OK) {
+        LcsState& S = ctx->lcs;
+        S.n = S.n_groups = 0;
+        S.max_len = 0;
+        S.groups.clear(); S.h_quirky.clear(); S.h_long.clear();
+    }
+    return rc;
+}
+
+static int lcs_upload_impl(famsa_ctx* ctx, const int8_t* codes, const uint64_t* offsets, const uint32_t* lens, uint32_t n)
 {
     LcsState& S = ctx->lcs;
     cudaStream_t st = ctx->stream;

@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(256) k_prof_leaf(const LeafDesc* __restrict__ 
         long long sc = gapv;
         int cn = 0;
         if (c) {
-            const int sym = s[c - 1];
+            int sym = s[c - 1];
+            if (sym < 0 || sym >= kNAA) sym = 22;                      // anything outside the alphabet counts as UNKNOWN
             cn = lane == sym;
             if (lane < kNAA) sc = sm[sym * kNAA + lane];
         }
