@@ -14,7 +14,7 @@ EXPORTED_SYMBOLS = [
     "famsa_lcs_rows", "famsa_lcs_rows_device", "famsa_lcs_assign", "famsa_lcs_prim", "famsa_transform_f64", "famsa_transform_f32",
     "famsa_lcs_last_timing", "famsa_dp_align_batch", "famsa_dp_align_batch_device", "famsa_dp_last_timing",
     "famsa_prof_set_scoring", "famsa_prof_put", "famsa_prof_merge_batch", "famsa_prof_get", "famsa_prof_drop",
-    "famsa_prof_last_timing", "famsa_prof_stats",
+    "famsa_prof_last_timing", "famsa_prof_stats", "famsa_prof_align_tree", "famsa_prof_tree_paths",
 ]
 
 PROF_LEAF = 0x80000000            # FAMSA_PROF_LEAF
@@ -36,6 +36,12 @@ class DpResult(C.Structure):
 
 class ProfMerge(C.Structure):
     _fields_ = [("child1", C.c_uint32), ("child2", C.c_uint32)]
+
+
+class TreeStats(C.Structure):
+    _fields_ = [("wall_ms", C.c_double), ("device_ms", C.c_double), ("cells", C.c_uint64), ("n_batches", C.c_uint32),
+                ("n_drains", C.c_uint32), ("max_in_flight", C.c_uint32), ("pad", C.c_uint32),
+                ("peak_resident_bytes", C.c_uint64)]
 
 
 class FamsaError(RuntimeError):
@@ -88,6 +94,8 @@ def load_library() -> C.CDLL:
     lib.famsa_prof_drop.argtypes = [vp, vp, u32]
     lib.famsa_prof_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.famsa_prof_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    lib.famsa_prof_align_tree.argtypes = [vp, vp, u32, vp, vp, C.POINTER(u32), C.POINTER(u64), vp]
+    lib.famsa_prof_tree_paths.argtypes = [vp, vp, u64]
     lib.famsa_dp_align_batch.argtypes = [vp, vp, u32, vp, vp, vp, vp]
     lib.famsa_dp_align_batch_device.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp]
     lib.famsa_dp_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(u64)]
@@ -290,6 +298,30 @@ class Engine:
             out.append(dict(path=path[r.path_offset:r.path_offset + r.path_len].copy(), total=int(r.total_score),
                             last=np.array(list(r.last), dtype=np.int64), swapped=bool(r.swapped), variant=int(r.variant)))
         return [int(x) for x in ids[:n]], out
+
+    def align_tree(self, merges, gaps, want_paths: bool = True):
+        """famsa_prof_align_tree: the whole progressive alignment of the uploaded sequences along a guide tree in one
+        call.  merges: (n-1, 2) child node ids (leaves 0..n-1, internal node n+k = merges[k]).  Returns
+        (root id, [dict(path, total, last, swapped, variant, rows_width, cols_width) per merge], stats dict)."""
+        t = np.ascontiguousarray(merges, dtype=np.int32).reshape(-1, 2)
+        n = len(t)
+        g = np.ascontiguousarray(gaps, dtype=np.int64)
+        res = (DpResult * max(n, 1))()
+        root, nbytes = C.c_uint32(), C.c_uint64()
+        st = TreeStats()
+        self._check(self.lib.famsa_prof_align_tree(self.h, _ptr(t), n + 1, _ptr(g), C.byref(res), C.byref(root), C.byref(nbytes),
+                                                   C.byref(st)))
+        stats = {f: getattr(st, f) for f, _ in TreeStats._fields_ if f != "pad"}
+        out = []
+        if want_paths:
+            path = np.zeros(max(nbytes.value, 1), dtype=np.uint8)
+            self._check(self.lib.famsa_prof_tree_paths(self.h, _ptr(path), path.size))
+            for k in range(n):
+                r = res[k]
+                out.append(dict(path=path[r.path_offset:r.path_offset + r.path_len].copy(), total=int(r.total_score),
+                                last=np.array(list(r.last), dtype=np.int64), swapped=bool(r.swapped), variant=int(r.variant),
+                                rows_width=int(r.rows_width), cols_width=int(r.cols_width)))
+        return root.value, out, stats
 
     def prof_get(self, pid: int, tables: bool = True):
         """(scores, counters, card) of a resident profile, or (width, card) with tables=False."""

@@ -68,6 +68,11 @@ int famsa_create(int device, famsa_ctx** out_ctx)
         FB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         for (auto& ev : ctx->ev) FB_CUDA(cudaEventCreate(&ev));
         FB_CUDA(cudaEventCreateWithFlags(&ctx->ev_busy, cudaEventDisableTiming));
+        // per-call scratch and resident profiles are stream-ordered allocations: the pool keeps what it has
+        cudaMemPool_t pool;
+        FB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        FB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         return FAMSA_OK;
     }();
     if (rc) { famsa_destroy(ctx); return rc; }
@@ -90,7 +95,7 @@ void famsa_destroy(famsa_ctx* ctx)
     fb::prof_release_all(ctx);
     fb::DpState& D = ctx->dp;
     if (D.h_pinned) cudaFreeHost(D.h_pinned);
-    for (fb::DevBuf* b : {&D.d_jobs, &D.d_order, &D.d_scratch, &D.d_dirs, &D.d_dirs_out, &D.d_tables, &D.d_results, &D.d_path, &D.d_meta, &D.d_tblock, &D.d_T})
+    for (fb::DevBuf* b : {&D.d_dirs_out, &D.d_tables, &D.d_results, &D.d_path})
         b->release();
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
@@ -385,7 +390,7 @@ int famsa_dp_align_batch_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32
     cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
     int rc = fb::scratch_acquire(ctx, st);
     if (rc) return rc;
-    rc = fb::dp_run_device(ctx, jobs, n_jobs, gaps, d_results, d_path_buf, d_dirs_buf, st);
+    rc = fb::dp_run_device(ctx, jobs, nullptr, n_jobs, gaps, d_results, d_path_buf, d_dirs_buf, nullptr, nullptr, st);
     if (rc) return rc;
     if (!stream) { FB_CUDA(cudaStreamSynchronize(st)); fb::scratch_release(ctx, st, true); return dp_finish_timing(ctx); }
     return fb::scratch_release(ctx, st, false);
@@ -432,6 +437,29 @@ int famsa_prof_merge_batch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint3
     rc = fb::prof_merge_batch(ctx, merges, n, gaps, merged_ids_out, results, path_buf, path_cap);
     if (rc || !n) return rc;
     return dp_finish_timing(ctx);
+}
+
+int famsa_prof_align_tree(famsa_ctx* ctx, const int32_t* tree, uint32_t n_leaves, const int64_t gaps[4],
+                          famsa_dp_result* results, uint32_t* root_id_out, uint64_t* path_bytes_out, famsa_tree_stats* stats)
+{
+    FB_CHECK_CTX(ctx);
+    if (!tree || !gaps || !results) { set_error("NULL argument"); return FAMSA_E_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    FB_CUDA(cudaSetDevice(ctx->device));
+    int rc = fb::scratch_acquire(ctx, ctx->stream);
+    if (rc) return rc;
+    rc = fb::prof_align_tree(ctx, tree, n_leaves, gaps, results, root_id_out, path_bytes_out, stats);
+    if (rc) return rc;
+    fb::scratch_release(ctx, ctx->stream, true);
+    return FAMSA_OK;
+}
+
+int famsa_prof_tree_paths(famsa_ctx* ctx, uint8_t* path_buf, uint64_t path_cap)
+{
+    FB_CHECK_CTX(ctx);
+    if (!path_buf) { set_error("NULL argument"); return FAMSA_E_INVALID; }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    return fb::prof_tree_paths(ctx, path_buf, path_cap);
 }
 
 int famsa_prof_get(famsa_ctx* ctx, uint32_t id, uint32_t* width, uint32_t* card, int64_t* scores, int32_t* counters)

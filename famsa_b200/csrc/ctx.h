@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/famsa_b200.h"
+#include "dp_dev.h"
 
 namespace fb {
 
@@ -62,7 +63,7 @@ struct LcsState {
 };
 
 struct DpState {
-    DevBuf d_jobs, d_order, d_scratch, d_dirs, d_dirs_out, d_tables, d_results, d_path, d_meta, d_tblock, d_T;
+    DevBuf d_dirs_out, d_tables, d_results, d_path;     // host entry point only; per-call scratch is stream-ordered
     void* h_pinned = nullptr;          // pinned staging buffer of the host entry point
     size_t h_pinned_cap = 0;
     uint64_t last_cells = 0;
@@ -73,9 +74,21 @@ struct DpState {
 struct ProfEntry {
     long long* scores = nullptr;   // (width+1) x 32 int64
     int* counters = nullptr;       // (width+1) x 32 int32
-    uint32_t width = 0, card = 0;
+    uint32_t width = 0, card = 0;  // pending: width is the upper bound the tables were sized for
     int slab = -1;
     bool live = false;
+    bool pending = false;          // produced by a batch the host has not collected yet: the real width lives in d_widths[id]
+    uint32_t gen = 0;              // bumped whenever the id is handed out again
+};
+// One queued batch of merges (prof_launch ... prof_collect)
+struct ProfTicket {
+    cudaEvent_t done = nullptr;
+    uint32_t n = 0;
+    std::vector<uint32_t> merged_ids, merged_gen;
+    famsa_dp_result* h_results = nullptr;   // filled by the batch's D2H copy
+    uint8_t* h_paths = nullptr;
+    uint64_t path_bytes = 0;
+    uint64_t cells_bound = 0;
 };
 struct ProfSlab {
     void* p = nullptr;
@@ -88,8 +101,13 @@ struct ProfState {
     std::vector<ProfSlab> slabs;
     std::vector<int> free_slabs;
     bool has_scoring = false, pool_ready = false;
-    DevBuf d_sm, d_leaf, d_leafdesc, d_results, d_path, d_cjobs;
+    DevBuf d_sm, d_widths;         // d_widths[id]: width of a pending profile, written by the fill kernel
+    std::vector<cudaEvent_t> free_events;
+    // result of the most recent famsa_prof_align_tree (pinned): per-merge records and all paths
+    famsa_dp_result* h_tree_results = nullptr; size_t h_tree_results_cap = 0;
+    uint8_t* h_tree_paths = nullptr; size_t h_tree_paths_cap = 0; uint64_t tree_path_bytes = 0; uint32_t tree_merges = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_tree[2] = {nullptr, nullptr};
     uint64_t resident_bytes = 0, n_live = 0;
     bool timing_valid = false;
 };
@@ -136,8 +154,10 @@ int lcs_assign(famsa_ctx* ctx, const uint32_t* h_seed_ids, uint32_t n_seeds, int
 int dp_run_host(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int64_t gaps[4], famsa_dp_result* results,
                 uint8_t* path_buf, uint8_t* dirs_buf);
 int dp_check_results(const famsa_dp_result* results, uint32_t n);
-int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int64_t gaps[4],
-                  famsa_dp_result* d_results, uint8_t* d_path, uint8_t* d_dirs, cudaStream_t st);
+// d_meta_out / d_blob_out non-NULL: the per-job DpMeta records stay valid until the caller cudaFreeAsync()s *d_blob_out
+int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext, uint32_t n, const int64_t gaps[4],
+                  famsa_dp_result* d_results, uint8_t* d_path, uint8_t* d_dirs, DpMeta** d_meta_out, void** d_blob_out,
+                  cudaStream_t st);
 // prof.cu
 int prof_set_scoring(famsa_ctx* ctx, const int64_t* sm);
 int prof_put(famsa_ctx* ctx, const famsa_dp_profile* profs, uint32_t n, uint32_t* ids);
@@ -146,5 +166,8 @@ int prof_merge_batch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t n,
 int prof_get(famsa_ctx* ctx, uint32_t id, uint32_t* width, uint32_t* card, int64_t* scores, int32_t* counters);
 int prof_drop(famsa_ctx* ctx, const uint32_t* ids, uint32_t n);
 int prof_last_timing(famsa_ctx* ctx, float* total_ms, float* construct_ms);
+int prof_align_tree(famsa_ctx* ctx, const int32_t* tree, uint32_t n_leaves, const int64_t gaps[4], famsa_dp_result* results,
+                    uint32_t* root_id, uint64_t* path_bytes, famsa_tree_stats* stats);
+int prof_tree_paths(famsa_ctx* ctx, uint8_t* path_buf, uint64_t cap);
 void prof_release_all(famsa_ctx* ctx);
 } // namespace fb

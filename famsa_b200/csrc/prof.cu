@@ -24,6 +24,9 @@
 #include <cstring>
 #include <numeric>
 
+#include <chrono>
+#include <deque>
+
 #include "ctx.h"
 
 namespace fb {
@@ -74,12 +77,13 @@ __global__ void __launch_bounds__(256) k_prof_leaf(const LeafDesc* __restrict__ 
     }
 }
 
-struct ConJob {
-    const long long* sr; const int* cr;    // row child (ConstructProfile's profile1)
-    const long long* sc; const int* cc;    // column child (profile2)
-    long long* os; int* oc;                // merged profile
-    const uint8_t* path;
-    uint32_t wr, wc, cardr, cardc, W, tile0;
+// One merge of a batch for k_prof_construct.  Everything that depends on the outcome of the DP -- which child is the row
+// profile, the real widths, the merged width -- is read on the device from the DP's own records, so the kernel can be
+// queued right behind the fill without the host looking at the results first.
+struct ConJobDev {
+    long long* os; int* oc;                // merged profile, sized for the upper bound w1 + w2
+    uint32_t job;                          // index into meta / results
+    uint32_t tile0;                        // first block of this merge (tiles counted with the upper bound)
 };
 
 struct GapSplit { int o, e, to, te; };
@@ -103,7 +107,18 @@ __device__ __forceinline__ GapSplit gap_split(int col, int nxt, uint32_t src, ui
     return g;
 }
 
-__global__ void __launch_bounds__(kConThreads) k_prof_construct(const ConJob* __restrict__ jobs, uint32_t n_jobs,
+struct ConJob {                            // resolved on the device at the top of k_prof_construct
+    const long long* sr; const int* cr;    // row child (ConstructProfile's profile1)
+    const long long* sc; const int* cc;    // column child (profile2)
+    long long* os; int* oc;                // merged profile
+    const uint8_t* path;
+    uint32_t wr, wc, cardr, cardc, W, tile0;
+};
+
+__global__ void __launch_bounds__(kConThreads) k_prof_construct(const ConJobDev* __restrict__ jobs, uint32_t n_jobs,
+                                                                const DpMeta* __restrict__ meta,
+                                                                const famsa_dp_result* __restrict__ results,
+                                                                const uint8_t* __restrict__ path_base,
                                                                 long long go, long long ge, long long to, long long te)
 {
     // block -> (job, tile of kConTile merged columns)
@@ -112,8 +127,18 @@ __global__ void __launch_bounds__(kConThreads) k_prof_construct(const ConJob* __
         const uint32_t mid = (lo + hi) >> 1;
         if (jobs[mid].tile0 <= blockIdx.x) lo = mid; else hi = mid;
     }
-    const ConJob J = jobs[lo];
+    ConJob J;
+    {
+        const ConJobDev D = jobs[lo];
+        const DpMeta M = meta[D.job];
+        const famsa_dp_result r = results[D.job];
+        if (M.bad || r.variant == 0xFF) return;
+        J.sr = M.SR; J.cr = M.CR; J.sc = M.SC; J.cc = M.CC; J.os = D.os; J.oc = D.oc;
+        J.path = path_base + r.path_offset;
+        J.wr = M.WR; J.wc = M.WC; J.cardr = (uint32_t)M.nR; J.cardc = (uint32_t)M.nC; J.W = r.path_len; J.tile0 = D.tile0;
+    }
     const uint32_t k0 = (blockIdx.x - J.tile0) * kConTile;          // first merged column of the tile (0 = column 0)
+    if (k0 > J.W) return;                                           // the tiles were counted with the upper bound
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     __shared__ uint32_t s_cnt[2][kConThreads / 32];
@@ -204,6 +229,7 @@ int ensure_pool(famsa_ctx* ctx)
     unsigned long long keep = ~0ull;                                // slabs are recycled by the pool, never trimmed
     FB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     for (auto& e : P.ev) FB_CUDA(cudaEventCreate(&e));
+    for (auto& e : P.ev_tree) FB_CUDA(cudaEventCreate(&e));
     P.pool_ready = true;
     return FAMSA_OK;
 }
@@ -228,7 +254,7 @@ int new_slab(famsa_ctx* ctx, size_t bytes, int* out)
 
 uint32_t new_entry(ProfState& P)
 {
-    if (!P.free_ids.empty()) { const uint32_t id = P.free_ids.back(); P.free_ids.pop_back(); return id; }
+    if (!P.free_ids.empty()) { const uint32_t id = P.free_ids.back(); P.free_ids.pop_back(); ++P.entries[id].gen; return id; }
     P.entries.emplace_back();
     return (uint32_t)P.entries.size() - 1;
 }
@@ -240,7 +266,7 @@ void place(ProfState& P, uint32_t id, int slab, size_t* cursor, uint32_t width, 
     char* base = static_cast<char*>(P.slabs[slab].p) + *cursor;
     e.scores = reinterpret_cast<long long*>(base);
     e.counters = reinterpret_cast<int*>(base + ((size_t)width + 1) * kRows * sizeof(long long));
-    e.width = width; e.card = card; e.slab = slab; e.live = true;
+    e.width = width; e.card = card; e.slab = slab; e.live = true; e.pending = false;
     *cursor += table_bytes(width);                                  // multiple of 384: keeps 128-byte alignment
     ++P.slabs[slab].live;
     ++P.n_live;
@@ -314,27 +340,50 @@ int prof_put(famsa_ctx* ctx, const famsa_dp_profile* profs, uint32_t n, uint32_t
     return FAMSA_OK;
 }
 
-int prof_merge_batch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t n, const int64_t gaps[4], uint32_t* merged_ids,
-                     famsa_dp_result* results, uint8_t* path_buf, uint64_t path_cap)
+// d_widths[id]: the slot a pending profile's width is published to (see ProfEntry::pending)
+static int ensure_widths(famsa_ctx* ctx, size_t n_ids)
+{
+    ProfState& P = ctx->prof;
+    if (n_ids * sizeof(uint32_t) <= P.d_widths.cap) return FAMSA_OK;
+    // growing moves the array: nothing may be in flight that still points into the old one
+    for (const ProfEntry& e : P.entries)
+        if (e.live && e.pending) { set_error("internal: width table cannot grow while merges are queued"); return FAMSA_E_STATE; }
+    return P.d_widths.reserve(std::max<size_t>(n_ids * 2, 4096) * sizeof(uint32_t));
+}
+
+static cudaEvent_t take_event(ProfState& P)
+{
+    if (!P.free_events.empty()) { cudaEvent_t e = P.free_events.back(); P.free_events.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    return e;
+}
+
+// Queues one batch of independent merges on the context's stream and returns without waiting: leaves, DP + traceback
+// (dp.cu), merged tables (k_prof_construct), then one copy of the result records and paths into h_results / h_paths
+// (pinned memory makes that copy asynchronous too).  Children may be profiles of batches that are still queued -- their
+// widths are then upper bounds on the host and are resolved on the device.  The merged profiles are sized for w1 + w2.
+static int prof_launch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t n, const int64_t gaps[4],
+                       famsa_dp_result* h_results, uint8_t* h_paths, uint64_t path_cap, ProfTicket* T)
 {
     ProfState& P = ctx->prof;
     LcsState& L = ctx->lcs;
-    FB_TRY(ensure_pool(ctx));
-    P.timing_valid = false;
-    if (!n) return FAMSA_OK;
     cudaStream_t st = ctx->stream;
 
-    // resolve the children; leaves get scratch tables for the duration of the call
+    // resolve the children; leaves get scratch tables for the duration of the batch
     std::vector<famsa_dp_job> jobs(n);
+    std::vector<DpJobExt> ext(n);
     std::vector<LeafDesc> leaves;
     std::vector<std::pair<uint32_t, int>> leaf_slot;                 // (job, side) per leaf, in `leaves` order
     std::vector<uint8_t> seen(P.entries.size(), 0);
     size_t leaf_bytes = 0;
-    uint64_t path_need = 0;
+    uint64_t path_need = 0, cells = 0;
     for (uint32_t k = 0; k < n; ++k) {
         for (int side = 0; side < 2; ++side) {
             const uint32_t c = side ? merges[k].child2 : merges[k].child1;
             famsa_dp_profile& p = side ? jobs[k].p2 : jobs[k].p1;
+            const uint32_t*& src = side ? ext[k].w2_src : ext[k].w1_src;
+            src = nullptr;
             if (c & FAMSA_PROF_LEAF) {
                 const uint32_t seq = c & ~FAMSA_PROF_LEAF;
                 if (seq >= L.n) { set_error("famsa_prof_merge_batch: leaf " + std::to_string(seq) + " was not uploaded (famsa_lcs_upload)"); return FAMSA_E_INVALID; }
@@ -351,84 +400,314 @@ int prof_merge_batch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t n,
                 seen[c] = 1;
                 const ProfEntry& e = P.entries[c];
                 p.scores = reinterpret_cast<const int64_t*>(e.scores); p.counters = e.counters; p.width = e.width; p.card = e.card;
+                if (e.pending) src = P.d_widths.as<uint32_t>() + c;
             }
         }
         path_need += (uint64_t)jobs[k].p1.width + jobs[k].p2.width;
+        cells += (uint64_t)jobs[k].p1.width * jobs[k].p2.width;
     }
     if (path_need > path_cap) {
         set_error("famsa_prof_merge_batch: path_buf holds " + std::to_string(path_cap) + " bytes, " + std::to_string(path_need) + " needed");
         return FAMSA_E_INVALID;
     }
+    FB_TRY(ensure_widths(ctx, P.entries.size() + n));
 
-    FB_CUDA(cudaEventRecord(P.ev[0], st));
-    if (!leaves.empty()) {
-        FB_TRY(P.d_leaf.reserve(leaf_bytes));
-        FB_TRY(P.d_leafdesc.reserve(sizeof(LeafDesc) * leaves.size()));
+    // merged tables: one slab per batch, every profile sized for the widest alignment possible (w1 + w2 columns)
+    size_t slab_bytes = 0;
+    for (uint32_t k = 0; k < n; ++k) slab_bytes += table_bytes(jobs[k].p1.width + jobs[k].p2.width);
+    int slab;
+    FB_TRY(new_slab(ctx, slab_bytes, &slab));
+    // batch blob: [results][con jobs][leaf descs][paths][leaf tables]
+    const size_t o_res = 0;
+    const size_t o_con = align_up(o_res + sizeof(famsa_dp_result) * n, 256);
+    const size_t o_leafd = align_up(o_con + sizeof(ConJobDev) * n, 256);
+    const size_t o_path = align_up(o_leafd + sizeof(LeafDesc) * leaves.size(), 256);
+    const size_t o_leaf = align_up(o_path + std::max<uint64_t>(path_need, 1), 256);
+    const size_t blob_bytes = o_leaf + leaf_bytes;
+    unsigned char* blob = nullptr;
+    {
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&blob), blob_bytes, st);
+        if (e != cudaSuccess) { set_error(std::string("cudaMallocAsync for a merge batch failed: ") + cudaGetErrorString(e)); return FAMSA_E_NOMEM; }
+    }
+    famsa_dp_result* d_results = reinterpret_cast<famsa_dp_result*>(blob + o_res);
+    uint8_t* d_path = blob + o_path;
+
+    std::vector<unsigned char> pack(o_path - o_con);
+    ConJobDev* cj = reinterpret_cast<ConJobDev*>(pack.data());
+    LeafDesc* ld = reinterpret_cast<LeafDesc*>(pack.data() + (o_leafd - o_con));
+    {
         size_t cur = 0;
         for (size_t a = 0; a < leaves.size(); ++a) {
             famsa_dp_profile& p = leaf_slot[a].second ? jobs[leaf_slot[a].first].p2 : jobs[leaf_slot[a].first].p1;
-            char* base = P.d_leaf.as<char>() + cur;
+            char* base = reinterpret_cast<char*>(blob + o_leaf + cur);
             leaves[a].scores = reinterpret_cast<long long*>(base);
             leaves[a].counters = reinterpret_cast<int*>(base + ((size_t)p.width + 1) * kRows * sizeof(long long));
             p.scores = reinterpret_cast<const int64_t*>(leaves[a].scores);
             p.counters = leaves[a].counters;
             cur += table_bytes(p.width);
+            ld[a] = leaves[a];
         }
-        FB_CUDA(cudaMemcpyAsync(P.d_leafdesc.p, leaves.data(), sizeof(LeafDesc) * leaves.size(), cudaMemcpyHostToDevice, st));
-        k_prof_leaf<<<(unsigned)leaves.size(), 256, 0, st>>>(P.d_leafdesc.as<LeafDesc>(), L.d_raw_codes.as<int8_t>(),
+    }
+    T->merged_ids.assign(n, 0);
+    T->merged_gen.assign(n, 0);
+    size_t cur = 0;
+    uint32_t tiles = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint32_t ub = jobs[k].p1.width + jobs[k].p2.width;
+        const uint32_t id = new_entry(P);
+        place(P, id, slab, &cur, ub, jobs[k].p1.card + jobs[k].p2.card);
+        P.entries[id].pending = true;
+        T->merged_ids[k] = id;
+        T->merged_gen[k] = P.entries[id].gen;
+        ext[k].w_dst = P.d_widths.as<uint32_t>() + id;
+        cj[k].os = P.entries[id].scores; cj[k].oc = P.entries[id].counters; cj[k].job = k; cj[k].tile0 = tiles;
+        tiles += (ub + 1 + kConTile - 1) / kConTile;
+    }
+    FB_CUDA(cudaEventRecord(P.ev[0], st));
+    FB_CUDA(cudaMemcpyAsync(blob + o_con, pack.data(), pack.size(), cudaMemcpyHostToDevice, st));
+    if (!leaves.empty()) {
+        k_prof_leaf<<<(unsigned)leaves.size(), 256, 0, st>>>(reinterpret_cast<const LeafDesc*>(blob + o_leafd), L.d_raw_codes.as<int8_t>(),
                                                              L.d_raw_off.as<uint64_t>(), L.d_raw_len.as<uint32_t>(),
                                                              P.d_sm.as<long long>(), gaps[0], gaps[1], gaps[2], gaps[3]);
         FB_CUDA(cudaGetLastError());
         ++ctx->launches;
     }
-
     // DP + traceback on the resident tables (dp.cu)
-    FB_TRY(P.d_results.reserve(sizeof(famsa_dp_result) * n));
-    FB_TRY(P.d_path.reserve(std::max<uint64_t>(path_need, 64)));
-    FB_TRY(dp_run_device(ctx, jobs.data(), n, gaps, P.d_results.as<famsa_dp_result>(), P.d_path.as<uint8_t>(), nullptr, st));
-    FB_CUDA(cudaMemcpyAsync(results, P.d_results.p, sizeof(famsa_dp_result) * n, cudaMemcpyDeviceToHost, st));
-    FB_CUDA(cudaMemcpyAsync(path_buf, P.d_path.p, path_need, cudaMemcpyDeviceToHost, st));
-    FB_CUDA(cudaStreamSynchronize(st));                             // the merged widths size the new tables
-    FB_TRY(dp_check_results(results, n));
-
-    // merged tables: one slab per call
-    size_t bytes = 0;
-    for (uint32_t k = 0; k < n; ++k) bytes += table_bytes(results[k].path_len);
-    int slab;
-    FB_TRY(new_slab(ctx, bytes, &slab));
-    std::vector<ConJob> cj(n);
-    size_t cur = 0;
-    uint32_t tiles = 0;
-    for (uint32_t k = 0; k < n; ++k) {
-        const famsa_dp_result& r = results[k];
-        const famsa_dp_profile& R = r.swapped ? jobs[k].p2 : jobs[k].p1;
-        const famsa_dp_profile& C = r.swapped ? jobs[k].p1 : jobs[k].p2;
-        const uint32_t id = new_entry(P);
-        place(P, id, slab, &cur, r.path_len, R.card + C.card);
-        merged_ids[k] = id;
-        ConJob& j = cj[k];
-        j.sr = reinterpret_cast<const long long*>(R.scores); j.cr = R.counters;
-        j.sc = reinterpret_cast<const long long*>(C.scores); j.cc = C.counters;
-        j.os = P.entries[id].scores; j.oc = P.entries[id].counters;
-        j.path = P.d_path.as<uint8_t>() + r.path_offset;
-        j.wr = R.width; j.wc = C.width; j.cardr = R.card; j.cardc = C.card; j.W = r.path_len; j.tile0 = tiles;
-        tiles += (r.path_len + 1 + kConTile - 1) / kConTile;
-    }
-    FB_TRY(P.d_cjobs.reserve(sizeof(ConJob) * n));
-    FB_CUDA(cudaMemcpyAsync(P.d_cjobs.p, cj.data(), sizeof(ConJob) * n, cudaMemcpyHostToDevice, st));
+    DpMeta* d_meta = nullptr;
+    void* dp_blob = nullptr;
+    FB_TRY(dp_run_device(ctx, jobs.data(), ext.data(), n, gaps, d_results, d_path, nullptr, &d_meta, &dp_blob, st));
     FB_CUDA(cudaEventRecord(P.ev[1], st));
-    k_prof_construct<<<tiles, kConThreads, 0, st>>>(P.d_cjobs.as<ConJob>(), n, gaps[0], gaps[1], gaps[2], gaps[3]);
+    k_prof_construct<<<tiles, kConThreads, 0, st>>>(reinterpret_cast<const ConJobDev*>(blob + o_con), n, d_meta, d_results, d_path,
+                                                    gaps[0], gaps[1], gaps[2], gaps[3]);
     FB_CUDA(cudaGetLastError());
     ++ctx->launches;
     FB_CUDA(cudaEventRecord(P.ev[2], st));
     P.timing_valid = true;
-
+    FB_CUDA(cudaMemcpyAsync(h_results, d_results, sizeof(famsa_dp_result) * n, cudaMemcpyDeviceToHost, st));
+    if (path_need) FB_CUDA(cudaMemcpyAsync(h_paths, d_path, path_need, cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaFreeAsync(dp_blob, st));
+    FB_CUDA(cudaFreeAsync(blob, st));
     // the children are consumed (msa.cpp:406-407); frees are ordered after the construct kernel
     for (uint32_t k = 0; k < n; ++k)
         for (uint32_t c : {merges[k].child1, merges[k].child2})
             if (!(c & FAMSA_PROF_LEAF)) FB_TRY(release_entry(ctx, c));
-    // cj (pageable) was handed to an async copy: make sure it has been consumed before it goes out of scope
-    FB_CUDA(cudaEventSynchronize(P.ev[1]));
+    T->done = take_event(P);
+    FB_CUDA(cudaEventRecord(T->done, st));
+    T->n = n; T->h_results = h_results; T->h_paths = h_paths; T->path_bytes = path_need; T->cells_bound = cells;
+    return FAMSA_OK;
+}
+
+// Waits for a queued batch and takes note of the merged widths.
+static int prof_collect(famsa_ctx* ctx, ProfTicket* T)
+{
+    ProfState& P = ctx->prof;
+    FB_CUDA(cudaEventSynchronize(T->done));
+    P.free_events.push_back(T->done);
+    T->done = nullptr;
+    int rc = FAMSA_OK;
+    for (uint32_t k = 0; k < T->n; ++k) {
+        ProfEntry& e = P.entries[T->merged_ids[k]];
+        const famsa_dp_result& r = T->h_results[k];
+        if (e.live && e.pending && e.gen == T->merged_gen[k]) {     // (a later batch may already have consumed it)
+            e.pending = false;
+            if (r.variant != 0xFF) e.width = r.path_len;
+        }
+        if (r.variant == 0xFF && rc == FAMSA_OK) {
+            set_error("merge " + std::to_string(k) + " of the batch: a profile holds negative residue / gap counts");
+            rc = FAMSA_E_INVALID;
+        }
+    }
+    return rc;
+}
+
+int prof_merge_batch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t n, const int64_t gaps[4], uint32_t* merged_ids,
+                     famsa_dp_result* results, uint8_t* path_buf, uint64_t path_cap)
+{
+    ProfState& P = ctx->prof;
+    FB_TRY(ensure_pool(ctx));
+    P.timing_valid = false;
+    if (!n) return FAMSA_OK;
+    ProfTicket T;
+    FB_TRY(prof_launch(ctx, merges, n, gaps, results, path_buf, path_cap, &T));
+    const int rc = prof_collect(ctx, &T);
+    for (uint32_t k = 0; k < n; ++k) merged_ids[k] = T.merged_ids[k];
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The whole progressive alignment (CFAMSA::ComputeAlignment, msa.cpp:360-438) as one call.
+//
+// The reference hands a merge to a worker thread as soon as both children are finished, deepest node first
+// (CProfileQueue, queues.cpp:27-40, 127-187).  Here the unit of submission is "every merge that is ready", and the host
+// does not wait for a batch before it queues the next one: all a parent needs from its children on the host side is an
+// upper bound of their widths (to size buffers); the real widths travel on the device.  Several batches are therefore in
+// flight on the stream while the host collects finished ones in the background to tighten its bounds; it only drains
+// the queue when the bounds of the next batch would inflate its scratch beyond what the real widths would need.
+// ------------------------------------------------------------------------------------------------
+static int pinned_reserve(void** p, size_t* cap, size_t bytes)
+{
+    if (bytes <= *cap) return FAMSA_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    FB_CUDA(cudaHostAlloc(p, want, cudaHostAllocDefault));
+    *cap = want;
+    return FAMSA_OK;
+}
+
+int prof_align_tree(famsa_ctx* ctx, const int32_t* tree, uint32_t n_leaves, const int64_t gaps[4], famsa_dp_result* results,
+                    uint32_t* root_id, uint64_t* path_bytes, famsa_tree_stats* stats)
+{
+    ProfState& P = ctx->prof;
+    LcsState& L = ctx->lcs;
+    FB_TRY(ensure_pool(ctx));
+    const auto t_begin = std::chrono::steady_clock::now();
+    if (n_leaves != L.n) { set_error("famsa_prof_align_tree: the tree has " + std::to_string(n_leaves) + " leaves, " + std::to_string(L.n) + " sequences are uploaded"); return FAMSA_E_INVALID; }
+    if (!P.has_scoring) { set_error("famsa_prof_align_tree: famsa_prof_set_scoring first"); return FAMSA_E_STATE; }
+    if (n_leaves < 2) { set_error("famsa_prof_align_tree: fewer than two sequences"); return FAMSA_E_INVALID; }
+    const uint32_t n_merges = n_leaves - 1, n_nodes = 2 * n_leaves - 1;
+    // dependency levels; children must precede parents (tree_structure order)
+    std::vector<uint32_t> depth(n_nodes, 0);
+    std::vector<std::vector<uint32_t>> levels;
+    std::vector<uint8_t> used(n_nodes, 0);
+    for (uint32_t k = 0; k < n_merges; ++k) {
+        const int32_t a = tree[2 * k], b = tree[2 * k + 1];
+        if (a < 0 || b < 0 || (uint32_t)a >= n_leaves + k || (uint32_t)b >= n_leaves + k || a == b || used[a] || used[b]) {
+            set_error("famsa_prof_align_tree: node " + std::to_string(n_leaves + k) + " has invalid children");
+            return FAMSA_E_INVALID;
+        }
+        used[a] = used[b] = 1;
+        const uint32_t d = std::max(depth[a], depth[b]) + 1;
+        depth[n_leaves + k] = d;
+        if (levels.size() < d) levels.resize(d);
+        levels[d - 1].push_back(k);
+    }
+    FB_TRY(ensure_widths(ctx, P.entries.size() + n_merges + 16));
+    FB_TRY(pinned_reserve(reinterpret_cast<void**>(&P.h_tree_results), &P.h_tree_results_cap, sizeof(famsa_dp_result) * n_merges));
+
+    std::vector<uint32_t> handle(n_nodes), width(n_nodes);           // width: layout width (bound until collected)
+    for (uint32_t i = 0; i < n_leaves; ++i) { handle[i] = FAMSA_PROF_LEAF | i; width[i] = L.h_len_sorted[L.h_invperm[i]]; }
+    struct InFlight { ProfTicket t; std::vector<uint32_t> merge_ids; uint64_t path_base; size_t res_base; };
+    std::deque<InFlight> q;
+    uint64_t path_cursor = 0, cells = 0;
+    size_t res_cursor = 0;
+    uint32_t n_batches = 0, max_in_flight = 0, n_drains = 0;
+    uint64_t peak_bytes = 0;
+    constexpr size_t kMaxInFlight = 8;
+    FB_CUDA(cudaEventRecord(P.ev_tree[0], ctx->stream));
+    auto collect_front = [&]() -> int {
+        InFlight& f = q.front();
+        const int rc = prof_collect(ctx, &f.t);
+        for (size_t a = 0; a < f.merge_ids.size(); ++a) {
+            const uint32_t k = f.merge_ids[a];
+            famsa_dp_result& r = P.h_tree_results[f.res_base + a];
+            r.path_offset += f.path_base;
+            results[k] = r;
+            width[n_leaves + k] = r.path_len;
+            cells += (uint64_t)r.rows_width * r.cols_width;
+        }
+        q.pop_front();
+        return rc;
+    };
+    int rc = FAMSA_OK;
+    // paths of all merges: one pinned arena, grown only while nothing is in flight
+    uint64_t arena_need = 0;
+    for (uint32_t i = 0; i < n_leaves; ++i) arena_need += width[i];
+    arena_need = arena_need * 4 + (1u << 20);
+    FB_TRY(pinned_reserve(reinterpret_cast<void**>(&P.h_tree_paths), &P.h_tree_paths_cap, arena_need));
+    for (size_t lv = 0; lv < levels.size() && rc == FAMSA_OK; ++lv) {
+        const std::vector<uint32_t>& level = levels[lv];
+        // collect whatever has finished already (tightens the bounds for free)
+        while (!q.empty() && cudaEventQuery(q.front().t.done) == cudaSuccess && rc == FAMSA_OK) rc = collect_front();
+        if (rc) break;
+        auto level_cost = [&](uint64_t* bound_cells, uint64_t* path_need) {
+            *bound_cells = *path_need = 0;
+            for (uint32_t k : level) {
+                const uint32_t a = (uint32_t)tree[2 * k], b = (uint32_t)tree[2 * k + 1];
+                *bound_cells += (uint64_t)width[a] * width[b];
+                *path_need += (uint64_t)width[a] + width[b];
+            }
+        };
+        uint64_t bound_cells, path_need;
+        level_cost(&bound_cells, &path_need);
+        // Run ahead of the device only while that is cheap: a few batches deep, and not when the bounds of this level
+        // (sums of bounds of uncollected children) would make its direction matrices much larger than they need to be.
+        bool pending_child = false;
+        for (uint32_t k : level)
+            for (int s = 0; s < 2; ++s) {
+                const uint32_t c = (uint32_t)tree[2 * k + s];
+                if (c >= n_leaves && P.entries[handle[c]].pending) pending_child = true;
+            }
+        const bool heavy = bound_cells > (64ull << 20);
+        if ((pending_child && heavy) || q.size() >= kMaxInFlight || path_cursor + path_need > P.h_tree_paths_cap) {
+            const bool all = (pending_child && heavy) || path_cursor + path_need > P.h_tree_paths_cap;
+            while (!q.empty() && rc == FAMSA_OK && (all || q.size() >= kMaxInFlight)) rc = collect_front();
+            if (rc) break;
+            ++n_drains;
+            level_cost(&bound_cells, &path_need);
+            if (path_cursor + path_need > P.h_tree_paths_cap) {      // nothing in flight now: the arena may move
+                uint8_t* old = P.h_tree_paths;
+                size_t old_cap = P.h_tree_paths_cap;
+                P.h_tree_paths = nullptr; P.h_tree_paths_cap = 0;
+                FB_TRY(pinned_reserve(reinterpret_cast<void**>(&P.h_tree_paths), &P.h_tree_paths_cap, (path_cursor + path_need) * 2));
+                memcpy(P.h_tree_paths, old, path_cursor);
+                cudaFreeHost(old);
+                (void)old_cap;
+            }
+        }
+        std::vector<famsa_prof_merge> mg(level.size());
+        for (size_t a = 0; a < level.size(); ++a) {
+            const uint32_t k = level[a];
+            mg[a].child1 = handle[(uint32_t)tree[2 * k]];
+            mg[a].child2 = handle[(uint32_t)tree[2 * k + 1]];
+        }
+        q.emplace_back();
+        InFlight& f = q.back();
+        f.merge_ids = level;
+        f.path_base = path_cursor;
+        f.res_base = res_cursor;
+        rc = prof_launch(ctx, mg.data(), (uint32_t)mg.size(), gaps, P.h_tree_results + res_cursor, P.h_tree_paths + path_cursor,
+                         P.h_tree_paths_cap - path_cursor, &f.t);
+        if (rc) { q.pop_back(); break; }
+        for (size_t a = 0; a < level.size(); ++a) {
+            const uint32_t k = level[a];
+            handle[n_leaves + k] = f.t.merged_ids[a];
+            width[n_leaves + k] = P.entries[f.t.merged_ids[a]].width;       // the bound w1 + w2
+        }
+        path_cursor += path_need;
+        res_cursor += level.size();
+        ++n_batches;
+        max_in_flight = std::max<uint32_t>(max_in_flight, (uint32_t)q.size());
+        peak_bytes = std::max(peak_bytes, P.resident_bytes);
+    }
+    while (!q.empty()) { const int r2 = collect_front(); if (rc == FAMSA_OK) rc = r2; }
+    if (rc) return rc;
+    FB_CUDA(cudaEventRecord(P.ev_tree[1], ctx->stream));
+    FB_CUDA(cudaEventSynchronize(P.ev_tree[1]));
+    float dev_ms = 0.f;
+    FB_CUDA(cudaEventElapsedTime(&dev_ms, P.ev_tree[0], P.ev_tree[1]));
+    P.tree_path_bytes = path_cursor;
+    P.tree_merges = n_merges;
+    if (root_id) *root_id = handle[n_nodes - 1];
+    if (path_bytes) *path_bytes = path_cursor;
+    if (stats) {
+        stats->wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        stats->device_ms = dev_ms;
+        stats->cells = cells;
+        stats->n_batches = n_batches;
+        stats->n_drains = n_drains;
+        stats->max_in_flight = max_in_flight;
+        stats->peak_resident_bytes = peak_bytes;
+    }
+    return FAMSA_OK;
+}
+
+int prof_tree_paths(famsa_ctx* ctx, uint8_t* path_buf, uint64_t cap)
+{
+    ProfState& P = ctx->prof;
+    if (!P.tree_merges) { set_error("famsa_prof_tree_paths: no famsa_prof_align_tree has run"); return FAMSA_E_STATE; }
+    if (cap < P.tree_path_bytes) { set_error("famsa_prof_tree_paths: buffer holds " + std::to_string(cap) + " bytes, " + std::to_string(P.tree_path_bytes) + " needed"); return FAMSA_E_INVALID; }
+    memcpy(path_buf, P.h_tree_paths, P.tree_path_bytes);
     return FAMSA_OK;
 }
 
@@ -476,8 +755,13 @@ void prof_release_all(famsa_ctx* ctx)
     for (ProfSlab& s : P.slabs)
         if (s.p) cudaFreeAsync(s.p, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&P.d_sm, &P.d_leaf, &P.d_leafdesc, &P.d_results, &P.d_path, &P.d_cjobs}) b->release();
+    for (DevBuf* b : {&P.d_sm, &P.d_widths}) b->release();
+    for (cudaEvent_t e : P.free_events) cudaEventDestroy(e);
+    if (P.h_tree_results) cudaFreeHost(P.h_tree_results);
+    if (P.h_tree_paths) cudaFreeHost(P.h_tree_paths);
     for (auto& e : P.ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : P.ev_tree)
         if (e) cudaEventDestroy(e);
     P = ProfState();
 }

@@ -233,6 +233,34 @@ int famsa_prof_put(famsa_ctx* ctx, const famsa_dp_profile* profiles, uint32_t n,
 int famsa_prof_merge_batch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t n, const int64_t gaps[4],
                            uint32_t* merged_ids_out, famsa_dp_result* results, uint8_t* path_buf, uint64_t path_cap);
 
+/* The whole progressive alignment as ONE call: replaces the worker loop of CFAMSA::ComputeAlignment
+ * (src/msa.cpp:360-438) together with CProfileQueue (src/core/queues.cpp:17-187), which hands a merge to a worker
+ * thread as soon as both of its children are finished.  Here every merge whose children are finished (or queued) is
+ * submitted to the device without the host waiting for earlier batches: widths of queued children travel on the
+ * device, so several dependency levels are in flight at once and nothing but the per-merge result records and
+ * traceback paths ever returns to the host.
+ * tree: the internal nodes of the reference's tree_structure (src/tree/TreeDefs.h:15-16), i.e. guide_tree.data() +
+ * n_leaves viewed as int32 pairs: tree[2k], tree[2k+1] = children of node n_leaves + k; leaves 0..n_leaves-1 are the
+ * sequences of famsa_lcs_upload in caller order; children precede parents.  Needs famsa_prof_set_scoring.
+ * results[k] (k < n_leaves - 1) describes merge k; its path_offset indexes the path buffer fetched afterwards with
+ * famsa_prof_tree_paths (*path_bytes_out bytes; offsets are not contiguous).  *root_id_out = resident id of the final
+ * profile (famsa_prof_get / famsa_prof_drop). */
+typedef struct {
+    double wall_ms;               /* host wall clock of the call */
+    double device_ms;             /* first to last operation on the stream (CUDA events) */
+    uint64_t cells;               /* sum over merges of rows_width * cols_width */
+    uint32_t n_batches;           /* submissions of ready merges */
+    uint32_t n_drains;            /* times the host had to wait for the device before it could submit more */
+    uint32_t max_in_flight;       /* batches queued at once */
+    uint32_t pad;
+    uint64_t peak_resident_bytes; /* HBM held by resident profiles at the high-water mark */
+} famsa_tree_stats;
+
+int famsa_prof_align_tree(famsa_ctx* ctx, const int32_t* tree, uint32_t n_leaves, const int64_t gaps[4],
+                          famsa_dp_result* results, uint32_t* root_id_out, uint64_t* path_bytes_out,
+                          famsa_tree_stats* stats /* may be NULL */);
+int famsa_prof_tree_paths(famsa_ctx* ctx, uint8_t* path_buf, uint64_t path_cap);
+
 /* width/card of a resident profile; scores ((width+1)*32 int64) / counters ((width+1)*32 int32) are
  * copied to the host when non-NULL. */
 int famsa_prof_get(famsa_ctx* ctx, uint32_t id, uint32_t* width, uint32_t* card, int64_t* scores, int32_t* counters);

@@ -181,6 +181,8 @@ def ref() -> C.CDLL:
         lib.ref_profile_construct.restype = vp
         lib.ref_dp_align_pairs_mt.argtypes = [vp, vp, vp, u32, C.c_int, vp]
         lib.ref_dp_align_pairs_mt.restype = C.c_double
+        lib.ref_align_tree_mt.argtypes = [vp, vp, u32, vp, C.c_int, vp, vp, vp, vp, u32]
+        lib.ref_align_tree_mt.restype = C.c_double
         _ref = lib
     return _ref
 
@@ -273,6 +275,24 @@ class RefDp:
         cells = C.c_uint64()
         sec = self.lib.ref_dp_align_pairs_mt(self.h, a, b, n, n_threads, C.byref(cells))
         return sec, cells.value
+
+    def align_tree_mt(self, seqs: list[str], merges, n_threads: int, want_rows: bool = False):
+        """The reference's whole ComputeAlignment (CProfileQueue + worker threads) over a guide tree.  merges: (n-1, 2)
+        child ids of the internal nodes.  Returns (seconds, cells, total score, width[, {seq_no: gapped row}])."""
+        n = len(seqs)
+        arr = (C.c_char_p * n)(*[s.encode("ascii") for s in seqs])
+        tree = np.full((2 * n - 1, 2), -1, dtype=np.int32)
+        tree[n:] = np.asarray(merges, dtype=np.int32).reshape(-1, 2)
+        cells, total, width = C.c_uint64(), C.c_int64(), C.c_uint32()
+        stride = int(sum(len(s) for s in seqs)) + 1 if want_rows else 0
+        stride = min(stride, 1 << 20)
+        rows = np.zeros(n * stride, dtype=np.uint8) if want_rows else None
+        sec = self.lib.ref_align_tree_mt(self.h, arr, n, _p(tree), n_threads, C.byref(cells), C.byref(total), C.byref(width),
+                                         _p(rows), stride)
+        out = (sec, cells.value, total.value, width.value)
+        if want_rows:
+            out += ({i: bytes(rows[i * stride:i * stride + width.value]).decode() for i in range(n)},)
+        return out
 
     def align(self, p1, p2, no_threads: int = 1):
         """Returns (merged profile handle, total_score).  p1 and p2 are consumed and freed."""

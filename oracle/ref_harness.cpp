@@ -19,6 +19,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 #include <thread>
@@ -30,6 +31,7 @@
 #include "core/defs.h"
 #include "core/params.h"
 #include "core/profile.h"
+#include "core/queues.h"
 #include "core/sequence.h"
 #include "lcs/lcsbp.h"
 #include "tree/AbstractTreeGenerator.h"
@@ -434,6 +436,70 @@ double ref_dp_align_pairs_mt(void* h, void** p1s, void** p2s, uint32_t n, int n_
         });
     for (auto& w : workers) w.join();
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// The whole progressive alignment the way CFAMSA::ComputeAlignment runs it (msa.cpp:360-438): n_threads workers take
+// tasks from the reference's own CProfileQueue (queues.cpp: deepest ready node first, leaves included) and build
+// `new CProfile(gs, params)` for a leaf or `new CProfile(p1, p2, params, no_threads, no_rows_per_box, atp)` for an
+// internal node (internal refinement is off: thr_internal_refinement = 0, and the sets timed here are above
+// thr_refinement).  The worker loop below restates msa.cpp:375-426 because msa.cpp itself drags in the I/O libraries;
+// queue, profiles and DP are the reference's object code.  tree: (2n-1) x 2 child ids, leaves (-1, -1).
+// Returns wall seconds (= the reference's time.alignment); *cells = sum of W1*W2 over the merges, *total / *width = total
+// score and width of the final profile, rows_out (optional, n x (width+1) bytes, row i = sequence number i).
+double ref_align_tree_mt(void* h, const char* const* letters, uint32_t n, const int* tree, int n_threads, uint64_t* cells,
+                         int64_t* total, uint32_t* width, char* rows_out, uint32_t rows_stride)
+{
+    auto* s = static_cast<DpSession*>(h);
+    CParams params = s->params;
+    params.n_threads = (uint32_t)n_threads;
+    refresh::active_thread_pool_v2 atp(n_threads, n_threads);
+    std::vector<CGappedSequence*> gapped;
+    for (uint32_t i = 0; i < n; ++i) {
+        CSequence seq("s" + std::to_string(i), std::string(letters[i]), (int)i, nullptr);
+        gapped.push_back(new CGappedSequence(std::move(seq)));
+    }
+    tree_structure guide_tree;
+    for (uint32_t i = 0; i < 2 * n - 1; ++i) guide_tree.emplace_back(tree[2 * i], tree[2 * i + 1]);
+    std::map<size_t, CProfile*> profiles;
+    std::atomic<uint64_t> c(0);
+    auto t0 = std::chrono::steady_clock::now();
+    {
+        CProfileQueue pq(&gapped, &profiles, &guide_tree, (uint32_t)n_threads);
+        std::vector<std::thread> workers;
+        for (int t = 0; t < n_threads; ++t)
+            workers.emplace_back([&] {
+                CGappedSequence* gs;
+                CProfile *prof1, *prof2, *prof_sol;
+                size_t prof_id;
+                uint32_t no_threads, no_rows_per_box;
+                while (pq.GetTask(prof_id, gs, prof1, prof2, no_threads, no_rows_per_box)) {
+                    if (gs != nullptr)
+                        prof_sol = new CProfile(*gs, &params);
+                    else {
+                        c += (uint64_t)prof1->width * prof2->width;
+                        prof_sol = new CProfile(prof1, prof2, &params, no_threads, no_rows_per_box, &atp);
+                        delete prof1;
+                        delete prof2;
+                    }
+                    pq.AddSolution(prof_id, prof_sol);
+                }
+            });
+        for (auto& w : workers) w.join();
+    }
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    CProfile* root = profiles.begin()->second;
+    if (cells) *cells = c.load();
+    if (total) *total = root->total_score;
+    if (width) *width = (uint32_t)root->width;
+    if (rows_out)
+        for (uint32_t i = 0; i < root->data.size(); ++i) {
+            std::vector<char> buf(root->width + 2);
+            const int no = ref_profile_row(root, i, buf.data());
+            if ((size_t)root->width + 1 <= rows_stride) memcpy(rows_out + (size_t)no * rows_stride, buf.data(), root->width + 1);
+        }
+    delete root;
+    for (auto* g : gapped) delete g;
+    return sec;
 }
 
 } // extern "C"

@@ -139,10 +139,45 @@ def make_hemopexin():
     print("hemopexin_medoid_sl.npz:", len(recs), "merges")
 
 
+def make_hemopexin_sl():
+    """hemopexin_sl.npz -- BASELINE config 4, second tree: test/hemopexin/hemopexin under the DEFAULT guide tree
+    (-gt sl = MSTPrim on the length-sorted set, msa.cpp:245-256 + MSTPrim.cpp:280-549; the reference holds no golden
+    file for it, so the tree is the reference's own MSTPrim run here).  Sequences in FAMSA's order, the tree's
+    merges, per-merge reference total score and CRC32 of each traceback path, CRC32 of the final alignment rows."""
+    import zlib
+    from oracle import pyoracle
+    from dp_cases import reference_merges
+    ids, seqs = seqio.read_fasta(os.path.join(REF, "hemopexin", "hemopexin"))
+    code_list = [seqio.encode(s.upper()) for s in seqs]
+    order = sorted(range(len(seqs)), key=lambda i: (-len(code_list[i]), code_list[i].tobytes()))
+    lseqs = [seqs[i].upper() for i in order]
+    n = len(lseqs)
+    tree = pyoracle.RefSeqSet(lseqs).mst_prim_tree(4)
+    merges = [(int(a), int(b)) for a, b in tree[n:]]
+    g, recs = reference_merges(lseqs, merges, threads=(1,))
+    totals, crcs = [], []
+    for r in recs:
+        o = pyoracle.dp_align(*r["job"], g)
+        pth = pyoracle.path_from_rows(r["rows"], r["m1"], r["m2"], o["swapped"])
+        assert np.array_equal(pth, o["path"]) and o["total"] == r["total"]
+        totals.append(r["total"]); crcs.append(zlib.crc32(pth.tobytes()))
+    final = recs[-1]["rows"]
+    rows_crc = zlib.crc32("\n".join(final[i] for i in range(n)).encode())
+    np.savez_compressed(os.path.join(HERE, "hemopexin_sl.npz"), seqs=np.array(lseqs), merges=np.array(merges), gaps=g,
+                        totals=np.array(totals, dtype=np.int64), path_crc=np.array(crcs, dtype=np.uint32),
+                        rows_crc=np.array(rows_crc, dtype=np.uint32), final_width=np.array(len(final[0])))
+    print("hemopexin_sl.npz:", len(recs), "merges, final width", len(final[0]))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        sys.path.insert(0, os.path.join(HERE, ".."))
+        globals()[sys.argv[1]]()
+        sys.exit(0)
     main()
     make_dp()
     make_hemopexin()
+    make_hemopexin_sl()
     make_sl_tree()
 
 
