@@ -52,6 +52,14 @@ def workload(n_gpus: int):
 from famsa_b200.sharding import row_shards, shard_sizes, tri, all_gather_blocks  # noqa: E402
 
 
+def config_for(n: int, world: int) -> dict:
+    """The `config` object of the JSON line -- identical in the b200 arm and in --impl reference."""
+    return {"workload": f"LCS triangle, {n} x {LEN} aa synthetic family (seed {SEED})",
+            "n_seqs": n, "len": LEN, "pairs_per_step": tri(n),
+            "out": "uint16 packed lower triangle", "l2": "flushed between timed iterations (192 MiB write)",
+            "multi_gpu": "row shards with equal pairs + one NCCL all-gather of row blocks" if world > 1 else "none"}
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -130,19 +138,48 @@ def dp_workload(rank: int):
     return rows, jobs
 
 
-def dp_cpu_reference(rows, threads):
+def dp_cpu_reference(rows, threads, min_seconds=2.0):
     """The reference's CProfile::Align (+ ConstructProfile, inseparable without patching it) over the same
-    aligned blocks, one merge per task on `threads` host threads (ComputeAlignment's shape, msa.cpp:375-426)."""
+    aligned blocks, one merge per task on `threads` host threads (ComputeAlignment's shape, msa.cpp:375-426).
+    The batch is repeated (profiles rebuilt outside the timed calls) until at least min_seconds have been timed."""
     from famsa_b200 import seqio
     from oracle import pyoracle
     dp = pyoracle.RefDp(0)
     dp.set_gaps(DP_GAPS)
     to_str = lambda r: ["".join("-" if c < 0 else seqio.ALPHABET[c] for c in row) + "A" for row in r]
-    p1 = [dp.profile(to_str(a), list(range(len(a)))) for a, _ in rows]
-    p2 = [dp.profile(to_str(b), list(range(1000, 1000 + len(b)))) for _, b in rows]
-    sec, cells = dp.align_pairs_mt(p1, p2, threads)
+    sec = 0.0
+    cells = 0
+    while sec < min_seconds:
+        p1 = [dp.profile(to_str(a), list(range(len(a)))) for a, _ in rows]
+        p2 = [dp.profile(to_str(b), list(range(1000, 1000 + len(b)))) for _, b in rows]
+        s1, c1 = dp.align_pairs_mt(p1, p2, threads)
+        sec += s1
+        cells += c1
     dp.close()
     return sec, cells
+
+
+def dp_verify_batch(rows, jobs, res, path, n_paths=24):
+    """Untimed: the bench's own DP batch against the reference -- total score of every merge, the whole traceback
+    path of the first n_paths merges (reference rows -> path)."""
+    from famsa_b200 import seqio
+    from oracle import pyoracle
+    dp = pyoracle.RefDp(0)
+    dp.set_gaps(DP_GAPS)
+    to_str = lambda r: ["".join("-" if c < 0 else seqio.ALPHABET[c] for c in row) + "A" for row in r]
+    ok_tot = ok_path = 0
+    for k, (a, b) in enumerate(rows):
+        na, nb = list(range(len(a))), list(range(1000, 1000 + len(b)))
+        m, total = dp.align(dp.profile(to_str(a), na), dp.profile(to_str(b), nb), 1)
+        r = res[k]
+        ok_tot += int(total == int(r.total_score))
+        if k < n_paths:
+            want = pyoracle.path_from_rows(dp.rows(m), set(na), set(nb), bool(r.swapped))
+            got = path[r.path_offset:r.path_offset + r.path_len]
+            ok_path += int(len(want) == len(got) and np.array_equal(want, got))
+        dp.free(m)
+    dp.close()
+    return {"totals_equal": ok_tot, "of": len(rows), "paths_equal": ok_path, "paths_checked": min(n_paths, len(rows))}
 
 
 def bench_dp(eng, torch, dist, world, rank, steps, warmup, l2_flush, stream, want_cpu):
@@ -260,19 +297,116 @@ def bench_dp(eng, torch, dist, world, rank, steps, warmup, l2_flush, stream, wan
                                         "level), merged tables built on the device, only results + paths return"},
                "gpu_launches": int(launches),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": dp_traffic, "peak_source": peak_src, "kernel": "fb::k_dp_prep + k_dp_t + k_dp_fill<8,1>",
-                            "kernel_ms": kern_ms,
-                            "note": "achieved = SURVEY 8d algorithmic bytes / time of the three kernels; traffic = DRAM bytes of "
-                                    "k_dp_fill alone (it reads the 8 B/cell T that k_dp_t wrote); the int64 recurrence is bound "
-                                    "by issue slots and the staircase's idle slots, not by HBM: see DESIGN.md section 4"}}
+                            "traffic": dp_traffic, "peak_source": peak_src, "kernel": "fb::k_dp_prep + k_dp_fill<NW,CL> + k_dp_trace",
+                            "kernel_ms": kern_ms, "algorithmic_bytes": alg,
+                            "note": "achieved = SURVEY 8d algorithmic bytes / time of the DP kernels of one batch; traffic = DRAM "
+                                    "bytes of the same kernels from ncu (profiles/dp_fill_traffic.json): the column-pair scores T "
+                                    "are built in shared memory (IMMA) and never reach HBM; the int64 recurrence is bound by "
+                                    "dependent-issue latency, not by HBM: see DESIGN.md section 4"}}
+        out["verified_vs_reference"] = None
         if want_cpu:
             from oracle import pyoracle
             if pyoracle.have_ref():
                 threads = usable_cpus()
                 sec, c = dp_cpu_reference(rows, threads)
                 out["cpu_baseline"] = {"value": c / sec, "unit": "cells/s", "cores": threads, "kind": "reference",
-                                       "sample": f"the same {n} merges, CProfile::Align incl. ConstructProfile, one merge per thread task ({sec:.2f} s)"}
+                                       "sample": f"the same {n} merges repeated for {sec:.2f} s, CProfile::Align incl. ConstructProfile, one merge per thread task"}
+                out["verified_vs_reference"] = dp_verify_batch(rows, jobs, hres, hpath)
     return out
+
+
+# ---------------------------------------------------------------------------------------------- whole-tree DP leg
+TREE_SYNTH = (2000, 400, 17, 1)          # sequences, length, family seed, tree seed
+
+
+def tree_workloads():
+    """BASELINE config 4 (test/hemopexin, every merge of the golden medoid-sl tree and of the default -gt sl tree; the
+    fixtures carry the reference's per-merge totals and path checksums) and a synthetic 2000 x 400 aa family under a
+    random guide tree.  Returns [(name, sequences, merges (n-1, 2), gaps, fixture or None)]."""
+    from famsa_b200 import seqio
+    G = os.path.join(ROOT, "tests", "golden")
+    out = []
+    for f in ("hemopexin_medoid_sl", "hemopexin_sl"):
+        z = np.load(os.path.join(G, f + ".npz"))
+        out.append((f, [str(x) for x in z["seqs"]], np.asarray(z["merges"], dtype=np.int32), np.asarray(z["gaps"], dtype=np.int64), z))
+    n, L, seed, tseed = TREE_SYNTH
+    codes, off, lens = seqio.synth_family(n, L, seed, sort_desc=False)
+    seqs = [seqio.decode(codes[int(o):int(o) + int(l)]) for o, l in zip(off, lens)]
+    rng = np.random.default_rng(tseed)
+    alive, merges = list(range(n)), []
+    while len(alive) > 1:                # random binary merge order, 5 % chain-like steps (tests/dp_cases.random_tree)
+        if rng.random() < 0.05 and merges:
+            a = alive.pop(); b = alive.pop(int(rng.integers(len(alive))))
+        else:
+            a = alive.pop(int(rng.integers(len(alive)))); b = alive.pop(int(rng.integers(len(alive))))
+        merges.append((a, b)); alive.append(n + len(merges) - 1)
+    out.append((f"synthetic {n} x {L} aa family, random guide tree", seqs, np.asarray(merges, dtype=np.int32), out[0][3], None))
+    return out
+
+
+def bench_dp_tree(eng, torch, dist, world, rank, steps, want_cpu):
+    """Whole progressive alignments through famsa_prof_align_tree (one call per tree: every merge of the guide tree,
+    profiles resident in HBM, per-merge records + paths back on the host), timed by the host clock around the call
+    plus the path fetch.  Next to it the reference's own ComputeAlignment loop (CProfileQueue + worker threads) on all
+    host cores, repeated for >= 2 s."""
+    import zlib
+    from famsa_b200 import seqio
+    sm = np.load(os.path.join(ROOT, "tests", "golden", "adeno_upgma_merges.npz"))["score_matrix"]
+    legs = []
+    for name, seqs, merges, gaps, fx in tree_workloads():
+        codes, off, lens = seqio.pack([seqio.encode(x) for x in seqs])
+        eng.upload(codes, off, lens)
+        eng.prof_set_scoring(sm)
+        root, res, st = eng.align_tree(merges, gaps)          # warm-up + the run that is verified
+        eng.prof_drop([root])
+        check = None
+        if fx is not None:
+            check = bool([r["total"] for r in res] == [int(t) for t in fx["totals"]]
+                         and [zlib.crc32(r["path"].tobytes()) for r in res] == [int(c) for c in fx["path_crc"]])
+        l0 = eng.kernel_launches()
+        walls, devs = [], []
+        for _ in range(steps):
+            if world > 1:
+                dist.barrier()
+            t0 = time.time()
+            root, _, st = eng.align_tree(merges, gaps)        # includes famsa_prof_tree_paths
+            walls.append(time.time() - t0)
+            devs.append(st["device_ms"])
+            eng.prof_drop([root])
+        launches = eng.kernel_launches() - l0
+        wall = sorted(walls)[len(walls) // 2]
+        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+        leg = {"tree": name, "n_seqs": len(seqs), "merges": int(len(merges)), "cells": int(st["cells"]), "final_width": int(len(res[-1]["path"])),
+               "wall_ms": 1e3 * wall, "device_ms": sorted(devs)[len(devs) // 2], "cells_per_s": st["cells"] * world / wall,
+               "batches": int(st["n_batches"]), "max_batches_in_flight": int(st["max_in_flight"]),
+               "gpu_launches_per_tree": int(launches // max(1, steps)),
+               "identical_to_reference_fixture": check}
+        if want_cpu and rank == 0:
+            from oracle import pyoracle
+            if pyoracle.have_ref():
+                threads = usable_cpus()
+                dp = pyoracle.RefDp(len(seqs))
+                dp.set_gaps(gaps)
+                sec, reps, rows, total = 0.0, 0, None, None
+                while sec < 2.0:
+                    out = dp.align_tree_mt(seqs, merges, threads, want_rows=(reps == 0))
+                    sec += out[0]; reps += 1
+                    if len(out) > 4:
+                        rows, total = out[4], out[2]
+                dp.close()
+                leg["cpu_reference"] = {"wall_ms": 1e3 * sec / reps, "cores": threads, "repeats": reps,
+                                        "what": "the reference's ComputeAlignment loop (CProfileQueue + workers, msa.cpp:360-438) on the same tree"}
+                leg["speedup_vs_reference"] = (sec / reps) / wall
+                # untimed: the alignment assembled from the GPU's paths is the reference's alignment, row for row
+                sys.path.insert(0, os.path.join(ROOT, "tests"))
+                from dp_cases import assemble_rows
+                mine = assemble_rows(seqs, [tuple(int(x) for x in m) for m in merges], res)
+                leg["alignment_identical_to_reference"] = bool(mine == rows and res[-1]["total"] == total)
+        legs.append(leg)
+    return legs
 
 
 def usable_cpus() -> int:
@@ -311,8 +445,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic", "config": {"workload": f"LCS triangle, {n} x {LEN} aa synthetic family (seed {SEED})",
-                                           "n_seqs": n, "len": LEN},
+            "data": "synthetic", "config": config_for(n, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
                              "sample": sample + "; CLCSBP AVX2 via calculateDistanceVector, one row per task"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -466,10 +599,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"LCS triangle, {n} x {LEN} aa synthetic family (seed {SEED})",
-                       "n_seqs": n, "len": LEN, "pairs_per_step": total_pairs, "rows_per_rank": [rb, re],
-                       "out": "uint16 packed lower triangle", "l2": "flushed between timed iterations (192 MiB write)",
-                       "multi_gpu": "row shards with equal pairs + one NCCL all-gather of row blocks" if world > 1 else "none"},
+            "config": config_for(n, world), "rows_of_rank0": [rb, re],
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps},
@@ -502,8 +632,10 @@ def main():
                                         "sample": f"last {n_s} rows ({pairs} pairs)"}
     dp = bench_dp(eng, torch, dist, world, rank, max(2, args.steps // 2), args.warmup, l2_flush, stream,
                   want_cpu=(world == 1 and not args.no_cpu_baseline))
+    dp_tree = bench_dp_tree(eng, torch, dist, world, rank, max(3, args.steps), want_cpu=(world == 1 and not args.no_cpu_baseline))
     if rank == 0:
         line["dp"] = dp
+        line["dp_tree"] = dp_tree
         line["gpu_launches"] = int(launches) + (dp["gpu_launches"] if dp else 0)
         if world == 1:
             # informational: the default guide tree (-gt sl) end to end on the same set -- famsa_lcs_prim =

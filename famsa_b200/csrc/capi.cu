@@ -68,6 +68,9 @@ int famsa_create(int device, famsa_ctx** out_ctx)
         FB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         for (auto& ev : ctx->ev) FB_CUDA(cudaEventCreate(&ev));
         FB_CUDA(cudaEventCreateWithFlags(&ctx->ev_busy, cudaEventDisableTiming));
+        FB_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        for (auto& e : ctx->ev_join) FB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& a : ctx->aux_stream) FB_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
         // per-call scratch and resident profiles are stream-ordered allocations: the pool keeps what it has
         cudaMemPool_t pool;
         FB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -104,6 +107,11 @@ void famsa_destroy(famsa_ctx* ctx)
     for (auto& ev : ctx->ev_host)
         if (ev) cudaEventDestroy(ev);
     if (ctx->ev_busy) cudaEventDestroy(ctx->ev_busy);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (auto& e : ctx->ev_join)
+        if (e) cudaEventDestroy(e);
+    for (auto& a : ctx->aux_stream)
+        if (a) cudaStreamDestroy(a);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -126,6 +126,9 @@ struct famsa_ctx {
     // (on whatever stream) waits for it before it touches the scratch again.
     cudaEvent_t ev_busy = nullptr;
     bool busy = false;
+    // fill launches of different shapes (cluster sizes) of one batch run side by side on these
+    cudaStream_t aux_stream[4] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[4] = {};
     std::mutex mu;
     uint64_t launches = 0;
     int sm_count = 0;

@@ -28,6 +28,7 @@
 //   k_dp_unskew only when the caller asks for CDPMatrix bytes: skewed directions -> row-major.
 #include <algorithm>
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
@@ -550,10 +551,10 @@ __device__ __forceinline__ void dp_step(WarpShared& W, const RowConst& R, const 
 // ahead (the loads fly during the 8 steps of the current chunk), looks at the tags afterwards and simply reloads until
 // all of them are the ones it expects.  Its lane 0 needs column 8c+7 of the stripe above, which that stripe's lane 31
 // computes at wavefront step 8c+38: the natural lag between consecutive stripes is about six chunks, self-regulating.
-template <int VAR, bool T32, int NW, int CL>
+template <int VAR, bool T32>
 __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, const long long* __restrict__ col, uint32_t cstride,
                                            unsigned long long* __restrict__ browg,
-                                           unsigned char* __restrict__ dirs, uint32_t team_warp,
+                                           unsigned char* __restrict__ dirs, uint32_t team_warp, uint32_t TW,
                                            long long* last_out, WarpShared& W)
 {
     const uint32_t lane = threadIdx.x & 31;
@@ -562,10 +563,9 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
     const uint32_t n_stripes = (WR + 31) / 32;
     const uint32_t steps = WC + 1 + 31;                              // wavefront steps per stripe
     const uint32_t S = (steps + kChunk - 1) / kChunk;                // macro steps per stripe
-    constexpr uint32_t TW = (uint32_t)NW * CL;                       // warps in the team (CL > 1: a thread-block cluster)
     int* const tring32 = reinterpret_cast<int*>(W.t);
 
-    for (uint32_t k = team_warp; k < n_stripes; k += TW) {
+    for (uint32_t k = team_warp; k < n_stripes; k += TW) {                // TW = warps in the team
         // ---- row-side constants into registers
         const uint32_t i = k * 32 + 1 + lane;
         RowConst R;
@@ -758,19 +758,27 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
     }
 }
 
-// NW == 1: four independent merges per 128-thread block (one warp each).  NW > 1: one merge per block.  CL > 1: one
-// merge per thread-block CLUSTER of CL blocks (the very wide merges near the root of the guide tree, where the
-// reference switches to its multi-threaded ParAlign* variants): the stripes then spread over NW*CL warps on CL SMs;
-// the boundary row travels through L2 either way.  There is no barrier anywhere: a warp leaves when its stripes are
-// done, the owner of cell (WR, WC) leaves (D, H, V) in the job's scratch for k_dp_trace.
-template <int NW, int CL>
+// NW == 1: four independent merges per 128-thread block (one warp each).  NW > 1: one merge per block.  CLUSTERED: one
+// merge per thread-block CLUSTER (2 .. 16 blocks, chosen per launch): consecutive stripes go to different blocks (stripe
+// k -> block k % CL, warp (k / CL) % NW), so that a merge with few stripes has one stripe per SM sub-partition -- two
+// active stripes on one sub-partition share its ALU pipe (one warp instruction per two cycles) and both run at half
+// speed, which is the wrong trade when a single merge is all there is to do (the top of the guide tree, where the
+// reference switches to its multi-threaded ParAlign* variants).  The boundary row travels through L2 either way.  There
+// is no barrier anywhere: a warp leaves when its stripes are done, the owner of cell (WR, WC) leaves (D, H, V) in the
+// job's scratch for k_dp_trace.
+template <int NW, bool CLUSTERED>
 __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32, 1) k_dp_fill(const DpParams P)
 {
     extern __shared__ __align__(16) unsigned char sm_dyn[];
     const uint32_t warp = threadIdx.x / 32;
     WarpShared& W = reinterpret_cast<WarpShared*>(sm_dyn)[warp];
-    const uint32_t cta_rank = CL > 1 ? cooperative_groups::this_cluster().block_rank() : 0;
-    const uint32_t team_warp = NW == 1 ? 0 : cta_rank * NW + warp;
+    uint32_t CL = 1, cta_rank = 0;
+    if (CLUSTERED) {
+        CL = cooperative_groups::this_cluster().num_blocks();
+        cta_rank = cooperative_groups::this_cluster().block_rank();
+    }
+    const uint32_t team_warp = NW == 1 ? 0 : warp * CL + cta_rank;
+    const uint32_t TW = NW == 1 ? 1 : (uint32_t)NW * CL;
     const uint32_t slot = NW == 1 ? blockIdx.x * kDpWarps + warp : blockIdx.x / CL;
     if (slot >= P.n_jobs) return;                                    // whole warp (NW == 1) / whole team otherwise
     const uint32_t jid = P.order[slot];
@@ -785,7 +793,7 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32, 1) k_dp_fill(c
     unsigned long long* browg = reinterpret_cast<unsigned long long*>(scratch + L.brow);
     long long* g_last = reinterpret_cast<long long*>(scratch + L.lastv);
     unsigned char* dirs = P.sdirs + J.t_off;
-#define FB_STRIPES(V, T) dp_stripes<V, T, NW, CL>(P, M, col, cstride, browg, dirs, team_warp, g_last, W)
+#define FB_STRIPES(V, T) dp_stripes<V, T>(P, M, col, cstride, browg, dirs, team_warp, TW, g_last, W)
     if (M.var == 0) { if (M.t32) FB_STRIPES(0, true); else FB_STRIPES(0, false); }
     else if (M.var == 1) { if (M.t32) FB_STRIPES(1, true); else FB_STRIPES(1, false); }
     else { if (M.t32) FB_STRIPES(2, true); else FB_STRIPES(2, false); }
@@ -849,28 +857,39 @@ __global__ void __launch_bounds__(kTraceWarps * 32) k_dp_trace(const DpParams P)
         }
         __syncwarp();
         if (lane == 0) {
-            // The cell visited next depends only on the current state, the state after that on the byte of the current
-            // cell: so the next cell's byte is requested before the current one is decoded, and the shared-memory
-            // latency overlaps two steps of the walk.
-            auto byte_at = [&](uint32_t i, uint32_t j) -> unsigned {
-                if (!i) return 0x15;                                 // row 0: all-H (CDPMatrix::set_dir_all)
-                const uint32_t l = (i - 1) & 31;
-                return tile[(j + l - j0) * 32 + l];
-            };
-            uint32_t ii = ti, jj = tj;
-            unsigned b = byte_at(ii, jj);
-            for (;;) {
-                tmp_path[n++] = (unsigned char)dir;
-                if (dir == 0 && (ii == 0 || jj == 0)) { ii = jj = 0; break; }      // cannot happen for a valid matrix
-                const uint32_t ni = ii - (dir != 1), nj = jj - (dir != 2);
-                if ((dir == 1 && jj == 0) || (dir == 2 && ii == 0)) { ii = jj = 0; break; }   // idem
-                const bool inside = (ni || nj) && ni >= row_lo && nj >= j0;
-                const unsigned nb = inside ? byte_at(ni, nj) : 0;
-                dir = (int)((b >> (2 * dir)) & 3);
-                ii = ni; jj = nj; b = nb;
-                if (!inside) break;
+            if (!ti) {
+                // row 0 (CDPMatrix::set_dir_all: every byte of row 0 is all-H)
+                uint32_t jj = tj;
+                while (jj && jj >= j0) {
+                    tmp_path[n++] = (unsigned char)dir;
+                    if (dir != 1) { jj = 0; break; }                 // cannot happen for a valid matrix
+                    dir = (0x15 >> (2 * dir)) & 3;
+                    --jj;
+                }
+                tj = jj;
+            } else {
+                // In the skewed tile cell (i, j) sits at idx = (j - j0 + l) * 32 + l, l = (i - 1) & 31, so the three moves are
+                // constant index steps: D -65, H -32, V -33.  The cell visited next depends only on the current state and
+                // the state after that on the current cell's byte, so the next byte is requested before the current one
+                // is decoded.
+                int l = (int)l_top, cj = (int)(tj - j0);
+                int idx = (cj + l) * 32 + l;
+                unsigned b = tile[idx];
+                unsigned char* out = tmp_path + n;
+                for (;;) {
+                    *out++ = (unsigned char)dir;
+                    const int di = dir != 1, dj = dir != 2;
+                    l -= di; cj -= dj; idx -= 32 * dj + 33 * di;
+                    const bool inside = (l | cj) >= 0;
+                    const unsigned nb = inside ? tile[idx] : 0;
+                    dir = (int)((b >> (2 * dir)) & 3);
+                    b = nb;
+                    if (!inside) break;
+                }
+                n = (uint32_t)(out - tmp_path);
+                ti = l < 0 ? row_lo - 1 : row_lo + (uint32_t)l;
+                tj = cj < 0 ? (j0 ? j0 - 1 : 0) : j0 + (uint32_t)cj;
             }
-            ti = ii; tj = jj;
         }
         ti = __shfl_sync(0xffffffffu, ti, 0);
         tj = __shfl_sync(0xffffffffu, tj, 0);
@@ -903,17 +922,61 @@ __global__ void __launch_bounds__(kTraceWarps * 32) k_dp_trace(const DpParams P)
         if (rc__ != FAMSA_OK) return rc__; \
     } while (0)
 
-template <int NW, int CL>
+template <int NW, bool CLUSTERED>
 static int configure_fill(famsa_ctx* ctx)
 {
     static std::atomic<bool> configured[64];
     constexpr int warps = NW == 1 ? kDpWarps : NW;
     if (!configured[ctx->device & 63].load(std::memory_order_acquire)) {
-        FB_CUDA(cudaFuncSetAttribute(k_dp_fill<NW, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(warps * sizeof(WarpShared))));
-        if (CL > 1) FB_CUDA(cudaFuncSetAttribute(k_dp_fill<NW, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
+        FB_CUDA(cudaFuncSetAttribute(k_dp_fill<NW, CLUSTERED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(warps * sizeof(WarpShared))));
+        if (CLUSTERED) FB_CUDA(cudaFuncSetAttribute(k_dp_fill<NW, CLUSTERED>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         configured[ctx->device & 63].store(true, std::memory_order_release);
     }
     return FAMSA_OK;
+}
+
+template <int NW>
+static int launch_cluster_fill(famsa_ctx* ctx, const DpParams& Q, uint32_t cl, cudaStream_t st)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(Q.n_jobs * cl);
+    cfg.blockDim = dim3(NW * 32);
+    cfg.dynamicSmemBytes = NW * sizeof(WarpShared);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FB_CUDA(cudaLaunchKernelEx(&cfg, k_dp_fill<NW, true>, Q));
+    ctx->launches++;
+    return FAMSA_OK;
+}
+
+// largest cluster size (<= 16) the 4-warp fill kernel can be launched with on this device
+static uint32_t max_cluster4(famsa_ctx* ctx)
+{
+    static std::atomic<int> cached[64];
+    int v = cached[ctx->device & 63].load(std::memory_order_acquire);
+    if (v) return (uint32_t)v;
+    v = 8;
+    for (int cl : {16}) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cl);
+        cfg.blockDim = dim3(4 * 32);
+        cfg.dynamicSmemBytes = 4 * sizeof(WarpShared);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, k_dp_fill<4, true>, &cfg) == cudaSuccess && n > 0) v = cl;
+        else cudaGetLastError();
+    }
+    cached[ctx->device & 63].store(v, std::memory_order_release);
+    return (uint32_t)v;
 }
 
 // Bytes of stream-ordered scratch one call of dp_run_device needs at most (it sub-batches above ~1 Gi cells).
@@ -955,11 +1018,12 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext,
     if (const char* e = getenv("FAMSA_DP_TEAM_WARPS")) nw_forced = atoi(e);                      // development knob
     uint32_t cluster_min = kDpClusterMinWidth;
     if (const char* e = getenv("FAMSA_DP_CLUSTER_MIN")) cluster_min = (uint32_t)atoi(e);         // development knob
-    FB_TRY((configure_fill<1, 1>(ctx)));
-    FB_TRY((configure_fill<2, 1>(ctx)));
-    FB_TRY((configure_fill<4, 1>(ctx)));
-    FB_TRY((configure_fill<kDpTeamWarps, 1>(ctx)));
-    FB_TRY((configure_fill<kDpTeamWarps, kDpCluster>(ctx)));
+    FB_TRY((configure_fill<1, false>(ctx)));
+    FB_TRY((configure_fill<2, false>(ctx)));
+    FB_TRY((configure_fill<4, false>(ctx)));
+    FB_TRY((configure_fill<kDpTeamWarps, false>(ctx)));
+    FB_TRY((configure_fill<4, true>(ctx)));
+    FB_TRY((configure_fill<kDpTeamWarps, true>(ctx)));
 
     // plan the sub-batches first: one stream-ordered allocation serves all of them
     struct Sub { uint32_t j0, j1; unsigned long long scratch, skew; std::vector<unsigned long long> tblock; };
@@ -1014,28 +1078,41 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext,
     if (n) FB_CUDA(cudaMemcpyAsync(d_jobs, dev.data(), sizeof(DpJobDev) * n, cudaMemcpyHostToDevice, st));
     for (const Sub& sb : subs) {
         const uint32_t j0 = sb.j0, j1 = sb.j1, m = j1 - j0;
-        // merges whose shorter side spans several 32-row stripes get a whole block (a team of warps pipelined over
-        // the stripes); the rest run one warp per merge.  Both groups cost-descending.
-        // class 2: shorter side > cluster_min -> a cluster of blocks; class 1: > team_min -> one block; class 0: one warp
-        // When a level holds only a handful of block-sized merges (the top of the guide tree) the GPU would sit idle:
-        // give every merge with more than 8 stripes a cluster then.
         // rows of the DP matrix as far as the host can tell (the orientation of ProfProf merges is decided on the device)
         auto stripes_of = [&](uint32_t a) {
             const DpJobDev& d = dev[a];
             const uint32_t rows = d.card1 == 1 ? d.w1 : (d.card2 == 1 ? d.w2 : std::min(d.w1, d.w2));
             return (rows + 31) / 32;
         };
+        // Two regimes.  A batch large enough to fill the device with one warp per stripe-pipeline is THROUGHPUT-bound:
+        // wide merges get a block (2, 4 or 8 warps by how many there are), the very widest a cluster of 8 x 8 warps, the
+        // rest run one warp per merge.  A small batch (the chain-like parts and the top of a guide tree, where a level is
+        // one or a few merges) is LATENCY-bound: every merge with more than one stripe gets a cluster of 4-warp blocks,
+        // one stripe per SM sub-partition, as many blocks as its stripes can use (up to 16).
+        uint32_t cl_cap = max_cluster4(ctx);
+        if (const char* e = getenv("FAMSA_DP_MAX_CLUSTER")) cl_cap = std::max(1u, std::min(cl_cap, (uint32_t)atoi(e)));   // development knob
+        // latency mode while the batch's stripes fit one per SM sub-partition
+        unsigned long long demand = 0;
         uint32_t n_teamable = 0;
-        for (uint32_t a = j0; a < j1; ++a) n_teamable += std::min(dev[a].w1, dev[a].w2) > team_min;
+        for (uint32_t a = j0; a < j1; ++a) {
+            demand += std::min(stripes_of(a), 4u * cl_cap);
+            n_teamable += std::min(dev[a].w1, dev[a].w2) > team_min;
+        }
+        bool small_batch = demand <= 4ull * (unsigned long long)ctx->sm_count;
+        if (const char* e = getenv("FAMSA_DP_LATENCY_MODE")) small_batch = atoi(e) != 0;                 // development knob
+        // throughput mode with only a handful of block-sized merges: give every merge with more than 8 stripes a cluster
         uint32_t cl_min = cluster_min;
         if (n_teamable * kDpCluster <= 2u * (uint32_t)ctx->sm_count) cl_min = std::min(cluster_min, std::max(team_min, 256u));
-        // A batch too small to fill the device with one warp per merge (the chain-like part of a guide tree, where a
-        // level is one or a few merges) is latency-bound: every merge with more than one stripe gets a team then.
-        const bool small_batch = m <= 2u * (uint32_t)ctx->sm_count;
-        auto cls = [&](uint32_t a) {
+        auto cluster_of = [&](uint32_t a) {                       // latency mode: blocks (of 4 warps) for merge a
+            const uint32_t want = (stripes_of(a) + 3) / 4;
+            uint32_t cl = 1;
+            while (cl < want && cl < cl_cap) cl *= 2;
+            return cl;
+        };
+        auto cls = [&](uint32_t a) -> int {                       // sort key: larger = launched first
             const uint32_t w = std::min(dev[a].w1, dev[a].w2);
+            if (small_batch) return stripes_of(a) >= 2 ? 10 + (int)cluster_of(a) : 0;
             if (w > cl_min) return 2;
-            if (small_batch) return stripes_of(a) >= 2 ? 1 : 0;
             return w > team_min ? 1 : 0;
         };
         std::vector<uint32_t> order(m);
@@ -1044,10 +1121,6 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext,
             if (cls(a) != cls(b)) return cls(a) > cls(b);
             return (unsigned long long)dev[a].w1 * dev[a].w2 > (unsigned long long)dev[b].w1 * dev[b].w2;
         });
-        uint32_t n_huge = 0, n_big = 0;
-        while (n_huge < m && cls(order[n_huge]) == 2) ++n_huge;
-        n_big = n_huge;
-        while (n_big < m && cls(order[n_big]) == 1) ++n_big;
 
         // one packed upload: order + tblock
         std::vector<unsigned char> pack(o_scratch - o_order);
@@ -1070,57 +1143,67 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext,
         k_dp_prep<<<m, kPrepThreads, 0, st>>>(P);
         FB_CUDA(cudaGetLastError());
         ctx->launches += 1;
-        // `order`: cluster jobs, then block jobs, then warp jobs (see the sort above)
-        if (n_huge) {
+        // one launch per run of equal class in `order`; different classes run side by side (fork after prep, join before
+        // the traceback) so that a level pays for its slowest merge once, not once per launch shape
+        static const bool debug = getenv("FAMSA_DP_DEBUG") != nullptr;
+        uint32_t n_classes = 0;
+        for (uint32_t q0 = 0; q0 < m;) { const int c = cls(order[q0]); while (q0 < m && cls(order[q0]) == c) ++q0; ++n_classes; }
+        if (n_classes > 1) FB_CUDA(cudaEventRecord(ctx->ev_fork, st));
+        uint32_t class_no = 0, aux_used = 0;
+        cudaStream_t main_st = st;
+        for (uint32_t q0 = 0; q0 < m;) {
+            const int c = cls(order[q0]);
+            uint32_t q1 = q0;
+            while (q1 < m && cls(order[q1]) == c) ++q1;
+            if (debug) fprintf(stderr, "[dp] batch of %u: class %d x %u (first %u x %u, %u stripes), demand %llu, cl_cap %u, latency_mode %d\n", m, c, q1 - q0,
+                               dev[order[q0]].w1, dev[order[q0]].w2, stripes_of(order[q0]), demand, cl_cap, (int)small_batch);
             DpParams Q = P;
-            Q.n_jobs = n_huge;
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(n_huge * kDpCluster);
-            cfg.blockDim = dim3(kDpTeamWarps * 32);
-            cfg.dynamicSmemBytes = kDpTeamWarps * sizeof(WarpShared);
-            cfg.stream = st;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = kDpCluster;
-            attr[0].val.clusterDim.y = 1;
-            attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr;
-            cfg.numAttrs = 1;
-            FB_CUDA(cudaLaunchKernelEx(&cfg, k_dp_fill<kDpTeamWarps, kDpCluster>, Q));
-            ctx->launches++;
-        }
-        if (n_big > n_huge) {
-            DpParams Q = P;
-            Q.order = P.order + n_huge;
-            Q.n_jobs = n_big - n_huge;
-            // Team size by how many merges there are: every SM holds 8 fill warps (shared memory), so a level with many
-            // block-class merges runs them with smaller teams -- 4 warps from 2 merges per SM on, 2 from 4 -- which lose
-            // less to the ramp-up / ramp-down of the stripe pipeline.
-            int nw = kDpTeamWarps;
-            if (Q.n_jobs >= 4u * (uint32_t)ctx->sm_count) nw = 2;
-            else if (Q.n_jobs >= 2u * (uint32_t)ctx->sm_count) nw = 4;
-            else {                                                // no more warps than the deepest merge has stripes
-                uint32_t smax = 1;
-                for (uint32_t q = n_huge; q < n_big; ++q) smax = std::max(smax, stripes_of(order[q]));
-                nw = smax <= 2 ? 2 : (smax <= 4 ? 4 : kDpTeamWarps);
+            Q.order = P.order + q0;
+            Q.n_jobs = q1 - q0;
+            // class 0 (first in launch order is the heaviest) stays on the main stream, the others go to the aux streams
+            cudaStream_t st = main_st;
+            if (class_no > 0) {
+                const uint32_t a = (class_no - 1) % 4;
+                st = ctx->aux_stream[a];
+                if (!(aux_used >> a & 1)) { FB_CUDA(cudaStreamWaitEvent(st, ctx->ev_fork, 0)); aux_used |= 1u << a; }
             }
-            if (nw_forced) nw = nw_forced;
-            switch (nw) {
-            case 2: k_dp_fill<2, 1><<<Q.n_jobs, 2 * 32, 2 * sizeof(WarpShared), st>>>(Q); break;
-            case 4: k_dp_fill<4, 1><<<Q.n_jobs, 4 * 32, 4 * sizeof(WarpShared), st>>>(Q); break;
-            default: k_dp_fill<kDpTeamWarps, 1><<<Q.n_jobs, kDpTeamWarps * 32, kDpTeamWarps * sizeof(WarpShared), st>>>(Q); break;
+            ++class_no;
+            if (c == 0) {
+                k_dp_fill<1, false><<<(Q.n_jobs + kDpWarps - 1) / kDpWarps, kDpWarps * 32, kDpWarps * sizeof(WarpShared), st>>>(Q);
+                FB_CUDA(cudaGetLastError());
+                ctx->launches++;
+            } else if (c >= 10) {
+                const uint32_t cl = (uint32_t)c - 10;
+                if (cl == 1) {
+                    k_dp_fill<4, false><<<Q.n_jobs, 4 * 32, 4 * sizeof(WarpShared), st>>>(Q);
+                    FB_CUDA(cudaGetLastError());
+                    ctx->launches++;
+                } else FB_TRY(launch_cluster_fill<4>(ctx, Q, cl, st));
+            } else if (c == 2) {
+                FB_TRY(launch_cluster_fill<kDpTeamWarps>(ctx, Q, kDpCluster, st));
+            } else {
+                // Team size by how many merges there are: every SM holds 8 fill warps (shared memory), so a level with many
+                // block-class merges runs them with smaller teams -- 4 warps from 2 merges per SM on, 2 from 4 -- which lose
+                // less to the ramp-up / ramp-down of the stripe pipeline.
+                int nw = kDpTeamWarps;
+                if (Q.n_jobs >= 4u * (uint32_t)ctx->sm_count) nw = 2;
+                else if (Q.n_jobs >= 2u * (uint32_t)ctx->sm_count) nw = 4;
+                if (nw_forced) nw = nw_forced;
+                switch (nw) {
+                case 2: k_dp_fill<2, false><<<Q.n_jobs, 2 * 32, 2 * sizeof(WarpShared), st>>>(Q); break;
+                case 4: k_dp_fill<4, false><<<Q.n_jobs, 4 * 32, 4 * sizeof(WarpShared), st>>>(Q); break;
+                default: k_dp_fill<kDpTeamWarps, false><<<Q.n_jobs, kDpTeamWarps * 32, kDpTeamWarps * sizeof(WarpShared), st>>>(Q); break;
+                }
+                FB_CUDA(cudaGetLastError());
+                ctx->launches++;
             }
-            FB_CUDA(cudaGetLastError());
-            ctx->launches++;
+            q0 = q1;
         }
-        if (m > n_big) {
-            DpParams Q = P;
-            Q.order = P.order + n_big;
-            Q.n_jobs = m - n_big;
-            k_dp_fill<1, 1><<<(Q.n_jobs + kDpWarps - 1) / kDpWarps, kDpWarps * 32, kDpWarps * sizeof(WarpShared), st>>>(Q);
-            FB_CUDA(cudaGetLastError());
-            ctx->launches++;
-        }
+        for (uint32_t a = 0; a < 4; ++a)
+            if (aux_used >> a & 1) {
+                FB_CUDA(cudaEventRecord(ctx->ev_join[a], ctx->aux_stream[a]));
+                FB_CUDA(cudaStreamWaitEvent(main_st, ctx->ev_join[a], 0));
+            }
         k_dp_trace<<<(m + kTraceWarps - 1) / kTraceWarps, kTraceWarps * 32, 0, st>>>(P);
         FB_CUDA(cudaGetLastError());
         ctx->launches++;

@@ -7,9 +7,18 @@ import famsa_b200
 from famsa_b200 import seqio
 G = os.path.join(ROOT, "tests", "golden")
 sm = np.load(os.path.join(G, "adeno_upgma_merges.npz"))["score_matrix"]
-z = np.load(os.path.join(G, (sys.argv[1] if len(sys.argv) > 1 else "hemopexin_sl") + ".npz"))
+name = sys.argv[1] if len(sys.argv) > 1 else "hemopexin_sl"
 eng = famsa_b200.Engine(0)
-codes, off, lens = seqio.pack([seqio.encode(str(s)) for s in z["seqs"]])
+if name.startswith("synthetic"):                       # synthetic:N:L[:caterpillar]
+    from dp_cases import random_tree
+    parts = name.split(":")
+    n, L = int(parts[1]), int(parts[2])
+    codes, off, lens = seqio.synth_family(n, L, 17, sort_desc=False)
+    z = {"merges": np.array(random_tree(n, np.random.default_rng(1), float(parts[3]) if len(parts) > 3 else 0.05)),
+         "gaps": np.load(os.path.join(G, "hemopexin_sl.npz"))["gaps"]}
+else:
+    z = np.load(os.path.join(G, name + ".npz"))
+    codes, off, lens = seqio.pack([seqio.encode(str(s)) for s in z["seqs"]])
 eng.upload(codes, off, lens); eng.prof_set_scoring(sm)
 root, _, st = eng.align_tree(z["merges"], z["gaps"], want_paths=False); eng.prof_drop([root])
 torch.cuda.cudart().cudaProfilerStart()
