@@ -49,7 +49,7 @@ def workload(n_gpus: int):
     return seqio.synth_family(n, LEN, SEED), n
 
 
-from famsa_b200.sharding import row_shards, shard_sizes, tri, all_gather_blocks  # noqa: E402
+from famsa_b200.sharding import (row_shards, shard_sizes, tri, triangle_allgather_pipelined, assign_allreduce)  # noqa: E402
 
 
 def config_for(n: int, world: int) -> dict:
@@ -57,7 +57,8 @@ def config_for(n: int, world: int) -> dict:
     return {"workload": f"LCS triangle, {n} x {LEN} aa synthetic family (seed {SEED})",
             "n_seqs": n, "len": LEN, "pairs_per_step": tri(n),
             "out": "uint16 packed lower triangle", "l2": "flushed between timed iterations (192 MiB write)",
-            "multi_gpu": "row shards with equal pairs + one NCCL all-gather of row blocks" if world > 1 else "none"}
+            "multi_gpu": ("row shards with equal pairs, each computed in 4 pieces; every finished piece is broadcast (NCCL) into its "
+                          "place of the full packed triangle while the next piece is computed") if world > 1 else "none"}
 
 
 class ClockSampler:
@@ -315,6 +316,135 @@ def bench_dp(eng, torch, dist, world, rank, steps, warmup, l2_flush, stream, wan
     return out
 
 
+# ---------------------------------------------------------------------------------------------- C3 / C5 legs
+C3_N, C3_SEED = 100000, 2
+C5_N, C5_LEN, C5_SEEDS, C5_SEED = 3000000, 250, 100, 3
+
+
+def bench_c3(eng, torch, dist, world, rank, stream, l2_flush):
+    """BASELINE config 3 (strong scaling): the LCS triangle of 100 000 x 400 aa (4 999 950 000 pairs) sharded over the
+    ranks, the exchange overlapped piece by piece; every rank ends with the full 10 GB packed triangle."""
+    from famsa_b200 import seqio
+    codes, offsets, lens = seqio.synth_family(C3_N, LEN, C3_SEED)
+    n = len(lens)
+    eng.upload(codes, offsets, lens)
+    bounds = row_shards(n, world)
+    full = torch.empty(tri(n), dtype=torch.int16, device="cuda")
+
+    def compute_rows(r0, r1, view):
+        eng.triangle_device(r0, r1, view.data_ptr(), 2, stream)
+
+    def step():
+        triangle_allgather_pipelined(compute_rows, bounds, rank, dist, full, n_sub=8)
+
+    step()
+    dist.barrier(); torch.cuda.synchronize()
+    steps = 2
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s in range(steps):
+        l2_flush.fill_(s)
+        ev[s][0].record(); step(); ev[s][1].record()
+    dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    # untimed checks: identical on every rank; oracle spot check on rank 0
+    chk = full.to(torch.int64).sum().reshape(1)
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    spot = None
+    if rank == 0:
+        from oracle import pyoracle
+        rng = np.random.default_rng(5)
+        spot = True
+        for ref in rng.integers(1, n, size=3):
+            cols = rng.integers(0, ref, size=200)
+            want = pyoracle.lcs_rows(codes, offsets, lens, [int(ref)], cols)[0]
+            got = full[tri(int(ref)) + torch.from_numpy(cols).cuda()].cpu().numpy().astype(np.uint32)
+            spot = spot and bool(np.array_equal(got, want))
+    out = {"metric": METRIC, "unit": UNIT, "scaling": "strong", "value": tri(n) / (ms / 1e3), "ms_per_step": ms, "steps": steps, "warmup": 1,
+           "config": {"workload": f"LCS triangle, {n} x {LEN} aa synthetic family (seed {C3_SEED}), rows sharded over {world} GPUs, "
+                                  "exchange overlapped in 8 pieces per rank", "pairs_per_step": tri(n)},
+           "gathered_triangle_identical_on_all_ranks": bool(lo.item() == hi.item()), "oracle_spot_check": spot}
+    del full
+    torch.cuda.empty_cache()
+    return out
+
+
+def c5_family(torch, n, L, seed):
+    """3M ABC-transporter-like sequences x 250 aa (2-level family, 300 sub-roots at 0.25 from the root, members
+    at 0.20 from their sub-root), generated on the GPU because a host generator would take minutes; lengths L-7 .. L."""
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    root = torch.randint(0, 20, (L,), generator=g, device="cuda", dtype=torch.int8)
+    subs = root.repeat(300, 1)
+    m = torch.rand((300, L), generator=g, device="cuda") < 0.25
+    subs[m] = torch.randint(0, 20, (int(m.sum()),), generator=g, device="cuda", dtype=torch.int8)
+    which = torch.randint(0, 300, (n,), generator=g, device="cuda")
+    codes = subs[which]
+    chunk = 1 << 18
+    for a in range(0, n, chunk):
+        blk = codes[a:a + chunk]
+        m = torch.rand(blk.shape, generator=g, device="cuda") < 0.20
+        blk[m] = torch.randint(0, 20, (int(m.sum()),), generator=g, device="cuda", dtype=torch.int8)
+    lens = (L - torch.randint(0, 8, (n,), generator=g, device="cuda")).to(torch.int32)
+    order = torch.argsort(lens, descending=True, stable=True)       # FAMSA's own order: longest first
+    codes, lens = codes[order].contiguous(), lens[order]
+    offsets = (torch.arange(n, device="cuda", dtype=torch.int64) * L)
+    return codes.cpu().numpy().reshape(-1), offsets.cpu().numpy().astype(np.uint64), lens.cpu().numpy().astype(np.uint32)
+
+
+def bench_c5(eng, torch, dist, world, rank, stream, steps):
+    """BASELINE config 5, the LCS side of -medoidtree: the assignment step of FastTree<>::makeEvaluation (FastTree.cpp:
+    309-324) for 100 seeds x 3 000 000 sequences x 250 aa, the sequences sharded over the ranks, one NCCL MIN all-reduce of
+    the packed (distance, seed) pairs."""
+    from famsa_b200.binding import unpack_assignment
+    codes, offsets, lens = c5_family(torch, C5_N, C5_LEN, C5_SEED)
+    n = len(lens)
+    eng.upload(codes, offsets, lens)
+    seeds = np.random.default_rng(C5_SEED).choice(n, size=C5_SEEDS, replace=False).astype(np.uint32)
+    packed = torch.empty(n, dtype=torch.int64, device="cuda")
+
+    def shard_fn(r, w, t):
+        eng.assign_shard(seeds, r, w, t.data_ptr(), 0, stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    assign_allreduce(shard_fn, packed, rank, world, dist)
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s in range(steps):
+        ev[s][0].record(); assign_allreduce(shard_fn, packed, rank, world, dist); ev[s][1].record()
+    barrier()
+    t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    out = None
+    if rank == 0:
+        a, d = unpack_assignment(packed.cpu().numpy())
+        same = None
+        if world > 1:                                # untimed: the unsharded call on this rank gives the same answer
+            a1, d1 = eng.assign(seeds, 0)
+            same = bool(np.array_equal(a, a1) and np.array_equal(d, d1))
+        pairs = n * C5_SEEDS
+        peak, _ = peaks()
+        b_pair = float(lens.mean()) + 4.0
+        out = {"metric": METRIC, "unit": UNIT, "scaling": "strong", "value": pairs / (ms / 1e3), "ms_per_step": ms, "steps": steps,
+               "config": {"workload": f"medoid assignment: {C5_SEEDS} seed rows x {n} sequences x {C5_LEN} aa (2-level synthetic family, "
+                                      f"seed {C5_SEED}), sequences sharded over {world} GPU(s), one MIN all-reduce of 8 B per sequence",
+                          "pairs_per_step": pairs},
+               "roofline": {"bound": "hbm", "achieved": pairs * b_pair / (ms / 1e3) / 1e9 / world, "peak": peak, "unit": "GB/s",
+                            "frac": pairs * b_pair / (ms / 1e3) / 1e9 / world / peak, "bytes_per_pair": b_pair,
+                            "note": "per GPU, whole step (seed-row tiles + gather + arg-min + all-reduce) against the HBM contract roofline"},
+               "assigned_to_seed0": int((a == 0).sum()), "cost": float(np.add.accumulate(d.astype(np.float32))[-1]),
+               "identical_to_unsharded": same}
+    del packed
+    torch.cuda.empty_cache()
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- whole-tree DP leg
 TREE_SYNTH = (2000, 400, 17, 1)          # sequences, length, family seed, tree seed
 
@@ -506,16 +636,20 @@ def main():
     eng = famsa_b200.Engine(local)
     eng.upload(codes, offsets, lens)                       # resident inputs for the `value` leg
     d_block = torch.empty(max(max_shard, 1), dtype=torch.int16, device="cuda")
-    d_all = torch.empty(max_shard * world, dtype=torch.int16, device="cuda") if world > 1 else None
+    d_full = torch.empty(total_pairs, dtype=torch.int16, device="cuda") if world > 1 else None   # the gathered packed triangle
     side = torch.cuda.Stream()                             # non-default stream shared by our kernels and NCCL
     torch.cuda.set_stream(side)
     stream = side.cuda_stream
     l2_flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
+    def compute_rows(r0, r1, view):
+        eng.triangle_device(r0, r1, view.data_ptr(), 2, stream)
+
     def step_device():
-        eng.triangle_device(rb, re, d_block.data_ptr(), 2, stream)
-        if world > 1:
-            all_gather_blocks(d_block, bounds, dist, out=d_all)
+        if world == 1:
+            eng.triangle_device(rb, re, d_block.data_ptr(), 2, stream)
+        else:
+            triangle_allgather_pipelined(compute_rows, bounds, rank, dist, d_full, n_sub=4)
 
     def barrier():
         if world > 1:
@@ -550,6 +684,27 @@ def main():
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     value = total_pairs * args.steps / (dev_ms / 1e3)
 
+    # the same steps without the exchange: what the all-gather still costs after overlapping
+    exchange = None
+    if world > 1:
+        evc = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        for s in range(args.steps):
+            l2_flush.fill_(s)
+            evc[s][0].record()
+            eng.triangle_device(rb, re, d_block.data_ptr(), 2, stream)
+            evc[s][1].record()
+        barrier()
+        t = torch.tensor([sum(a.elapsed_time(b) for a, b in evc)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        comp_ms = float(t.item())
+        # every rank must hold the same gathered triangle: compare a checksum
+        chk = d_full.view(torch.int16).to(torch.int64).sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        exchange = {"compute_only_ms_per_step": comp_ms / args.steps, "all_gather_exposed_ms_per_step": (dev_ms - comp_ms) / args.steps,
+                    "gathered_bytes_per_rank": int(total_pairs * 2), "gathered_triangle_identical_on_all_ranks": bool(lo.item() == hi.item())}
+
     # dominant kernel, timed live with CUDA events on its launch stream (single launch class at this config)
     kern_ms = []
     for _ in range(3):
@@ -564,12 +719,10 @@ def main():
     codes_p = torch.from_numpy(codes).pin_memory().numpy()
 
     def step_e2e():
+        # N > 1: every rank's row block returns to its own host process (a row-partitioned consumer, e.g. the rows a
+        # distributed tree builder owns); there is no collective on this path
         eng.upload(codes_p, offsets, lens)
         eng.triangle(rb, re, out=h_np)
-        if world > 1:
-            # the gathered triangle is what a host-side tree builder consumes
-            d_block[:my_pairs].copy_(h_out[:my_pairs].cuda(non_blocking=True))
-            all_gather_blocks(d_block, bounds, dist, out=d_all)
 
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
@@ -602,7 +755,10 @@ def main():
             "config": config_for(n, world), "rows_of_rank0": [rb, re],
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_s / args.steps},
+                    "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "note": ("per rank: upload + own row block + D2H of that block to the rank's own host consumer; byte counts are per rank"
+                             if world > 1 else "famsa_lcs_upload + famsa_lcs_triangle with host buffers")},
+            "exchange": exchange,
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "fb::k_lcs_tile<NL>",
@@ -633,9 +789,13 @@ def main():
     dp = bench_dp(eng, torch, dist, world, rank, max(2, args.steps // 2), args.warmup, l2_flush, stream,
                   want_cpu=(world == 1 and not args.no_cpu_baseline))
     dp_tree = bench_dp_tree(eng, torch, dist, world, rank, max(3, args.steps), want_cpu=(world == 1 and not args.no_cpu_baseline))
+    c3 = bench_c3(eng, torch, dist, world, rank, stream, l2_flush) if world > 1 else None
+    c5 = bench_c5(eng, torch, dist, world, rank, stream, max(2, args.steps // 2))
     if rank == 0:
         line["dp"] = dp
         line["dp_tree"] = dp_tree
+        line["c3_triangle_100k"] = c3 if c3 else {"skipped": "strong-scaling leg: runs when launched on more than one GPU"}
+        line["c5_medoid_assignment_3m"] = c5
         line["gpu_launches"] = int(launches) + (dp["gpu_launches"] if dp else 0)
         if world == 1:
             # informational: the default guide tree (-gt sl) end to end on the same set -- famsa_lcs_prim =

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 EXPORTED_SYMBOLS = [
     "famsa_abi_version", "famsa_create", "famsa_destroy", "famsa_last_error", "famsa_kernel_launches",
     "famsa_lcs_upload", "famsa_lcs_n_seqs", "famsa_lcs_triangle", "famsa_lcs_triangle_device",
-    "famsa_lcs_rows", "famsa_lcs_rows_device", "famsa_lcs_assign", "famsa_lcs_prim", "famsa_transform_f64", "famsa_transform_f32",
+    "famsa_lcs_rows", "famsa_lcs_rows_device", "famsa_lcs_assign", "famsa_lcs_assign_shard", "famsa_lcs_prim", "famsa_transform_f64", "famsa_transform_f32",
     "famsa_lcs_last_timing", "famsa_dp_align_batch", "famsa_dp_align_batch_device", "famsa_dp_last_timing",
     "famsa_prof_set_scoring", "famsa_prof_put", "famsa_prof_merge_batch", "famsa_prof_get", "famsa_prof_drop",
     "famsa_prof_last_timing", "famsa_prof_stats", "famsa_prof_align_tree", "famsa_prof_tree_paths",
@@ -82,6 +82,7 @@ def load_library() -> C.CDLL:
     lib.famsa_lcs_rows_device.argtypes = [vp, vp, u32, vp, u32, vp, i32, vp]
     lib.famsa_lcs_prim.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.famsa_lcs_assign.argtypes = [vp, vp, u32, i32, vp, vp]
+    lib.famsa_lcs_assign_shard.argtypes = [vp, vp, u32, i32, u32, u32, vp, vp]
     lib.famsa_transform_f64.argtypes = [i32, u32, u32, u32]
     lib.famsa_transform_f64.restype = C.c_double
     lib.famsa_transform_f32.argtypes = [i32, u32, u32, u32]
@@ -105,6 +106,12 @@ def load_library() -> C.CDLL:
 
 def _ptr(a: np.ndarray | None):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def unpack_assignment(packed: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """(assignments uint32[n], min_dist float32[n]) from the MIN-reduced packed array of famsa_lcs_assign_shard."""
+    p = np.ascontiguousarray(packed, dtype=np.int64).view(np.uint64)
+    return (p & np.uint64(0xffffffff)).astype(np.uint32), (p >> np.uint64(32)).astype(np.uint32).view(np.float32)
 
 
 def tri_size(row_begin: int, row_end: int) -> int:
@@ -186,6 +193,13 @@ class Engine:
         d = np.empty(self.n, dtype=np.float32)
         self._check(self.lib.famsa_lcs_assign(self.h, _ptr(seeds), len(seeds), kind, _ptr(a), _ptr(d)))
         return a, d
+
+    def assign_shard(self, seed_ids, shard: int, n_shards: int, d_packed_ptr: int, kind: int = 0, stream: int = 0):
+        """famsa_lcs_assign_shard: this rank's slice of the medoid assignment, packed for a MIN all-reduce, into the
+        device int64 array at d_packed_ptr (n entries).  unpack_assignment() splits the reduced array."""
+        seeds = np.ascontiguousarray(seed_ids, dtype=np.uint32)
+        self._check(self.lib.famsa_lcs_assign_shard(self.h, _ptr(seeds), len(seeds), kind, shard, n_shards,
+                                                    C.c_void_p(d_packed_ptr), C.c_void_p(stream) if stream else None))
 
     def rows_device(self, d_ref_ptr: int, n_ref: int, d_col_ptr: int, n_col: int, d_out_ptr: int,
                     elem_bytes: int, stream: int = 0):

@@ -351,6 +351,28 @@ int famsa_lcs_assign(famsa_ctx* ctx, const uint32_t* seed_ids, uint32_t n_seeds,
     return finish_timing(ctx);
 }
 
+int famsa_lcs_assign_shard(famsa_ctx* ctx, const uint32_t* seed_ids, uint32_t n_seeds, int distance_kind, uint32_t shard,
+                           uint32_t n_shards, int64_t* d_packed, void* stream)
+{
+    FB_CHECK_CTX(ctx);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->lcs.n == 0) { set_error("famsa_lcs_upload has not been called"); return FAMSA_E_STATE; }
+    if (!seed_ids || !n_seeds || !d_packed) { set_error("NULL argument / no seeds"); return FAMSA_E_INVALID; }
+    if (distance_kind < 0 || distance_kind > 2) { set_error("distance_kind must be 0, 1 or 2"); return FAMSA_E_INVALID; }
+    if (!n_shards || shard >= n_shards) { set_error("shard out of range"); return FAMSA_E_INVALID; }
+    for (uint32_t k = 0; k < n_seeds; ++k)
+        if (seed_ids[k] >= ctx->lcs.n) { set_error("seed id out of range"); return FAMSA_E_INVALID; }
+    FB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    int rc = fb::scratch_acquire(ctx, st);
+    if (rc) return rc;
+    rc = fb::lcs_assign_shard(ctx, seed_ids, n_seeds, distance_kind, shard, n_shards, reinterpret_cast<long long*>(d_packed), st);
+    if (rc) return rc;
+    if (!stream) { FB_CUDA(cudaStreamSynchronize(st)); fb::scratch_release(ctx, st, true); return finish_timing(ctx); }
+    // the seed ids were handed to an async copy from pageable memory: staged by the driver before the call returned
+    return fb::scratch_release(ctx, st, false);
+}
+
 int famsa_lcs_last_timing(const famsa_ctx* ctx, float* total_ms, float* main_kernel_ms, uint64_t* n_pairs)
 {
     FB_CHECK_CTX(ctx);

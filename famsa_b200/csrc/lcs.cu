@@ -396,6 +396,32 @@ __global__ void k_assign(const void* __restrict__ lcs, int elem_bytes, uint32_t 
     mind[j] = best;
 }
 
+// Sharded form: only the sequences whose mask group lies in [g_begin, g_end) are answered; the result is packed as
+// (float bits of the distance << 32) | seed index so that an element-wise MIN over the shards (one all-reduce) assembles
+// the complete assignment -- distances are >= 0, so their bit patterns order like the values, and among equal distances
+// the lowest seed index wins, which is what the strict < of the sequential loop does.  Unanswered entries hold INT64_MAX.
+__global__ void k_assign_packed(const void* __restrict__ lcs, int elem_bytes, uint32_t n, uint32_t n_seeds,
+                                const uint32_t* __restrict__ seed_ids, const uint32_t* __restrict__ lens,
+                                const float* __restrict__ pow075, int kind, float never,
+                                const uint32_t* __restrict__ invperm, uint32_t g_begin, uint32_t g_end,
+                                long long* __restrict__ packed)
+{
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t g = invperm[j] / 32;
+    if (g < g_begin || g >= g_end) { packed[j] = 0x7fffffffffffffffll; return; }
+    const uint32_t lj = lens[j];
+    float best = 0.f;
+    uint32_t a = 0;
+    for (uint32_t k = 0; k < n_seeds; ++k) {
+        const size_t at = (size_t)k * n + j;
+        const uint32_t l = elem_bytes == 2 ? static_cast<const uint16_t*>(lcs)[at] : static_cast<const uint32_t*>(lcs)[at];
+        const float d = transform_f32(kind, l, lens[seed_ids[k]], lj, pow075, never);
+        if (k == 0 || d < best) { best = d; a = k; }
+    }
+    packed[j] = (long long)(((unsigned long long)__float_as_uint(best) << 32) | a);
+}
+
 // ------------------------------------------------------------------------------------------------
 // MST-Prim vertex loop (MSTPrim<>::run_view, MSTPrim.cpp:280-549) on the resident LCS triangle
 // ------------------------------------------------------------------------------------------------
@@ -975,7 +1001,8 @@ int lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_o
 }
 
 int lcs_rows(famsa_ctx* ctx, const uint32_t* d_ref_ids, const uint32_t* h_ref_ids, uint32_t n_ref,
-             const uint32_t* d_col_ids, uint32_t n_col, void* d_out, int elem_bytes, cudaStream_t st)
+             const uint32_t* d_col_ids, uint32_t n_col, void* d_out, int elem_bytes, cudaStream_t st,
+             uint32_t g_begin, uint32_t g_end)
 {
     LcsState& S = ctx->lcs;
     const uint32_t n = S.n;
@@ -992,7 +1019,8 @@ int lcs_rows(famsa_ctx* ctx, const uint32_t* d_ref_ids, const uint32_t* h_ref_id
     FB_TRY(S.d_res.reserve((size_t)res_bytes * npad * std::max(1u, n_ref)));
 
     std::vector<std::vector<uint3>> by_nl(kMaxNL + 1);
-    for (uint32_t g = 0; g < S.n_groups; ++g) {
+    g_end = std::min(g_end, S.n_groups);
+    for (uint32_t g = g_begin; g < g_end; ++g) {                     // the mask groups (= columns) this call answers for
         const uint32_t nl = S.groups[g].nl;
         if (nl == 0) continue;
         for (uint32_t q0 = 0; q0 < n_ref; q0 += kTileQ)
@@ -1234,6 +1262,31 @@ int lcs_assign(famsa_ctx* ctx, const uint32_t* h_seed_ids, uint32_t n_seeds, int
     FB_CUDA(cudaMemcpyAsync(h_assign, S.d_assign.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
     FB_CUDA(cudaMemcpyAsync(h_mind, S.d_mind.p, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
     FB_CUDA(cudaStreamSynchronize(st));
+    return FAMSA_OK;
+}
+
+// famsa_lcs_assign_shard: the seed rows against this shard's slice of the mask groups only, packed for a MIN all-reduce
+int lcs_assign_shard(famsa_ctx* ctx, const uint32_t* h_seed_ids, uint32_t n_seeds, int kind, uint32_t shard, uint32_t n_shards,
+                     long long* d_packed, cudaStream_t st)
+{
+    LcsState& S = ctx->lcs;
+    const uint32_t n = S.n;
+    const int eb = S.max_len < 65536 ? 2 : 4;
+    const uint32_t g_begin = (uint32_t)((unsigned long long)S.n_groups * shard / n_shards);
+    const uint32_t g_end = (uint32_t)((unsigned long long)S.n_groups * (shard + 1) / n_shards);
+    FB_TRY(S.d_assign_lcs.reserve((size_t)eb * n * n_seeds));
+    FB_TRY(S.d_ids_a.reserve(sizeof(uint32_t) * n_seeds));
+    FB_CUDA(cudaMemcpyAsync(S.d_ids_a.p, h_seed_ids, sizeof(uint32_t) * n_seeds, cudaMemcpyHostToDevice, st));
+    FB_TRY(lcs_rows(ctx, S.d_ids_a.as<uint32_t>(), h_seed_ids, n_seeds, nullptr, n, S.d_assign_lcs.p, eb, st, g_begin, g_end));
+    S.last_pairs = 0;
+    for (uint32_t g = g_begin; g < g_end; ++g) S.last_pairs += (uint64_t)std::min(32u, n - g * 32) * n_seeds;
+    const float never = (float)nextafter((double)FLT_MAX, 0.0);
+    k_assign_packed<<<(n + 255) / 256, 256, 0, st>>>(S.d_assign_lcs.p, eb, n, n_seeds, S.d_ids_a.as<uint32_t>(),
+                                                    S.d_raw_len.as<uint32_t>(), S.d_pow075.as<float>(), kind, never,
+                                                    S.d_invperm.as<uint32_t>(), g_begin, g_end, d_packed);
+    FB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    FB_CUDA(cudaEventRecord(ctx->ev[3], st));
     return FAMSA_OK;
 }
 

@@ -44,3 +44,77 @@ def full_triangle(gathered, bounds):
     sizes = shard_sizes(bounds)
     m = max(sizes)
     return torch.cat([gathered[r * m:r * m + sizes[r]] for r in range(len(sizes))])
+
+
+def sub_bounds(row_begin: int, row_end: int, n_sub: int) -> list[int]:
+    """Splits rows [row_begin, row_end) into n_sub consecutive pieces holding (almost) the same number of pairs."""
+    lo, hi = tri(row_begin), tri(row_end)
+    b = [row_begin]
+    for k in range(1, n_sub):
+        target = lo + (hi - lo) * k / n_sub
+        r = int(round((1 + math.sqrt(1 + 8 * target)) / 2))
+        b.append(min(max(r, b[-1]), row_end))
+    b.append(row_end)
+    return b
+
+
+_side_stream = None
+
+
+def triangle_allgather_pipelined(compute_rows, bounds, rank, dist, full, n_sub: int = 4):
+    """The N>1 triangle with its exchange step overlapped: every rank computes its row shard in n_sub pieces, and as
+    soon as a piece is finished every rank's piece of that number is broadcast straight into its place in `full` (the
+    packed lower triangle of all n rows, identical on every rank afterwards) while the next piece is being computed --
+    no padding, no staging copy, and only the last piece's exchange is exposed.
+    compute_rows(r0, r1, view): queues the computation of rows [r0, r1) on the current stream, writing the packed rows
+    into `view` (= full[tri(r0):tri(r1)]).  Works on CPU tensors too (gloo; everything is then synchronous)."""
+    import torch
+    global _side_stream
+    world = len(bounds) - 1
+    subs = [sub_bounds(bounds[r], bounds[r + 1], n_sub) for r in range(world)]
+    cuda = full.is_cuda
+    works = []
+    if cuda:
+        main = torch.cuda.current_stream()
+        if _side_stream is None:
+            _side_stream = torch.cuda.Stream()
+    for b in range(n_sub):
+        r0, r1 = subs[rank][b], subs[rank][b + 1]
+        if r1 > r0 and tri(r1) > tri(r0):
+            compute_rows(r0, r1, full[tri(r0):tri(r1)])
+        # raw bytes: every backend (gloo in the CPU tests, NCCL on GPUs) moves uint8
+        views = [(src, full[tri(subs[src][b]):tri(subs[src][b + 1])].view(torch.uint8)) for src in range(world)]
+        if cuda:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(_side_stream):
+                _side_stream.wait_event(ev)
+                for src, v in views:
+                    if v.numel():
+                        works.append(dist.broadcast(v, src=src, async_op=True))
+        else:
+            for src, v in views:
+                if v.numel():
+                    dist.broadcast(v, src=src)
+    for w in works:
+        w.wait()                      # the current stream waits for the exchange; the host does not
+    if cuda:
+        main.wait_stream(_side_stream)
+    return full
+
+
+def group_slice(n_groups: int, shard: int, n_shards: int) -> tuple[int, int]:
+    """The run of 32-sequence mask groups (length-sorted order) rank `shard` answers for -- same split as
+    famsa_lcs_assign_shard."""
+    return n_groups * shard // n_shards, n_groups * (shard + 1) // n_shards
+
+
+def assign_allreduce(assign_shard, packed, rank: int, world: int, dist):
+    """Medoid assignment (FastTree<>::makeEvaluation, FastTree.cpp:309-324) over `world` ranks: rank r computes the seed
+    rows against its slice of the sequences only (assign_shard(r, world, packed) fills the int64 tensor `packed`, see
+    famsa_lcs_assign_shard), then ONE element-wise MIN all-reduce completes the (distance, seed) pairs on every rank.
+    Returns `packed` (reduced in place); binding.unpack_assignment() splits it."""
+    assign_shard(rank, world, packed)
+    if world > 1:
+        dist.all_reduce(packed, op=dist.ReduceOp.MIN)
+    return packed

@@ -111,6 +111,17 @@ int famsa_lcs_rows_device(famsa_ctx* ctx, const uint32_t* d_ref_ids, uint32_t n_
 int famsa_lcs_assign(famsa_ctx* ctx, const uint32_t* seed_ids, uint32_t n_seeds, int distance_kind,
                      uint32_t* assignments, float* min_dist);
 
+/* The same assignment sharded across GPUs ("row-vs-all splits the column range G ways"): the context of rank
+ * `shard` of `n_shards` -- every rank has uploaded the same set -- answers only for its slice of the sequences (a contiguous
+ * run of the 32-sequence mask groups of the length-sorted order, i.e. 1/n_shards of the LCS work) and writes
+ *   d_packed[j] = ((int64) float bits of min_dist[j] << 32) | assignments[j]      for its sequences j (caller order),
+ *   d_packed[j] = INT64_MAX                                                       for everybody else's,
+ * into a DEVICE array of n_seqs int64.  One element-wise MIN all-reduce over the ranks (NCCL) completes it everywhere:
+ * distances are >= 0, so the packed values order like (distance, seed index) and ties go to the lowest seed exactly like
+ * the strict < of the sequential loop.  stream: cudaStream_t or NULL (the context's stream, synchronised). */
+int famsa_lcs_assign_shard(famsa_ctx* ctx, const uint32_t* seed_ids, uint32_t n_seeds, int distance_kind,
+                           uint32_t shard, uint32_t n_shards, int64_t* d_packed, void* stream);
+
 /* The default guide tree (-gt sl): the vertex loop of MSTPrim<>::run_view (src/tree/MSTPrim.cpp:280-549) on the
  * device.  Per step: distances from the current vertex (as the row, seq0) to every unvisited sequence through
  * Transform<double, distance>, the relaxation  s = {d, ~ids_to_uint64(v, j)};  if (d <= best[j].first && s < best[j])

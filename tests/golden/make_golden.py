@@ -169,6 +169,38 @@ def make_hemopexin_sl():
     print("hemopexin_sl.npz:", len(recs), "merges, final width", len(final[0]))
 
 
+def make_hemopexin_dups():
+    """hemopexin_dups.npz -- test/hemopexin_duplicates with -keep-duplicates under its golden tree medoid-sl-dups.dnd
+    (self-hosted.yml:317-329: "medoid + sl + keep duplicates (from tree)"): identical sequences are merged like any
+    others.  Sequences in the tree's leaf order, merges, per-merge reference totals and path CRCs, CRC of the final rows;
+    generation asserts the final alignment equals medoid-sl-dups.fasta."""
+    import zlib
+    from oracle import pyoracle
+    from treeutil import parse_newick
+    from dp_cases import reference_merges
+    T = os.path.join(REF, "hemopexin_duplicates")
+    ids, seqs = seqio.read_fasta(os.path.join(T, "hemopexin_duplicates"))
+    name2seq = dict(zip(ids, seqs))
+    leaves, merges = parse_newick(open(os.path.join(T, "medoid-sl-dups.dnd")).read())
+    lseqs = [name2seq[n].upper() for n in leaves]
+    g, recs = reference_merges(lseqs, merges, threads=(1,))
+    ig, sg = seqio.read_fasta(os.path.join(T, "medoid-sl-dups.fasta"))
+    gold = dict(zip(ig, sg))
+    final = recs[-1]["rows"]
+    assert all(final[i] == gold[leaves[i]].upper() for i in range(len(leaves))), "does not reproduce medoid-sl-dups.fasta"
+    totals, crcs = [], []
+    for r in recs:
+        o = pyoracle.dp_align(*r["job"], g)
+        pth = pyoracle.path_from_rows(r["rows"], r["m1"], r["m2"], o["swapped"])
+        assert np.array_equal(pth, o["path"]) and o["total"] == r["total"]
+        totals.append(r["total"]); crcs.append(zlib.crc32(pth.tobytes()))
+    rows_crc = zlib.crc32("\n".join(final[i] for i in range(len(leaves))).encode())
+    np.savez_compressed(os.path.join(HERE, "hemopexin_dups.npz"), seqs=np.array(lseqs), merges=np.array(merges), gaps=g,
+                        totals=np.array(totals, dtype=np.int64), path_crc=np.array(crcs, dtype=np.uint32),
+                        rows_crc=np.array(rows_crc, dtype=np.uint32))
+    print("hemopexin_dups.npz:", len(recs), "merges,", len(set(lseqs)), "distinct sequences of", len(lseqs))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         sys.path.insert(0, os.path.join(HERE, ".."))
@@ -178,6 +210,7 @@ if __name__ == "__main__":
     make_dp()
     make_hemopexin()
     make_hemopexin_sl()
+    make_hemopexin_dups()
     make_sl_tree()
 
 

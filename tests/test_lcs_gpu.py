@@ -127,6 +127,23 @@ def test_full_size_properties(engine):
     assert int(tri.astype(np.uint64).sum()) == int(engine.triangle(dtype=np.uint16).astype(np.uint64).sum())
 
 
+@pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref not built")
+def test_full_c2_triangle_equals_reference(engine):
+    """BASELINE config 2 in full: all 49 995 000 LCS lengths of the 10k x 400 aa set against the unmodified reference
+    (CLCSBP AVX2 through calculateDistanceVector, oracle/_ref) -- every pair, not a sample."""
+    codes, offsets, lens = seqio.synth_family(10000, 400, seed=1)
+    n = len(lens)
+    letters = [seqio.decode(codes[int(o):int(o) + int(l)]) for o, l in zip(offsets, lens)]
+    rs = pyoracle.RefSeqSet(letters)
+    _, pairs, want = rs.triangle_mt(0, n, max(1, len(os.sched_getaffinity(0))), 2, want_lcs=True)
+    rs.close()
+    assert pairs == n * (n - 1) // 2
+    engine.upload(codes, offsets, lens)
+    got = engine.triangle(dtype=np.uint16)
+    assert got.size == want.size
+    assert np.array_equal(got, want.astype(np.uint16)), "the C2 triangle differs from the reference's"
+
+
 def _assign_reference(codes, offsets, lens, seeds, kind, lcs_rows):
     """FastTree<>::makeEvaluation (src/tree/FastTree.cpp:309-324) restated with the oracle's float Transform."""
     n = len(lens)
@@ -187,6 +204,27 @@ def test_medoid_assignment_large(engine):
 
 @pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("modified", [False, True])
+def test_medoid_assignment_sharded(engine):
+    """famsa_lcs_assign_shard: three shards of one context, combined with an element-wise MIN (what the NCCL all-reduce
+    does across GPUs), equal the unsharded famsa_lcs_assign bit for bit -- ragged lengths, unsorted input, a repeated seed."""
+    import torch
+    from famsa_b200.binding import unpack_assignment
+    codes, offsets, lens = seqio.pack(random_set(np.random.default_rng(77), 1000, 30, 300))
+    engine.upload(codes, offsets, lens)
+    seeds = np.array([5, 900, 17, 5, 333, 64], dtype=np.uint32)
+    for kind in (0, 2):
+        want_a, want_d = engine.assign(seeds, kind)
+        parts = []
+        for sh in range(3):
+            t = torch.empty(len(lens), dtype=torch.int64, device="cuda")
+            engine.assign_shard(seeds, sh, 3, t.data_ptr(), kind)
+            parts.append(t.cpu().numpy())
+        owned = np.stack([p != np.iinfo(np.int64).max for p in parts])
+        assert np.all(owned.sum(axis=0) == 1), "the shards must partition the sequences"
+        a, d = unpack_assignment(np.minimum.reduce(parts))
+        assert np.array_equal(a, want_a) and np.array_equal(d, want_d)
+
+
 def test_gpu_driven_upgma_tree(engine, modified):
     """Drop-in proof for HP-1: GPU LCS triangle -> host Transform<float, indel075_div_lcs> -> the reference's own,
     unmodified UPGMA agglomeration (UPGMA<>::computeTree) gives exactly the guide tree the reference builds from

@@ -31,6 +31,80 @@ def _worker(rank, world, port, n, out_dir):
     dist.destroy_process_group()
 
 
+def _pipelined_worker(rank, world, port, n, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    codes, offsets, lens = seqio.synth_family(n, 60, seed=4)
+    bounds = sharding.row_shards(n, world)
+    full = torch.full((sharding.tri(n),), -1, dtype=torch.int16)
+
+    def compute_rows(r0, r1, view):
+        view.copy_(torch.from_numpy(pyoracle.lcs_triangle(codes, offsets, lens, r0, r1).astype(np.int16)))
+    sharding.triangle_allgather_pipelined(compute_rows, bounds, rank, dist, full, n_sub=3)
+    want = pyoracle.lcs_triangle(codes, offsets, lens)
+    ok = np.array_equal(full.numpy().astype(np.uint32), want)
+    open(os.path.join(out_dir, f"rank{rank}.txt"), "w").write("ok" if ok else "bad")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 101), (3, 64), (2, 3)])
+def test_pipelined_all_gather(tmp_path, world, n):
+    """Row shards cut into pieces, every piece broadcast into its place of the full packed triangle (the overlapped
+    exchange of the N>1 bench path) -- host logic on gloo, compute by the oracle."""
+    port = 29700 + world * 7 + (os.getpid() % 50)
+    mp.spawn(_pipelined_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f"rank{r}.txt").read() == "ok"
+
+
+def _assign_worker(rank, world, port, n, out_dir):
+    """Host logic of the sharded medoid assignment on gloo: per-shard packed results (computed by the oracle here),
+    one MIN all-reduce, unpack == the sequential loop over all seeds."""
+    from famsa_b200.binding import unpack_assignment
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    codes, offsets, lens = seqio.synth_family(n, 50, seed=9, sort_desc=False)
+    seeds = np.array([3, 17, 5, 3, n - 1], dtype=np.uint32)          # a repeated seed: ties must go to the first
+    rows = pyoracle.lcs_rows(codes, offsets, lens, seeds)
+    dmat = np.array([[pyoracle.transform(0, int(rows[k, j]), int(lens[seeds[k]]), int(lens[j]), False) for j in range(n)]
+                     for k in range(len(seeds))], dtype=np.float32)
+    want_a = np.zeros(n, dtype=np.uint32); want_d = dmat[0].copy()
+    for k in range(1, len(seeds)):                                   # FastTree.cpp:317-322, strict <
+        better = dmat[k] < want_d
+        want_a[better] = k; want_d[better] = dmat[k][better]
+    order = np.argsort(-lens.astype(np.int64), kind="stable")        # famsa_lcs_upload's length-descending order
+    pos = np.empty(n, dtype=np.int64); pos[order] = np.arange(n)
+
+    def assign_shard(shard, n_shards, packed):
+        g0, g1 = sharding.group_slice((n + 31) // 32, shard, n_shards)
+        mine = (pos // 32 >= g0) & (pos // 32 < g1)
+        p = np.full(n, np.iinfo(np.int64).max, dtype=np.int64)
+        p[mine] = (want_d[mine].view(np.uint32).astype(np.int64) << 32) | want_a[mine].astype(np.int64)
+        packed.copy_(torch.from_numpy(p))
+    packed = torch.empty(n, dtype=torch.int64)
+    sharding.assign_allreduce(assign_shard, packed, rank, world, dist)
+    a, d = unpack_assignment(packed.numpy())
+    ok = np.array_equal(a, want_a) and np.array_equal(d, want_d)
+    open(os.path.join(out_dir, f"rank{rank}.txt"), "w").write("ok" if ok else "bad")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 150), (3, 70)])
+def test_sharded_assignment_allreduce(tmp_path, world, n):
+    port = 29800 + world * 7 + (os.getpid() % 50)
+    mp.spawn(_assign_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f"rank{r}.txt").read() == "ok"
+
+
+def test_sub_bounds():
+    for rb, re, k in [(0, 1000, 4), (700, 1000, 4), (5, 6, 4), (0, 0, 3), (0, 2, 8)]:
+        b = sharding.sub_bounds(rb, re, k)
+        assert b[0] == rb and b[-1] == re and len(b) == k + 1 and all(x <= y for x, y in zip(b, b[1:]))
+
+
 @pytest.mark.parametrize("world,n", [(2, 101), (3, 64)])
 def test_row_shards_all_gather(tmp_path, world, n):
     port = 29600 + world * 7 + (os.getpid() % 50)
