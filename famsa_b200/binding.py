@@ -337,6 +337,29 @@ class Engine:
                                 rows_width=int(r.rows_width), cols_width=int(r.cols_width)))
         return root.value, out, stats
 
+    def align_tree_buffers(self, merges, gaps, stats_of_a_run):
+        """Prebuilt arguments of famsa_prof_align_tree / famsa_prof_tree_paths (what a C caller holds), sized from an
+        earlier run of the same tree: for align_tree_raw."""
+        t = np.ascontiguousarray(merges, dtype=np.int32).reshape(-1, 2)
+        n = len(t)
+        nbytes = C.c_uint64()
+        res = (DpResult * max(n, 1))()
+        root = C.c_uint32()
+        g = np.ascontiguousarray(gaps, dtype=np.int64)
+        st = TreeStats()
+        self._check(self.lib.famsa_prof_align_tree(self.h, _ptr(t), n + 1, _ptr(g), C.byref(res), C.byref(root), C.byref(nbytes), C.byref(st)))
+        self.prof_drop([root.value])
+        return dict(tree=t, n=n, gaps=g, res=res, path=np.zeros(max(int(nbytes.value) * 2, 1), dtype=np.uint8))
+
+    def align_tree_raw(self, b):
+        """The two C calls on prebuilt buffers, without this binding's per-merge Python objects.  Returns (root id, stats)."""
+        root, nbytes = C.c_uint32(), C.c_uint64()
+        st = TreeStats()
+        self._check(self.lib.famsa_prof_align_tree(self.h, _ptr(b["tree"]), b["n"] + 1, _ptr(b["gaps"]), C.byref(b["res"]), C.byref(root),
+                                                   C.byref(nbytes), C.byref(st)))
+        self._check(self.lib.famsa_prof_tree_paths(self.h, _ptr(b["path"]), b["path"].size))
+        return root.value, {f: getattr(st, f) for f, _ in TreeStats._fields_ if f != "pad"}
+
     def prof_get(self, pid: int, tables: bool = True):
         """(scores, counters, card) of a resident profile, or (width, card) with tables=False."""
         w, k = C.c_uint32(), C.c_uint32()

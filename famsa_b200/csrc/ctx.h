@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -81,8 +82,59 @@ struct ProfEntry {
     uint32_t gen = 0;              // bumped whenever the id is handed out again
 };
 // One queued batch of merges (prof_launch ... prof_collect)
+// In-order ring allocator (offsets only): batches take space when they are queued and give it back when they are
+// collected, oldest first -- the stream is a FIFO, so that is the order they finish in.
+struct Ring {
+    size_t cap = 0, head = 0, tail = 0;
+    bool empty = true;
+    // returns the offset or (size_t)-1; `need` is rounded up to 256 bytes
+    size_t alloc(size_t need)
+    {
+        need = (need + 255) & ~(size_t)255;
+        if (need > cap) return (size_t)-1;
+        if (empty) { head = tail = 0; }
+        size_t off;
+        if (empty || head > tail) {                 // free space: [head, cap) and [0, tail)
+            if (head + need <= cap) off = head;
+            else if (need <= tail && !empty) off = 0;
+            else if (empty) off = 0;
+            else return (size_t)-1;
+        } else {                                    // head <= tail (wrapped, or full): free space is [head, tail)
+            if (head == tail || head + need > tail) return (size_t)-1;
+            off = head;
+        }
+        head = off + need;
+        empty = false;
+        return off;
+    }
+    void release_to(size_t pos) { tail = pos; if (tail == head) empty = true; }
+};
+
+// Host-side sub-allocator over a few large device chunks for the resident profile tables.  Everything that touches a
+// profile is ordered on the context's stream, so a block given back when the batch that consumes it is QUEUED may be handed
+// to any batch queued later; no allocator call reaches the driver in steady state (a stream-ordered cudaMallocAsync per
+// batch turned out to leave the device idle between the batches of a chain-like guide tree).
+struct DevArena {
+    struct Chunk { char* base; size_t bytes; };
+    std::vector<Chunk> chunks;
+    std::map<char*, std::pair<size_t, int>> free_by_addr;          // start -> (bytes, chunk)
+    std::multimap<size_t, char*> free_by_size;
+    size_t chunk_bytes = 256u << 20;
+    void* alloc(size_t n);                                          // nullptr when the device is out of memory
+    void free(void* p, size_t n);
+    void release_all();
+    void erase_size(size_t n, char* p)
+    {
+        auto r = free_by_size.equal_range(n);
+        for (auto it = r.first; it != r.second; ++it)
+            if (it->second == p) { free_by_size.erase(it); return; }
+    }
+};
+
 struct ProfTicket {
+    size_t ring_host_end = (size_t)-1, ring_dev_end = (size_t)-1;    // ring positions to release when the batch is collected
     cudaEvent_t done = nullptr;
+    unsigned long long done_seq = 0;   // != 0: completion is published in ProfState::h_done instead of an event
     uint32_t n = 0;
     std::vector<uint32_t> merged_ids, merged_gen;
     famsa_dp_result* h_results = nullptr;   // filled by the batch's D2H copy
@@ -102,6 +154,14 @@ struct ProfState {
     std::vector<int> free_slabs;
     bool has_scoring = false, pool_ready = false;
     DevBuf d_sm, d_widths;         // d_widths[id]: width of a pending profile, written by the fill kernel
+    // small batches (the fused one-block-per-merge path): job descriptors live in mapped pinned host memory that the kernel
+    // reads directly, scratch comes from a device ring -- no copy-engine operation and no allocator call per batch
+    DevArena arena;                 // storage of the resident profiles
+    volatile unsigned long long* h_done = nullptr;   // mapped host word: sequence number of the last finished flag-tracked batch
+    unsigned long long done_seq = 0;
+    DevBuf d_block_counter;
+    unsigned char* h_ring_mem = nullptr; Ring h_ring;
+    DevBuf d_ring_mem; Ring d_ring;
     std::vector<cudaEvent_t> free_events;
     // result of the most recent famsa_prof_align_tree (pinned): per-merge records and all paths
     famsa_dp_result* h_tree_results = nullptr; size_t h_tree_results_cap = 0;
@@ -160,9 +220,15 @@ int dp_run_host(famsa_ctx* ctx, const famsa_dp_job* jobs, uint32_t n, const int6
                 uint8_t* path_buf, uint8_t* dirs_buf);
 int dp_check_results(const famsa_dp_result* results, uint32_t n);
 // d_meta_out / d_blob_out non-NULL: the per-job DpMeta records stay valid until the caller cudaFreeAsync()s *d_blob_out
+// fused non-NULL (a FusedParams, prof_dev.cuh): every merge runs whole -- leaves, prep, fill, traceback, merged tables --
+// in one block of k_merge_fused; the caller then launches neither the leaf nor the construct kernel.
 int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext, uint32_t n, const int64_t gaps[4],
                   famsa_dp_result* d_results, uint8_t* d_path, uint8_t* d_dirs, DpMeta** d_meta_out, void** d_blob_out,
-                  cudaStream_t st);
+                  cudaStream_t st, const void* fused = nullptr);
+int dp_fused_plan(const famsa_dp_job* jobs, const DpJobExt* ext, uint32_t n, bool align16, DpJobDev* out, DpFusedPlan* plan);
+int dp_fused_launch(famsa_ctx* ctx, const DpJobDev* jobs, uint32_t n, const int64_t gaps[4], famsa_dp_result* d_results, uint8_t* d_path,
+                    DpMeta* d_meta, uint8_t* d_scratch, uint8_t* d_skew, famsa_dp_result* h_results, uint8_t* h_path,
+                    const void* fused_params, uint64_t cells, bool record_events, cudaStream_t st);
 // prof.cu
 int prof_set_scoring(famsa_ctx* ctx, const int64_t* sm);
 int prof_put(famsa_ctx* ctx, const famsa_dp_profile* profs, uint32_t n, uint32_t* ids);

@@ -38,6 +38,7 @@
 
 #include "ctx.h"
 #include "dp_dev.h"
+#include "prof_dev.cuh"
 
 namespace fb {
 
@@ -195,15 +196,17 @@ struct DpParams {
     unsigned char* scratch;
     const unsigned long long* tblock;   // k_dp_unskew: first block of each job (n_jobs + 1 entries)
     famsa_dp_result* results;
+    famsa_dp_result* h_results;   // optional mapped host copies written by the traceback itself (no D2H copy afterwards)
+    unsigned char* h_path;
 };
 
 // ------------------------------------------------------------------------------------------------
 // k_dp_prep: one block per job
 // ------------------------------------------------------------------------------------------------
 constexpr int kPrepThreads = 512;
-__global__ void __launch_bounds__(kPrepThreads) k_dp_prep(const DpParams P)
+// all threads of the block (any multiple of 32 up to kPrepThreads)
+__device__ __forceinline__ void prep_body(const DpParams& P, uint32_t jid)
 {
-    const uint32_t jid = P.job_base + blockIdx.x;
     const DpJobDev J = P.jobs[jid];
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
 
@@ -243,33 +246,44 @@ __global__ void __launch_bounds__(kPrepThreads) k_dp_prep(const DpParams P)
         const uint32_t w = side ? w2 : w1;
         const int card = (int)(side ? J.card2 : J.card1);
         unsigned long long nz = 0, smax = 0, flags = 0;
-        if (var == 2)
-            for (size_t k = tid; k < ((size_t)w + 1) * 32; k += nthr) nz += cnt[k] != 0;
-        if (is_col)
-            for (size_t e = 32 + tid; e < ((size_t)w + 1) * 32; e += nthr) {   // columns 1..w, rows 0..29 feed T
-                if ((e & 31) >= 30) continue;
-                const long long v = sc[e];
-                flags |= v != (long long)(int)v;
-                const unsigned long long a = (unsigned long long)(v < 0 ? -v : v);
-                smax = a > smax ? a : smax;
-            }
-        if (var == 2)
-            for (uint32_t c = 1 + tid; c <= w; c += nthr) {
-                int a, b, d, e, f, g;
-                solve_gaps(cnt, c, w, card, a, b, d, e, f, g);
-                int bad = (a | b | d | e | f | g) < 0;
+        // one thread per column, all loads of a column issued together (the block is small: memory-level parallelism
+        // is what makes this pass short)
+        for (uint32_t c = tid; c <= w; c += nthr) {
+            if (var == 2) {
                 const int4* cc = reinterpret_cast<const int4*>(cnt + (size_t)c * 32);
+                int4 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = cc[q];
                 int neg = 0, over = 0;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    int4 v = cc[q];
-                    if (q == 7) { v.z = 0; v.w = 0; }                 // rows 30 (GAP) and 31 (GUARD) are not counts of a symbol
-                    neg |= v.x | v.y | v.z | v.w;
-                    over |= (v.x > card) | (v.y > card) | (v.z > card) | (v.w > card);
+                    nz += (v[q].x != 0) + (v[q].y != 0) + (v[q].z != 0) + (v[q].w != 0);
+                    int4 u = v[q];
+                    if (q == 7) { u.z = 0; u.w = 0; }                 // rows 30 (GAP) and 31 (GUARD) are not counts of a symbol
+                    neg |= u.x | u.y | u.z | u.w;
+                    over |= (u.x > card) | (u.y > card) | (u.z > card) | (u.w > card);
                 }
-                bad |= neg < 0 || over;
-                flags |= bad ? 2 : 0;
+                if (c >= 1) {
+                    int a2, b2, d2, e2, f2, g2;
+                    solve_gaps(cnt, c, w, card, a2, b2, d2, e2, f2, g2);
+                    if ((a2 | b2 | d2 | e2 | f2 | g2) < 0 || neg < 0 || over) flags |= 2;
+                }
             }
+            if (is_col && c >= 1) {                                   // columns 1..w, rows 0..29 feed T
+                const longlong2* sp = reinterpret_cast<const longlong2*>(sc + (size_t)c * 32);
+                longlong2 v[15];
+#pragma unroll
+                for (int q = 0; q < 15; ++q) v[q] = sp[q];
+#pragma unroll
+                for (int q = 0; q < 15; ++q) {
+                    flags |= (v[q].x != (long long)(int)v[q].x) | (v[q].y != (long long)(int)v[q].y);
+                    const unsigned long long ax = (unsigned long long)(v[q].x < 0 ? -v[q].x : v[q].x);
+                    const unsigned long long ay = (unsigned long long)(v[q].y < 0 ? -v[q].y : v[q].y);
+                    smax = ax > smax ? ax : smax;
+                    smax = ay > smax ? ay : smax;
+                }
+            }
+        }
         for (int o = 16; o; o >>= 1) {
             nz += __shfl_xor_sync(0xffffffffu, nz, o);
             const unsigned long long x = __shfl_xor_sync(0xffffffffu, smax, o);
@@ -355,6 +369,11 @@ __global__ void __launch_bounds__(kPrepThreads) k_dp_prep(const DpParams P)
         }
         if (tid == 0) park_cell(browg, Cell{0, kNegInf, kNegInf, 0}, 1);
     }
+}
+
+__global__ void __launch_bounds__(kPrepThreads) k_dp_prep(const DpParams P)
+{
+    prep_body(P, P.job_base + blockIdx.x);
 }
 
 // Caller-visible CDPMatrix bytes (row-major, row 0 all-H, column 0 all-V) from the skewed internal directions.
@@ -766,22 +785,9 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
 // reference switches to its multi-threaded ParAlign* variants).  The boundary row travels through L2 either way.  There
 // is no barrier anywhere: a warp leaves when its stripes are done, the owner of cell (WR, WC) leaves (D, H, V) in the
 // job's scratch for k_dp_trace.
-template <int NW, bool CLUSTERED>
-__global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32, 1) k_dp_fill(const DpParams P)
+// the stripes of merge `jid` that belong to team warp `team_warp` of `TW`
+__device__ __forceinline__ void fill_body(const DpParams& P, uint32_t jid, uint32_t team_warp, uint32_t TW, WarpShared& W)
 {
-    extern __shared__ __align__(16) unsigned char sm_dyn[];
-    const uint32_t warp = threadIdx.x / 32;
-    WarpShared& W = reinterpret_cast<WarpShared*>(sm_dyn)[warp];
-    uint32_t CL = 1, cta_rank = 0;
-    if (CLUSTERED) {
-        CL = cooperative_groups::this_cluster().num_blocks();
-        cta_rank = cooperative_groups::this_cluster().block_rank();
-    }
-    const uint32_t team_warp = NW == 1 ? 0 : warp * CL + cta_rank;
-    const uint32_t TW = NW == 1 ? 1 : (uint32_t)NW * CL;
-    const uint32_t slot = NW == 1 ? blockIdx.x * kDpWarps + warp : blockIdx.x / CL;
-    if (slot >= P.n_jobs) return;                                    // whole warp (NW == 1) / whole team otherwise
-    const uint32_t jid = P.order[slot];
     const DpJobDev J = P.jobs[jid];
     const DpMeta M = P.meta[jid];
     if (M.bad == 2) return;                                          // a child failed: k_dp_trace reports it
@@ -800,6 +806,24 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32, 1) k_dp_fill(c
 #undef FB_STRIPES
 }
 
+template <int NW, bool CLUSTERED>
+__global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32, 1) k_dp_fill(const DpParams P)
+{
+    extern __shared__ __align__(16) unsigned char sm_dyn[];
+    const uint32_t warp = threadIdx.x / 32;
+    WarpShared& W = reinterpret_cast<WarpShared*>(sm_dyn)[warp];
+    uint32_t CL = 1, cta_rank = 0;
+    if (CLUSTERED) {
+        CL = cooperative_groups::this_cluster().num_blocks();
+        cta_rank = cooperative_groups::this_cluster().block_rank();
+    }
+    const uint32_t team_warp = NW == 1 ? 0 : warp * CL + cta_rank;
+    const uint32_t TW = NW == 1 ? 1 : (uint32_t)NW * CL;
+    const uint32_t slot = NW == 1 ? blockIdx.x * kDpWarps + warp : blockIdx.x / CL;
+    if (slot >= P.n_jobs) return;                                    // whole warp (NW == 1) / whole team otherwise
+    fill_body(P, P.order[slot], team_warp, TW, W);
+}
+
 // ------------------------------------------------------------------------------------------------
 // k_dp_trace: the traceback of ConstructProfile (profile.cpp:727-775), one warp per merge.
 // The direction bytes are stored skewed -- inside one 32-row stripe, wavefront step s = j + lane is the major index --
@@ -807,13 +831,11 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32, 1) k_dp_fill(c
 // its rows are kept inside a stripe: the warp copies it with 16-byte loads, lane 0 walks inside it, repeat.
 // ------------------------------------------------------------------------------------------------
 constexpr int kTraceWarps = 4;
-__global__ void __launch_bounds__(kTraceWarps * 32) k_dp_trace(const DpParams P)
+// one warp; tile: 64 x 32 bytes of shared memory; all_dirs: the merge's whole skewed direction matrix already in shared
+// memory (small merges in the fused kernel), or NULL
+__device__ __forceinline__ void trace_body(const DpParams& P, uint32_t jid, unsigned char* tile, const unsigned char* all_dirs = nullptr)
 {
-    __shared__ __align__(16) unsigned char sm_tile[kTraceWarps][64 * 32];
-    const uint32_t warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-    const uint32_t slot = blockIdx.x * kTraceWarps + warp;
-    if (slot >= P.n_jobs) return;
-    const uint32_t jid = P.job_base + slot;
+    const uint32_t lane = threadIdx.x % 32;
     const DpJobDev J = P.jobs[jid];
     const DpMeta M = P.meta[jid];
     if (M.bad == 2) {                                                // a child failed: report, touch nothing else
@@ -823,6 +845,7 @@ __global__ void __launch_bounds__(kTraceWarps * 32) k_dp_trace(const DpParams P)
             r.path_offset = J.path_off; r.dirs_offset = J.dirs_off;
             r.variant = 0xFF;
             P.results[jid] = r;
+            if (P.h_results) P.h_results[jid] = r;
             if (J.w_dst) *J.w_dst = kWidthBad;
         }
         return;
@@ -836,7 +859,6 @@ __global__ void __launch_bounds__(kTraceWarps * 32) k_dp_trace(const DpParams P)
     const size_t steps = (size_t)WC + 32;
     const long long last[3] = {__ldcg(g_last), __ldcg(g_last + 1), __ldcg(g_last + 2)};
 
-    unsigned char* tile = sm_tile[warp];
     uint32_t n = 0;
     long long total;
     int dir;
@@ -844,6 +866,37 @@ __global__ void __launch_bounds__(kTraceWarps * 32) k_dp_trace(const DpParams P)
     else if (last[1] > last[2]) { dir = 1; total = last[1]; }
     else { dir = 2; total = last[2]; }
     uint32_t ti = WR, tj = WC;
+    if (all_dirs && ti) {
+        // the whole matrix is at hand: one uninterrupted walk down to row 0 (same index steps as below, D -65, H -32, V -33;
+        // leaving a stripe through its first row re-bases the index on the stripe above)
+        if (lane == 0) {
+            uint32_t ii = ti, jj = tj, stripe = (ii - 1) >> 5;
+            int l = (int)((ii - 1) & 31);
+            uint32_t idx = (uint32_t)((stripe * steps + jj + l) * 32 + l);
+            unsigned b = all_dirs[idx];
+            unsigned char* out = tmp_path;
+            for (;;) {
+                *out++ = (unsigned char)dir;
+                const int di = dir != 1, dj = dir != 2;
+                if (dj && !jj) { ii = 0; jj = 0; break; }                // cannot happen for a valid matrix
+                ii -= di; jj -= dj; l -= di; idx -= 32 * dj + 33 * di;
+                if (l < 0) {
+                    if (!ii) { dir = (int)((b >> (2 * dir)) & 3); break; }
+                    l = 31; --stripe;
+                    idx = (uint32_t)((stripe * steps + jj + 31) * 32 + 31);
+                }
+                const unsigned nb = all_dirs[idx];
+                dir = (int)((b >> (2 * dir)) & 3);
+                b = nb;
+            }
+            n = (uint32_t)(out - tmp_path);
+            ti = ii; tj = jj;
+        }
+        ti = __shfl_sync(0xffffffffu, ti, 0);
+        tj = __shfl_sync(0xffffffffu, tj, 0);
+        dir = __shfl_sync(0xffffffffu, dir, 0);
+        n = __shfl_sync(0xffffffffu, n, 0);
+    }
     while (ti || tj) {
         // rows [row_lo, ti] (inside the stripe of ti), columns [j0, tj]
         const uint32_t stripe = ti ? (ti - 1) >> 5 : 0, l_top = ti ? (ti - 1) & 31 : 0;
@@ -900,6 +953,21 @@ __global__ void __launch_bounds__(kTraceWarps * 32) k_dp_trace(const DpParams P)
     __syncwarp();
     unsigned char* path = P.path + J.path_off;
     for (uint32_t k = lane; k < n; k += 32) path[k] = tmp_path[n - 1 - k];
+    if (P.h_path) {                                                 // zero-copy: 16 path bytes per store over PCIe
+        unsigned char* hp = P.h_path + J.path_off;
+        const bool aligned = ((J.path_off | (unsigned long long)(size_t)P.h_path) & 15) == 0;
+        if (aligned) {
+            for (uint32_t k = lane * 16; k < n; k += 32 * 16) {
+                unsigned w[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (uint32_t b = 0; b < 16; ++b)
+                    if (k + b < n) w[b >> 2] |= (unsigned)tmp_path[n - 1 - (k + b)] << (8 * (b & 3));
+                *reinterpret_cast<uint4*>(hp + k) = make_uint4(w[0], w[1], w[2], w[3]);     // (the tail may spill up to 15 bytes into this job's own slack)
+            }
+        } else {
+            for (uint32_t k = lane; k < n; k += 32) hp[k] = tmp_path[n - 1 - k];
+        }
+    }
     if (lane == 0) {
         famsa_dp_result r;
         r.total_score = total;
@@ -908,8 +976,119 @@ __global__ void __launch_bounds__(kTraceWarps * 32) k_dp_trace(const DpParams P)
         r.path_len = n; r.rows_width = WR; r.cols_width = WC;
         r.swapped = (uint8_t)M.sw; r.variant = M.bad ? (uint8_t)0xFF : (uint8_t)M.var; r.pad[0] = r.pad[1] = 0;
         P.results[jid] = r;
+        if (P.h_results) P.h_results[jid] = r;
         if (J.w_dst) *J.w_dst = M.bad ? kWidthBad : n;              // the merged profile's width, for merges queued behind this one
     }
+}
+
+__global__ void __launch_bounds__(kTraceWarps * 32) k_dp_trace(const DpParams P)
+{
+    __shared__ __align__(16) unsigned char sm_tile[kTraceWarps][64 * 32];
+    const uint32_t warp = threadIdx.x / 32;
+    const uint32_t slot = blockIdx.x * kTraceWarps + warp;
+    if (slot >= P.n_jobs) return;
+    trace_body(P, P.job_base + slot, sm_tile[warp]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_merge_fused: a whole small merge in ONE block of four warps -- leaf materialisation, prep, the stripes, the
+// traceback and the merged tables, phase after phase with block barriers instead of kernel boundaries.  For the
+// chain-like parts of a guide tree, where a level is one small merge and five launches cost more than the work.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFusedWarps = 4;
+__device__ unsigned long long g_fused_phase_ns[8];          // development aid (FAMSA_FUSED_TIMING): per phase, the sum over launches of
+__device__ unsigned long long g_fused_phase_max[2][8];      // the slowest block's time; [launch parity][phase] collects one launch
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define FB_PHASE(k)                                                                     \
+    do {                                                                                \
+        if (F.timing && threadIdx.x == 0) {                                             \
+            const unsigned long long now__ = globaltimer_ns();                          \
+            atomicMax(&g_fused_phase_max[F.timing & 1][k], now__ - t_phase);            \
+            t_phase = now__;                                                            \
+        }                                                                               \
+    } while (0)
+__global__ void __launch_bounds__(kFusedWarps * 32, 1) k_merge_fused(const DpParams P, const FusedParams F)
+{
+    unsigned long long t_phase = F.timing ? globaltimer_ns() : 0;
+    const unsigned long long t_begin = t_phase;
+    if (F.timing && blockIdx.x == 0 && threadIdx.x == 0) {           // fold the previous launch (other parity) into the totals
+        const int q = (F.timing & 1) ^ 1;
+        for (int k = 0; k < 7; ++k) { g_fused_phase_ns[k] += g_fused_phase_max[q][k]; g_fused_phase_max[q][k] = 0; }
+        // slot 7 of a launch = when its last block ended (absolute): the idle time before this launch
+        if (g_fused_phase_max[q][7] && t_begin > g_fused_phase_max[q][7]) g_fused_phase_ns[7] += t_begin - g_fused_phase_max[q][7];
+        g_fused_phase_max[q][7] = 0;
+    }
+    extern __shared__ __align__(16) unsigned char sm_dyn[];
+    __shared__ __align__(16) unsigned char sm_tile[64 * 32];
+    __shared__ ConShared sm_con;
+    const uint32_t warp = threadIdx.x / 32;
+    const uint32_t jid = blockIdx.x;
+    const FusedJob fj = F.jobs[jid];
+    for (int side = 0; side < 2; ++side)
+        if (fj.leaf[side].seq != 0xffffffffu) leaf_body(fj.leaf[side], F.codes, F.off, F.len, F.sm, P.go, P.ge, P.to, P.te);
+    __syncthreads();
+    FB_PHASE(0);
+    prep_body(P, jid);
+    __syncthreads();
+    FB_PHASE(1);
+    fill_body(P, jid, warp, kFusedWarps, reinterpret_cast<WarpShared*>(sm_dyn)[warp]);
+    __syncthreads();
+    FB_PHASE(2);
+    // the traceback walks the direction bytes: bring the whole (skewed) matrix into the shared memory the fill no longer
+    // needs when it fits, so that the walk never waits for a tile
+    const unsigned char* all_dirs = nullptr;
+    {
+        const DpMeta M = P.meta[jid];
+        const unsigned long long bytes = (unsigned long long)((M.WR + 31) / 32) * ((unsigned long long)M.WC + 32) * 32;
+        if (M.bad != 2 && M.WR && bytes <= kFusedWarps * sizeof(WarpShared)) {
+            const uint4* src = reinterpret_cast<const uint4*>(P.sdirs + P.jobs[jid].t_off);
+            uint4* dst = reinterpret_cast<uint4*>(sm_dyn);
+            for (uint32_t q = threadIdx.x; q < bytes / 16; q += blockDim.x) dst[q] = __ldcg(src + q);
+            all_dirs = sm_dyn;
+        }
+    }
+    __syncthreads();
+    FB_PHASE(3);
+    if (warp == 0) trace_body(P, jid, sm_tile, all_dirs);
+    __syncthreads();
+    FB_PHASE(4);
+    ConJob J;
+    if (con_resolve(fj.con, P.meta[jid], P.results[jid], P.path, J))
+        for (uint32_t k0 = 0; k0 <= J.W; k0 += kConTile) construct_tile(J, k0, sm_con, P.go, P.ge, P.to, P.te);
+    FB_PHASE(5);
+    if (F.timing && threadIdx.x == 0) atomicMax(&g_fused_phase_max[F.timing & 1][6], globaltimer_ns() - t_begin);   // whole block
+    if (F.h_done) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();                                  // this block's records and paths are in host memory
+            if (atomicAdd(F.block_counter, 1u) == gridDim.x - 1) {
+                *F.block_counter = 0;
+                __threadfence_system();
+                *F.h_done = F.done_seq;
+            }
+        }
+    }
+    if (F.timing && threadIdx.x == 0) atomicMax(&g_fused_phase_max[F.timing & 1][7], globaltimer_ns());
+}
+#undef FB_PHASE
+
+// development aid (not part of the ABI): accumulated nanoseconds of block 0 per phase of k_merge_fused since the last call
+// -- leaves, prep, fill, load of the direction bytes, traceback, merged tables; active when FAMSA_FUSED_TIMING is set
+extern "C" int famsa_debug_fused_phases(double out_ns[8])
+{
+    unsigned long long h[8], m[2][8];
+    if (cudaMemcpyFromSymbol(h, g_fused_phase_ns, sizeof(h)) != cudaSuccess) return 1;
+    if (cudaMemcpyFromSymbol(m, g_fused_phase_max, sizeof(m)) != cudaSuccess) return 1;
+    for (int k = 0; k < 7; ++k) out_ns[k] = (double)(h[k] + m[0][k] + m[1][k]);
+    out_ns[7] = (double)h[7];
+    memset(h, 0, sizeof(h)); memset(m, 0, sizeof(m));
+    if (cudaMemcpyToSymbol(g_fused_phase_max, m, sizeof(m)) != cudaSuccess) return 1;
+    return cudaMemcpyToSymbol(g_fused_phase_ns, h, sizeof(h)) == cudaSuccess ? 0 : 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -979,11 +1158,65 @@ static uint32_t max_cluster4(famsa_ctx* ctx)
     return (uint32_t)v;
 }
 
+// ---- the fused path (k_merge_fused): planning and launch are separate so that the caller can place the descriptors in
+// mapped host memory and every device buffer in its own ring (no copy, no allocator call per batch)
+int dp_fused_plan(const famsa_dp_job* jobs, const DpJobExt* ext, uint32_t n, bool align16, DpJobDev* out, DpFusedPlan* plan)
+{
+    unsigned long long path_off = 0, scratch_off = 0, t_off = 0, cells = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const famsa_dp_job& j = jobs[k];
+        if (j.p1.width == 0 || j.p2.width == 0 || j.p1.card == 0 || j.p2.card == 0) { set_error("dp job " + std::to_string(k) + ": empty profile"); return FAMSA_E_INVALID; }
+        DpJobDev& d = out[k];
+        d.s1 = reinterpret_cast<const long long*>(j.p1.scores); d.c1 = j.p1.counters;
+        d.s2 = reinterpret_cast<const long long*>(j.p2.scores); d.c2 = j.p2.counters;
+        d.w1 = j.p1.width; d.card1 = j.p1.card; d.w2 = j.p2.width; d.card2 = j.p2.card;
+        d.w1_src = ext ? ext[k].w1_src : nullptr; d.w2_src = ext ? ext[k].w2_src : nullptr; d.w_dst = ext ? ext[k].w_dst : nullptr;
+        d.path_off = path_off; d.dirs_off = 0;
+        d.scratch_off = scratch_off; d.t_off = t_off;
+        path_off += align16 ? align_up((unsigned long long)d.w1 + d.w2, 16) : (unsigned long long)d.w1 + d.w2;   // 16-byte slots: the traceback
+                                                                       // then stores paths to the host in uint4 units
+        scratch_off += Scratch(d.w1, d.w2).total;
+        t_off += skew_elems(d.w1, d.w2);
+        cells += (unsigned long long)d.w1 * d.w2;
+    }
+    plan->scratch_bytes = scratch_off; plan->skew_bytes = t_off; plan->path_bytes = path_off; plan->cells = cells;
+    return FAMSA_OK;
+}
+
+int dp_fused_launch(famsa_ctx* ctx, const DpJobDev* jobs, uint32_t n, const int64_t gaps[4], famsa_dp_result* d_results, uint8_t* d_path,
+                    DpMeta* d_meta, uint8_t* d_scratch, uint8_t* d_skew, famsa_dp_result* h_results, uint8_t* h_path,
+                    const void* fused_params, uint64_t cells, bool record_events, cudaStream_t st)
+{
+    static std::atomic<bool> configured[64];
+    if (!configured[ctx->device & 63].load(std::memory_order_acquire)) {
+        FB_CUDA(cudaFuncSetAttribute(k_merge_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFusedWarps * sizeof(WarpShared))));
+        configured[ctx->device & 63].store(true, std::memory_order_release);
+    }
+    ctx->dp.last_cells = cells;
+    DpParams P{};
+    P.jobs = jobs;
+    P.meta = d_meta;
+    P.n_jobs = n;
+    P.go = gaps[0]; P.ge = gaps[1]; P.to = gaps[2]; P.te = gaps[3];
+    P.sdirs = d_skew;
+    P.path = d_path;
+    P.scratch = d_scratch;
+    P.results = d_results;
+    P.h_results = h_results;
+    P.h_path = h_path;
+    if (record_events) { FB_CUDA(cudaEventRecord(ctx->ev[0], st)); FB_CUDA(cudaEventRecord(ctx->ev[1], st)); }
+    k_merge_fused<<<n, kFusedWarps * 32, kFusedWarps * sizeof(WarpShared), st>>>(P, *static_cast<const FusedParams*>(fused_params));
+    FB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    if (record_events) { FB_CUDA(cudaEventRecord(ctx->ev[2], st)); FB_CUDA(cudaEventRecord(ctx->ev[3], st)); }
+    return FAMSA_OK;
+}
+
 // Bytes of stream-ordered scratch one call of dp_run_device needs at most (it sub-batches above ~1 Gi cells).
 // jobs[k].p1/p2 hold DEVICE pointers here; widths are the layout widths (upper bounds when ext[k].w*_src is set).
 int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext, uint32_t n, const int64_t gaps[4],
                   famsa_dp_result* d_results, uint8_t* d_path, uint8_t* d_dirs, DpMeta** d_meta_out, void** d_blob_out,
-                  cudaStream_t st)
+                  cudaStream_t st, const void* fused)
 {
     DpState& S = ctx->dp;
     std::vector<DpJobDev> dev(n);
@@ -1024,6 +1257,13 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext,
     FB_TRY((configure_fill<kDpTeamWarps, false>(ctx)));
     FB_TRY((configure_fill<4, true>(ctx)));
     FB_TRY((configure_fill<kDpTeamWarps, true>(ctx)));
+    {
+        static std::atomic<bool> configured[64];
+        if (!configured[ctx->device & 63].load(std::memory_order_acquire)) {
+            FB_CUDA(cudaFuncSetAttribute(k_merge_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFusedWarps * sizeof(WarpShared))));
+            configured[ctx->device & 63].store(true, std::memory_order_release);
+        }
+    }
 
     // plan the sub-batches first: one stream-ordered allocation serves all of them
     struct Sub { uint32_t j0, j1; unsigned long long scratch, skew; std::vector<unsigned long long> tblock; };
@@ -1076,6 +1316,26 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext,
     FB_CUDA(cudaEventRecord(ctx->ev[0], st));
     FB_CUDA(cudaEventRecord(ctx->ev[1], st));
     if (n) FB_CUDA(cudaMemcpyAsync(d_jobs, dev.data(), sizeof(DpJobDev) * n, cudaMemcpyHostToDevice, st));
+    if (fused) {
+        if (subs.size() != 1 || d_dirs) { set_error("internal: a fused batch must be one sub-batch without CDPMatrix output"); cudaFreeAsync(blob, st); return FAMSA_E_INVALID; }
+        DpParams P{};
+        P.jobs = d_jobs;
+        P.meta = d_meta;
+        P.order = nullptr;
+        P.n_jobs = n;
+        P.job_base = 0;
+        P.go = gaps[0]; P.ge = gaps[1]; P.to = gaps[2]; P.te = gaps[3];
+        P.dirs = nullptr;
+        P.sdirs = blob + o_skew;
+        P.path = d_path;
+        P.scratch = blob + o_scratch;
+        P.tblock = nullptr;
+        P.results = d_results;
+        k_merge_fused<<<n, kFusedWarps * 32, kFusedWarps * sizeof(WarpShared), st>>>(P, *static_cast<const FusedParams*>(fused));
+        FB_CUDA(cudaGetLastError());
+        ctx->launches++;
+        subs.clear();
+    }
     for (const Sub& sb : subs) {
         const uint32_t j0 = sb.j0, j1 = sb.j1, m = j1 - j0;
         // rows of the DP matrix as far as the host can tell (the orientation of ProfProf merges is decided on the device)

@@ -40,6 +40,8 @@ struct DpJobExt {
     uint32_t* w_dst;
 };
 
+struct DpFusedPlan { unsigned long long scratch_bytes, skew_bytes, path_bytes, cells; };
+
 struct DpMeta {            // written by k_dp_prep
     const long long* SR; const int* CR;        // row profile of the DP matrix (after the orientation swap)
     const long long* SC; const int* CC;        // column profile

@@ -24,10 +24,13 @@
 #include <cstring>
 #include <numeric>
 
+#include <atomic>
 #include <chrono>
+#include <cstdio>
 #include <deque>
 
 #include "ctx.h"
+#include "prof_dev.cuh"
 
 namespace fb {
 
@@ -39,81 +42,13 @@ namespace fb {
 
 namespace {
 
-constexpr int kRows = 32;                 // NO_SYMBOLS, defs.h:69
-constexpr int kGO = 25, kGE = 26, kTE = 27, kTO = 28, kGAP = 30, kNAA = 24;   // defs.h:62-74
-constexpr int kConThreads = 256, kConTile = 64;
-constexpr size_t kColBytes = kRows * (sizeof(long long) + sizeof(int));        // 384 B per profile column
-
-struct LeafDesc {
-    uint32_t seq;
-    long long* scores;
-    int* counters;
-};
-
-// One block per leaf: CalculateCounters + CalculateScores for a profile of one ungapped sequence
-// (profile.cpp:101-217): column c >= 1 holds counter 1 at its residue, the residue's substitution row in
-// scores[0..23] and the four gap costs; column 0 holds card(=1) x gap costs.
 __global__ void __launch_bounds__(256) k_prof_leaf(const LeafDesc* __restrict__ leaves, const int8_t* __restrict__ codes,
                                                    const uint64_t* __restrict__ off, const uint32_t* __restrict__ len,
                                                    const long long* __restrict__ sm, long long go, long long ge,
                                                    long long to, long long te)
 {
-    const LeafDesc L = leaves[blockIdx.x];
-    const uint32_t n = len[L.seq];
-    const int8_t* s = codes + off[L.seq];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long gapv = lane == kGO ? go : lane == kGE ? ge : lane == kTE ? te : lane == kTO ? to : 0;
-    for (uint32_t c = warp; c <= n; c += 8) {
-        long long sc = gapv;
-        int cn = 0;
-        if (c) {
-            int sym = s[c - 1];
-            if (sym < 0 || sym >= kNAA) sym = 22;                      // anything outside the alphabet counts as UNKNOWN
-            cn = lane == sym;
-            if (lane < kNAA) sc = sm[sym * kNAA + lane];
-        }
-        L.scores[(size_t)c * kRows + lane] = sc;
-        L.counters[(size_t)c * kRows + lane] = cn;
-    }
+    leaf_body(leaves[blockIdx.x], codes, off, len, sm, go, ge, to, te);
 }
-
-// One merge of a batch for k_prof_construct.  Everything that depends on the outcome of the DP -- which child is the row
-// profile, the real widths, the merged width -- is read on the device from the DP's own records, so the kernel can be
-// queued right behind the fill without the host looking at the results first.
-struct ConJobDev {
-    long long* os; int* oc;                // merged profile, sized for the upper bound w1 + w2
-    uint32_t job;                          // index into meta / results
-    uint32_t tile0;                        // first block of this merge (tiles counted with the upper bound)
-};
-
-struct GapSplit { int o, e, to, te; };
-
-// Column of gaps inserted into a child (counters `c`, width `w`, `card` members) after its column `src`.
-// col / nxt: this lane's counters of columns src and src+1 (nxt = 0 past the end).
-__device__ __forceinline__ GapSplit gap_split(int col, int nxt, uint32_t src, uint32_t w, int card, bool starts)
-{
-    const int go_s = __shfl_sync(0xffffffffu, col, kGO), ge_s = __shfl_sync(0xffffffffu, col, kGE);
-    const int to_s = __shfl_sync(0xffffffffu, col, kTO), te_s = __shfl_sync(0xffffffffu, col, kTE);
-    const int to_n = __shfl_sync(0xffffffffu, nxt, kTO);
-    GapSplit g{0, 0, 0, 0};
-    if (starts) {
-        if (src == 0) g.to = card;
-        else if (src >= w) { g.te = to_s + te_s; g.to = card - g.te; }
-        else { g.to = to_n; g.te = to_s + te_s; g.e = go_s + ge_s; g.o = card - g.e - g.to - g.te; }
-    } else {
-        if (src == 0 || src == w) g.te = card;
-        else { g.te = to_n + to_s + te_s; g.e = card - g.te; }
-    }
-    return g;
-}
-
-struct ConJob {                            // resolved on the device at the top of k_prof_construct
-    const long long* sr; const int* cr;    // row child (ConstructProfile's profile1)
-    const long long* sc; const int* cc;    // column child (profile2)
-    long long* os; int* oc;                // merged profile
-    const uint8_t* path;
-    uint32_t wr, wc, cardr, cardc, W, tile0;
-};
 
 __global__ void __launch_bounds__(kConThreads) k_prof_construct(const ConJobDev* __restrict__ jobs, uint32_t n_jobs,
                                                                 const DpMeta* __restrict__ meta,
@@ -121,6 +56,7 @@ __global__ void __launch_bounds__(kConThreads) k_prof_construct(const ConJobDev*
                                                                 const uint8_t* __restrict__ path_base,
                                                                 long long go, long long ge, long long to, long long te)
 {
+    __shared__ ConShared S;
     // block -> (job, tile of kConTile merged columns)
     uint32_t lo = 0, hi = n_jobs;
     while (hi - lo > 1) {
@@ -128,97 +64,75 @@ __global__ void __launch_bounds__(kConThreads) k_prof_construct(const ConJobDev*
         if (jobs[mid].tile0 <= blockIdx.x) lo = mid; else hi = mid;
     }
     ConJob J;
-    {
-        const ConJobDev D = jobs[lo];
-        const DpMeta M = meta[D.job];
-        const famsa_dp_result r = results[D.job];
-        if (M.bad || r.variant == 0xFF) return;
-        J.sr = M.SR; J.cr = M.CR; J.sc = M.SC; J.cc = M.CC; J.os = D.os; J.oc = D.oc;
-        J.path = path_base + r.path_offset;
-        J.wr = M.WR; J.wc = M.WC; J.cardr = (uint32_t)M.nR; J.cardc = (uint32_t)M.nC; J.W = r.path_len; J.tile0 = D.tile0;
-    }
+    const ConJobDev D = jobs[lo];
+    if (!con_resolve(D, meta[D.job], results[D.job], path_base, J)) return;
     const uint32_t k0 = (blockIdx.x - J.tile0) * kConTile;          // first merged column of the tile (0 = column 0)
     if (k0 > J.W) return;                                           // the tiles were counted with the upper bound
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    __shared__ uint32_t s_cnt[2][kConThreads / 32];
-    __shared__ uint8_t s_dir[kConTile + 1];                         // s_dir[t] = path[k0 + t - 2]  (dir of column k0+t-1)
-    __shared__ uint32_t s_nh[kConTile], s_nv[kConTile];
-
-    // H / V counts over the path entries of the columns before the tile: path[0 .. k0-2]
-    const uint32_t before = k0 ? k0 - 1 : 0;
-    uint32_t nh = 0, nv = 0;
-    for (uint32_t p = threadIdx.x; p < before; p += kConThreads) {
-        const uint8_t d = J.path[p];
-        nh += d == 1; nv += d == 2;
-    }
-    for (int o = 16; o; o >>= 1) { nh += __shfl_xor_sync(0xffffffffu, nh, o); nv += __shfl_xor_sync(0xffffffffu, nv, o); }
-    if (lane == 0) { s_cnt[0][warp] = nh; s_cnt[1][warp] = nv; }
-    if (threadIdx.x <= kConTile) {
-        const long long p = (long long)k0 + threadIdx.x - 2;
-        s_dir[threadIdx.x] = (p >= 0 && p < (long long)J.W) ? J.path[p] : 0;      // "previous" of the first column is D
-    }
-    __syncthreads();
-    nh = nv = 0;
-    for (int w = 0; w < kConThreads / 32; ++w) { nh += s_cnt[0][w]; nv += s_cnt[1][w]; }
-    if (threadIdx.x < kConTile) {
-        // inclusive counts up to and including the direction of column k0 + threadIdx.x
-        uint32_t a = nh, b = nv;
-        for (uint32_t u = (k0 ? 0 : 1); u <= threadIdx.x; ++u) { a += s_dir[u + 1] == 1; b += s_dir[u + 1] == 2; }
-        s_nh[threadIdx.x] = a; s_nv[threadIdx.x] = b;
-    }
-    __syncthreads();
-
-    const long long tr_open = ge - go, tr_term = te - to;
-    for (int t = warp; t < kConTile; t += kConThreads / 32) {
-        const uint32_t k = k0 + t;
-        if (k > J.W) break;
-        long long os = 0;
-        int oc = 0;
-        if (k == 0) {                                               // profile.cpp:998-1001
-            const long long tot = (long long)J.cardr + J.cardc;
-            os = lane == kGO ? go * tot : lane == kGE ? ge * tot : lane == kTO ? to * tot : lane == kTE ? te * tot : 0;
-        } else {
-            const int d = s_dir[t + 1], prev = s_dir[t];
-            const uint32_t i = k - s_nh[t], j = k - s_nv[t];        // child columns consumed after this step
-            if (d != 1) {                                           // D or V: the row child's column i
-                const int c = J.cr[(size_t)i * kRows + lane];
-                long long s = J.sr[(size_t)i * kRows + lane];
-                int tt = __shfl_sync(0xffffffffu, c, kTO), tg = __shfl_sync(0xffffffffu, c, kGO);
-                if (prev != 1) tt = tg = 0;
-                if (i == 1) tg = 0;                                 // the run sat before the first column: terminal only
-                oc += c + (lane == kGE ? tg : lane == kGO ? -tg : lane == kTE ? tt : lane == kTO ? -tt : 0);
-                if (lane < kNAA) s += tg * tr_open + tt * tr_term;
-                os += s;
-            }
-            if (d != 2) {                                           // D or H: the column child's column j
-                const int c = J.cc[(size_t)j * kRows + lane];
-                long long s = J.sc[(size_t)j * kRows + lane];
-                int tt = __shfl_sync(0xffffffffu, c, kTO), tg = __shfl_sync(0xffffffffu, c, kGO);
-                if (prev != 2) tt = tg = 0;
-                if (j == 1) tg = 0;
-                oc += c + (lane == kGE ? tg : lane == kGO ? -tg : lane == kTE ? tt : lane == kTO ? -tt : 0);
-                if (lane < kNAA) s += tg * tr_open + tt * tr_term;
-                os += s;
-            }
-            if (d != 0) {                                           // a column of gaps in the row (H) / column (V) child
-                const bool isH = d == 1;
-                const int* cg = isH ? J.cr : J.cc;
-                const uint32_t src = isH ? i : j, w = isH ? J.wr : J.wc;
-                const int card = (int)(isH ? J.cardr : J.cardc);
-                const int col = cg[(size_t)src * kRows + lane];
-                const int nxt = src < w ? cg[(size_t)(src + 1) * kRows + lane] : 0;
-                const GapSplit g = gap_split(col, nxt, src, w, card, prev != d);
-                oc += lane == kGO ? g.o : lane == kGE ? g.e : lane == kTO ? g.to : lane == kTE ? g.te : lane == kGAP ? card : 0;
-                if (lane < kNAA) os += g.o * go + g.e * ge + g.to * to + g.te * te;
-            }
-        }
-        J.os[(size_t)k * kRows + lane] = os;
-        J.oc[(size_t)k * kRows + lane] = oc;
-    }
+    construct_tile(J, k0, S, go, ge, to, te);
 }
 
 size_t table_bytes(uint32_t width) { return ((size_t)width + 1) * kColBytes; }
+
+} // namespace
+
+void* DevArena::alloc(size_t n)
+{
+    n = (n + 511) & ~(size_t)511;
+    auto it = free_by_size.lower_bound(n);
+    if (it == free_by_size.end()) {
+        const size_t want = std::max(n, chunk_bytes);
+        char* base = nullptr;
+        if (cudaMalloc(reinterpret_cast<void**>(&base), want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        chunks.push_back(Chunk{base, want});
+        free_by_addr[base] = {want, (int)chunks.size() - 1};
+        it = free_by_size.emplace(want, base);
+    }
+    char* p = it->second;
+    const size_t have = it->first;
+    free_by_size.erase(it);
+    const int chunk = free_by_addr[p].second;
+    free_by_addr.erase(p);
+    if (have > n) {
+        free_by_addr[p + n] = {have - n, chunk};
+        free_by_size.emplace(have - n, p + n);
+    }
+    return p;
+}
+
+void DevArena::free(void* ptr, size_t n)
+{
+    n = (std::max<size_t>(n, 256) + 511) & ~(size_t)511;
+    char* p = static_cast<char*>(ptr);
+    int chunk = -1;
+    for (size_t c = 0; c < chunks.size(); ++c)
+        if (p >= chunks[c].base && p < chunks[c].base + chunks[c].bytes) { chunk = (int)c; break; }
+    // merge with the free neighbours of the same chunk
+    auto nx = free_by_addr.lower_bound(p);
+    if (nx != free_by_addr.end() && nx->first == p + n && nx->second.second == chunk) {
+        erase_size(nx->second.first, nx->first);
+        n += nx->second.first;
+        nx = free_by_addr.erase(nx);
+    }
+    if (nx != free_by_addr.begin()) {
+        auto pv = std::prev(nx);
+        if (pv->first + pv->second.first == p && pv->second.second == chunk) {
+            erase_size(pv->second.first, pv->first);
+            p = pv->first;
+            n += pv->second.first;
+            free_by_addr.erase(pv);
+        }
+    }
+    free_by_addr[p] = {n, chunk};
+    free_by_size.emplace(n, p);
+}
+
+void DevArena::release_all()
+{
+    for (Chunk& c : chunks) cudaFree(c.base);
+    chunks.clear(); free_by_addr.clear(); free_by_size.clear();
+}
+
+namespace {
 
 int ensure_pool(famsa_ctx* ctx)
 {
@@ -237,10 +151,10 @@ int ensure_pool(famsa_ctx* ctx)
 int new_slab(famsa_ctx* ctx, size_t bytes, int* out)
 {
     ProfState& P = ctx->prof;
-    void* p = nullptr;
-    cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(bytes, 256), ctx->stream);
-    if (e != cudaSuccess) {
-        set_error(std::string("cudaMallocAsync(") + std::to_string(bytes) + ") for resident profiles failed: " + cudaGetErrorString(e));
+    bytes = std::max<size_t>(bytes, 256);
+    void* p = P.arena.alloc(bytes);
+    if (!p) {
+        set_error("no device memory for " + std::to_string(bytes) + " bytes of resident profiles");
         return FAMSA_E_NOMEM;
     }
     int id;
@@ -280,7 +194,7 @@ int release_entry(famsa_ctx* ctx, uint32_t id)
     --P.n_live;
     ProfSlab& s = P.slabs[e.slab];
     if (--s.live == 0) {
-        FB_CUDA(cudaFreeAsync(s.p, ctx->stream));                   // stream-ordered: after the kernels that read it
+        P.arena.free(s.p, s.bytes);                                  // reusable by batches queued from now on (stream order)
         P.resident_bytes -= s.bytes;
         s.p = nullptr; s.bytes = 0;
         P.free_slabs.push_back(e.slab);
@@ -363,8 +277,26 @@ static cudaEvent_t take_event(ProfState& P)
 // (dp.cu), merged tables (k_prof_construct), then one copy of the result records and paths into h_results / h_paths
 // (pinned memory makes that copy asynchronous too).  Children may be profiles of batches that are still queued -- their
 // widths are then upper bounds on the host and are resolved on the device.  The merged profiles are sized for w1 + w2.
+static int ensure_rings(famsa_ctx* ctx)
+{
+    ProfState& P = ctx->prof;
+    if (P.h_ring_mem) return FAMSA_OK;
+    const size_t hcap = 8u << 20, dcap = 512u << 20;
+    FB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&P.h_ring_mem), hcap, cudaHostAllocMapped));
+    P.h_ring.cap = hcap;
+    FB_TRY(P.d_ring_mem.reserve(dcap));
+    P.d_ring.cap = dcap;
+    FB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(const_cast<unsigned long long**>(&P.h_done)), 64, cudaHostAllocMapped));
+    *P.h_done = 0;
+    FB_TRY(P.d_block_counter.reserve(64));
+    FB_CUDA(cudaMemsetAsync(P.d_block_counter.p, 0, 64, ctx->stream));
+    return FAMSA_OK;
+}
+
+// host_mapped: h_results / h_paths are mapped pinned memory the device may write to directly (and path slots are 16-byte
+// aligned: job k's path at the running sum of align16(w1 + w2))
 static int prof_launch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t n, const int64_t gaps[4],
-                       famsa_dp_result* h_results, uint8_t* h_paths, uint64_t path_cap, ProfTicket* T)
+                       famsa_dp_result* h_results, uint8_t* h_paths, uint64_t path_cap, bool host_mapped, ProfTicket* T)
 {
     ProfState& P = ctx->prof;
     LcsState& L = ctx->lcs;
@@ -406,21 +338,114 @@ static int prof_launch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t 
         path_need += (uint64_t)jobs[k].p1.width + jobs[k].p2.width;
         cells += (uint64_t)jobs[k].p1.width * jobs[k].p2.width;
     }
+    // A batch of small merges only (the chain-like parts of a guide tree: every level one or a few short merges) runs
+    // every merge whole in one block of k_merge_fused instead of five launches.
+    bool fused = n <= 4096;
+    for (uint32_t k = 0; k < n && fused; ++k) {
+        const famsa_dp_job& j = jobs[k];
+        const uint32_t rows = j.p1.card == 1 ? j.p1.width : (j.p2.card == 1 ? j.p2.width : std::min(j.p1.width, j.p2.width));
+        fused = rows <= 256 && std::max(j.p1.width, j.p2.width) <= 8192;
+    }
+    if (const char* e = getenv("FAMSA_PROF_FUSED")) fused = fused && atoi(e) != 0;                  // development knob
+    if (host_mapped) {
+        path_need = 0;
+        for (uint32_t k = 0; k < n; ++k) path_need += align_up((uint64_t)jobs[k].p1.width + jobs[k].p2.width, 16);
+    }
     if (path_need > path_cap) {
         set_error("famsa_prof_merge_batch: path_buf holds " + std::to_string(path_cap) + " bytes, " + std::to_string(path_need) + " needed");
         return FAMSA_E_INVALID;
     }
     FB_TRY(ensure_widths(ctx, P.entries.size() + n));
+    if (fused) {
+        // ---- ring-backed fast path: descriptors in mapped host memory, every device buffer from the device ring, results and
+        // paths written to the host by the kernel itself when the caller's buffers allow it; one launch, no copy, no allocator call
+        FB_TRY(ensure_rings(ctx));
+        std::vector<DpJobDev> plan_jobs(n);
+        DpFusedPlan plan;
+        FB_TRY(dp_fused_plan(jobs.data(), ext.data(), n, host_mapped, plan_jobs.data(), &plan));
+        const size_t h_bytes = align_up(sizeof(DpJobDev) * n, 256) + sizeof(FusedJob) * n;
+        const size_t o_res = 0;
+        const size_t o_meta = align_up(o_res + sizeof(famsa_dp_result) * n, 256);
+        const size_t o_path = align_up(o_meta + sizeof(DpMeta) * n, 256);
+        const size_t o_leaf = align_up(o_path + std::max<uint64_t>(plan.path_bytes, 1), 256);
+        const size_t o_scr = align_up(o_leaf + leaf_bytes, 256);
+        const size_t o_skew = align_up(o_scr + plan.scratch_bytes, 256);
+        const size_t d_bytes = o_skew + plan.skew_bytes;
+        const Ring h_save = P.h_ring, d_save = P.d_ring;
+        const size_t h_off = P.h_ring.alloc(h_bytes);
+        const size_t d_off = h_off == (size_t)-1 ? (size_t)-1 : P.d_ring.alloc(d_bytes);
+        if (h_off == (size_t)-1 || d_off == (size_t)-1) { P.h_ring = h_save; P.d_ring = d_save; fused = false; }
+        else {
+            int slab;
+            size_t slab_bytes = 0;
+            for (uint32_t k = 0; k < n; ++k) slab_bytes += table_bytes(jobs[k].p1.width + jobs[k].p2.width);
+            FB_TRY(new_slab(ctx, slab_bytes, &slab));
+            unsigned char* hb = P.h_ring_mem + h_off;
+            unsigned char* db = P.d_ring_mem.as<unsigned char>() + d_off;
+            DpJobDev* hj = reinterpret_cast<DpJobDev*>(hb);
+            FusedJob* fj = reinterpret_cast<FusedJob*>(hb + align_up(sizeof(DpJobDev) * n, 256));
+            famsa_dp_result* d_results = reinterpret_cast<famsa_dp_result*>(db + o_res);
+            for (uint32_t k = 0; k < n; ++k) fj[k].leaf[0].seq = fj[k].leaf[1].seq = 0xffffffffu;
+            size_t cur = 0;
+            for (size_t a = 0; a < leaves.size(); ++a) {
+                const uint32_t k = leaf_slot[a].first;
+                const int side = leaf_slot[a].second;
+                const uint32_t w = side ? jobs[k].p2.width : jobs[k].p1.width;
+                char* base = reinterpret_cast<char*>(db + o_leaf + cur);
+                leaves[a].scores = reinterpret_cast<long long*>(base);
+                leaves[a].counters = reinterpret_cast<int*>(base + ((size_t)w + 1) * kRows * sizeof(long long));
+                (side ? plan_jobs[k].s2 : plan_jobs[k].s1) = leaves[a].scores;
+                (side ? plan_jobs[k].c2 : plan_jobs[k].c1) = leaves[a].counters;
+                fj[k].leaf[side] = leaves[a];
+                cur += table_bytes(w);
+            }
+            T->merged_ids.assign(n, 0);
+            T->merged_gen.assign(n, 0);
+            cur = 0;
+            for (uint32_t k = 0; k < n; ++k) {
+                const uint32_t ub = jobs[k].p1.width + jobs[k].p2.width;
+                const uint32_t id = new_entry(P);
+                place(P, id, slab, &cur, ub, jobs[k].p1.card + jobs[k].p2.card);
+                P.entries[id].pending = true;
+                T->merged_ids[k] = id;
+                T->merged_gen[k] = P.entries[id].gen;
+                plan_jobs[k].w_dst = P.d_widths.as<uint32_t>() + id;
+                fj[k].con.os = P.entries[id].scores; fj[k].con.oc = P.entries[id].counters; fj[k].con.job = k; fj[k].con.tile0 = 0;
+            }
+            memcpy(hj, plan_jobs.data(), sizeof(DpJobDev) * n);          // (write-combined order does not matter: the launch orders it)
+            FusedParams FP{fj, L.d_raw_codes.as<int8_t>(), L.d_raw_off.as<uint64_t>(), L.d_raw_len.as<uint32_t>(), P.d_sm.as<long long>(),
+                           0, P.d_block_counter.as<unsigned>(), nullptr, 0};
+            if (host_mapped) { FP.h_done = P.h_done; FP.done_seq = ++P.done_seq; }
+            if (getenv("FAMSA_FUSED_TIMING")) { static int launch_no = 0; FP.timing = 2 + (++launch_no & 1); }   // development aid
+            if (!host_mapped) { FB_CUDA(cudaEventRecord(P.ev[0], st)); FB_CUDA(cudaEventRecord(P.ev[1], st)); }
+            FB_TRY(dp_fused_launch(ctx, hj, n, gaps, d_results, db + o_path, reinterpret_cast<DpMeta*>(db + o_meta), db + o_scr, db + o_skew,
+                                   host_mapped ? h_results : nullptr, host_mapped ? h_paths : nullptr, &FP, plan.cells, !host_mapped, st));
+            if (!host_mapped) { FB_CUDA(cudaEventRecord(P.ev[2], st)); P.timing_valid = true; }
+            if (!host_mapped) {
+                FB_CUDA(cudaMemcpyAsync(h_results, d_results, sizeof(famsa_dp_result) * n, cudaMemcpyDeviceToHost, st));
+                if (plan.path_bytes) FB_CUDA(cudaMemcpyAsync(h_paths, db + o_path, plan.path_bytes, cudaMemcpyDeviceToHost, st));
+            }
+            for (uint32_t k = 0; k < n; ++k)
+                for (uint32_t c : {merges[k].child1, merges[k].child2})
+                    if (!(c & FAMSA_PROF_LEAF)) FB_TRY(release_entry(ctx, c));
+            if (host_mapped) T->done_seq = FP.done_seq;
+            else { T->done = take_event(P); FB_CUDA(cudaEventRecord(T->done, st)); }
+            T->n = n; T->h_results = h_results; T->h_paths = h_paths; T->path_bytes = plan.path_bytes; T->cells_bound = plan.cells;
+            T->ring_host_end = P.h_ring.head; T->ring_dev_end = P.d_ring.head;
+            return FAMSA_OK;
+        }
+    }
 
     // merged tables: one slab per batch, every profile sized for the widest alignment possible (w1 + w2 columns)
     size_t slab_bytes = 0;
     for (uint32_t k = 0; k < n; ++k) slab_bytes += table_bytes(jobs[k].p1.width + jobs[k].p2.width);
     int slab;
     FB_TRY(new_slab(ctx, slab_bytes, &slab));
+    fused = false;                                                   // (the launch-by-launch path below)
     // batch blob: [results][con jobs][leaf descs][paths][leaf tables]
     const size_t o_res = 0;
     const size_t o_con = align_up(o_res + sizeof(famsa_dp_result) * n, 256);
-    const size_t o_leafd = align_up(o_con + sizeof(ConJobDev) * n, 256);
+    const size_t o_leafd = align_up(o_con + (fused ? sizeof(FusedJob) : sizeof(ConJobDev)) * n, 256);
     const size_t o_path = align_up(o_leafd + sizeof(LeafDesc) * leaves.size(), 256);
     const size_t o_leaf = align_up(o_path + std::max<uint64_t>(path_need, 1), 256);
     const size_t blob_bytes = o_leaf + leaf_bytes;
@@ -433,8 +458,12 @@ static int prof_launch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t 
     uint8_t* d_path = blob + o_path;
 
     std::vector<unsigned char> pack(o_path - o_con);
-    ConJobDev* cj = reinterpret_cast<ConJobDev*>(pack.data());
+    std::vector<ConJobDev> cj_store(n);
+    ConJobDev* cj = cj_store.data();
+    FusedJob* fj = reinterpret_cast<FusedJob*>(pack.data());
     LeafDesc* ld = reinterpret_cast<LeafDesc*>(pack.data() + (o_leafd - o_con));
+    if (fused)
+        for (uint32_t k = 0; k < n; ++k) fj[k].leaf[0].seq = fj[k].leaf[1].seq = 0xffffffffu;
     {
         size_t cur = 0;
         for (size_t a = 0; a < leaves.size(); ++a) {
@@ -446,6 +475,7 @@ static int prof_launch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t 
             p.counters = leaves[a].counters;
             cur += table_bytes(p.width);
             ld[a] = leaves[a];
+            if (fused) fj[leaf_slot[a].first].leaf[leaf_slot[a].second] = leaves[a];
         }
     }
     T->merged_ids.assign(n, 0);
@@ -462,10 +492,12 @@ static int prof_launch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t 
         ext[k].w_dst = P.d_widths.as<uint32_t>() + id;
         cj[k].os = P.entries[id].scores; cj[k].oc = P.entries[id].counters; cj[k].job = k; cj[k].tile0 = tiles;
         tiles += (ub + 1 + kConTile - 1) / kConTile;
+        if (fused) fj[k].con = cj[k];
     }
+    if (!fused) memcpy(pack.data(), cj, sizeof(ConJobDev) * n);
     FB_CUDA(cudaEventRecord(P.ev[0], st));
     FB_CUDA(cudaMemcpyAsync(blob + o_con, pack.data(), pack.size(), cudaMemcpyHostToDevice, st));
-    if (!leaves.empty()) {
+    if (!leaves.empty() && !fused) {
         k_prof_leaf<<<(unsigned)leaves.size(), 256, 0, st>>>(reinterpret_cast<const LeafDesc*>(blob + o_leafd), L.d_raw_codes.as<int8_t>(),
                                                              L.d_raw_off.as<uint64_t>(), L.d_raw_len.as<uint32_t>(),
                                                              P.d_sm.as<long long>(), gaps[0], gaps[1], gaps[2], gaps[3]);
@@ -475,12 +507,16 @@ static int prof_launch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t 
     // DP + traceback on the resident tables (dp.cu)
     DpMeta* d_meta = nullptr;
     void* dp_blob = nullptr;
-    FB_TRY(dp_run_device(ctx, jobs.data(), ext.data(), n, gaps, d_results, d_path, nullptr, &d_meta, &dp_blob, st));
+    FusedParams FP{reinterpret_cast<const FusedJob*>(blob + o_con), L.d_raw_codes.as<int8_t>(), L.d_raw_off.as<uint64_t>(),
+                   L.d_raw_len.as<uint32_t>(), P.d_sm.as<long long>(), getenv("FAMSA_FUSED_TIMING") ? 1 : 0};
+    FB_TRY(dp_run_device(ctx, jobs.data(), ext.data(), n, gaps, d_results, d_path, nullptr, &d_meta, &dp_blob, st, fused ? &FP : nullptr));
     FB_CUDA(cudaEventRecord(P.ev[1], st));
-    k_prof_construct<<<tiles, kConThreads, 0, st>>>(reinterpret_cast<const ConJobDev*>(blob + o_con), n, d_meta, d_results, d_path,
-                                                    gaps[0], gaps[1], gaps[2], gaps[3]);
-    FB_CUDA(cudaGetLastError());
-    ++ctx->launches;
+    if (!fused) {
+        k_prof_construct<<<tiles, kConThreads, 0, st>>>(reinterpret_cast<const ConJobDev*>(blob + o_con), n, d_meta, d_results, d_path,
+                                                        gaps[0], gaps[1], gaps[2], gaps[3]);
+        FB_CUDA(cudaGetLastError());
+        ++ctx->launches;
+    }
     FB_CUDA(cudaEventRecord(P.ev[2], st));
     P.timing_valid = true;
     FB_CUDA(cudaMemcpyAsync(h_results, d_results, sizeof(famsa_dp_result) * n, cudaMemcpyDeviceToHost, st));
@@ -501,9 +537,29 @@ static int prof_launch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t 
 static int prof_collect(famsa_ctx* ctx, ProfTicket* T)
 {
     ProfState& P = ctx->prof;
-    FB_CUDA(cudaEventSynchronize(T->done));
-    P.free_events.push_back(T->done);
-    T->done = nullptr;
+    if (T->done_seq) {
+        // flag-tracked batch: the kernel's last block published its sequence number after fencing every block's results
+        unsigned spins = 0;
+        while (*P.h_done < T->done_seq) {
+            if (++spins > 2000000u) {                                // ~ seconds: make sure the device is still alive
+                const cudaError_t e = cudaStreamQuery(ctx->stream);
+                if (e != cudaSuccess && e != cudaErrorNotReady) { FB_CUDA(e); }
+                if (e == cudaSuccess && *P.h_done < T->done_seq) { set_error("internal: a flag-tracked batch finished without publishing"); return FAMSA_E_CUDA; }
+                spins = 0;
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        T->done_seq = 0;
+    } else {
+        FB_CUDA(cudaEventSynchronize(T->done));
+        P.free_events.push_back(T->done);
+        T->done = nullptr;
+    }
+    if (T->ring_host_end != (size_t)-1) { P.h_ring.release_to(T->ring_host_end); T->ring_host_end = (size_t)-1; }
+    if (T->ring_dev_end != (size_t)-1) { P.d_ring.release_to(T->ring_dev_end); T->ring_dev_end = (size_t)-1; }
     int rc = FAMSA_OK;
     for (uint32_t k = 0; k < T->n; ++k) {
         ProfEntry& e = P.entries[T->merged_ids[k]];
@@ -528,7 +584,7 @@ int prof_merge_batch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t n,
     P.timing_valid = false;
     if (!n) return FAMSA_OK;
     ProfTicket T;
-    FB_TRY(prof_launch(ctx, merges, n, gaps, results, path_buf, path_cap, &T));
+    FB_TRY(prof_launch(ctx, merges, n, gaps, results, path_buf, path_cap, false, &T));
     const int rc = prof_collect(ctx, &T);
     for (uint32_t k = 0; k < n; ++k) merged_ids[k] = T.merged_ids[k];
     return rc;
@@ -550,7 +606,7 @@ static int pinned_reserve(void** p, size_t* cap, size_t bytes)
     if (*p) cudaFreeHost(*p);
     *p = nullptr; *cap = 0;
     const size_t want = bytes + bytes / 4 + 4096;
-    FB_CUDA(cudaHostAlloc(p, want, cudaHostAllocDefault));
+    FB_CUDA(cudaHostAlloc(p, want, cudaHostAllocMapped));
     *cap = want;
     return FAMSA_OK;
 }
@@ -595,9 +651,13 @@ int prof_align_tree(famsa_ctx* ctx, const int32_t* tree, uint32_t n_leaves, cons
     uint64_t peak_bytes = 0;
     constexpr size_t kMaxInFlight = 8;
     FB_CUDA(cudaEventRecord(P.ev_tree[0], ctx->stream));
+    double t_collect = 0, t_launch = 0;
+    auto now = []() { return std::chrono::steady_clock::now(); };
     auto collect_front = [&]() -> int {
         InFlight& f = q.front();
+        const auto t0 = now();
         const int rc = prof_collect(ctx, &f.t);
+        t_collect += std::chrono::duration<double, std::micro>(now() - t0).count();
         for (size_t a = 0; a < f.merge_ids.size(); ++a) {
             const uint32_t k = f.merge_ids[a];
             famsa_dp_result& r = P.h_tree_results[f.res_base + a];
@@ -618,14 +678,15 @@ int prof_align_tree(famsa_ctx* ctx, const int32_t* tree, uint32_t n_leaves, cons
     for (size_t lv = 0; lv < levels.size() && rc == FAMSA_OK; ++lv) {
         const std::vector<uint32_t>& level = levels[lv];
         // collect whatever has finished already (tightens the bounds for free)
-        while (!q.empty() && cudaEventQuery(q.front().t.done) == cudaSuccess && rc == FAMSA_OK) rc = collect_front();
+        auto finished = [&](const ProfTicket& t) { return t.done_seq ? *P.h_done >= t.done_seq : cudaEventQuery(t.done) == cudaSuccess; };
+        while (!q.empty() && finished(q.front().t) && rc == FAMSA_OK) rc = collect_front();
         if (rc) break;
         auto level_cost = [&](uint64_t* bound_cells, uint64_t* path_need) {
             *bound_cells = *path_need = 0;
             for (uint32_t k : level) {
                 const uint32_t a = (uint32_t)tree[2 * k], b = (uint32_t)tree[2 * k + 1];
                 *bound_cells += (uint64_t)width[a] * width[b];
-                *path_need += (uint64_t)width[a] + width[b];
+                *path_need += align_up((uint64_t)width[a] + width[b], 16);
             }
         };
         uint64_t bound_cells, path_need;
@@ -666,8 +727,10 @@ int prof_align_tree(famsa_ctx* ctx, const int32_t* tree, uint32_t n_leaves, cons
         f.merge_ids = level;
         f.path_base = path_cursor;
         f.res_base = res_cursor;
+        const auto t0 = now();
         rc = prof_launch(ctx, mg.data(), (uint32_t)mg.size(), gaps, P.h_tree_results + res_cursor, P.h_tree_paths + path_cursor,
-                         P.h_tree_paths_cap - path_cursor, &f.t);
+                         P.h_tree_paths_cap - path_cursor, true, &f.t);
+        t_launch += std::chrono::duration<double, std::micro>(now() - t0).count();
         if (rc) { q.pop_back(); break; }
         for (size_t a = 0; a < level.size(); ++a) {
             const uint32_t k = level[a];
@@ -682,6 +745,9 @@ int prof_align_tree(famsa_ctx* ctx, const int32_t* tree, uint32_t n_leaves, cons
     }
     while (!q.empty()) { const int r2 = collect_front(); if (rc == FAMSA_OK) rc = r2; }
     if (rc) return rc;
+    if (getenv("FAMSA_DP_DEBUG"))
+        fprintf(stderr, "[tree] host time: %.0f us in prof_launch, %.0f us waiting in prof_collect, %.0f us total so far, %u batches\n", t_launch, t_collect,
+                std::chrono::duration<double, std::micro>(now() - t_begin).count(), n_batches);
     FB_CUDA(cudaEventRecord(P.ev_tree[1], ctx->stream));
     FB_CUDA(cudaEventSynchronize(P.ev_tree[1]));
     float dev_ms = 0.f;
@@ -752,11 +818,14 @@ int prof_last_timing(famsa_ctx* ctx, float* total_ms, float* construct_ms)
 void prof_release_all(famsa_ctx* ctx)
 {
     ProfState& P = ctx->prof;
-    for (ProfSlab& s : P.slabs)
-        if (s.p) cudaFreeAsync(s.p, ctx->stream);
     cudaStreamSynchronize(ctx->stream);
+    P.arena.release_all();
     for (DevBuf* b : {&P.d_sm, &P.d_widths}) b->release();
     for (cudaEvent_t e : P.free_events) cudaEventDestroy(e);
+    if (P.h_ring_mem) cudaFreeHost(P.h_ring_mem);
+    if (P.h_done) cudaFreeHost(const_cast<unsigned long long*>(P.h_done));
+    P.d_block_counter.release();
+    P.d_ring_mem.release();
     if (P.h_tree_results) cudaFreeHost(P.h_tree_results);
     if (P.h_tree_paths) cudaFreeHost(P.h_tree_paths);
     for (auto& e : P.ev)

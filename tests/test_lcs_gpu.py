@@ -203,7 +203,6 @@ def test_medoid_assignment_large(engine):
 
 
 @pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref not built")
-@pytest.mark.parametrize("modified", [False, True])
 def test_medoid_assignment_sharded(engine):
     """famsa_lcs_assign_shard: three shards of one context, combined with an element-wise MIN (what the NCCL all-reduce
     does across GPUs), equal the unsharded famsa_lcs_assign bit for bit -- ragged lengths, unsorted input, a repeated seed."""
@@ -225,6 +224,7 @@ def test_medoid_assignment_sharded(engine):
         assert np.array_equal(a, want_a) and np.array_equal(d, want_d)
 
 
+@pytest.mark.parametrize("modified", [False, True])
 def test_gpu_driven_upgma_tree(engine, modified):
     """Drop-in proof for HP-1: GPU LCS triangle -> host Transform<float, indel075_div_lcs> -> the reference's own,
     unmodified UPGMA agglomeration (UPGMA<>::computeTree) gives exactly the guide tree the reference builds from

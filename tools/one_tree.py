@@ -21,7 +21,16 @@ else:
     codes, off, lens = seqio.pack([seqio.encode(str(s)) for s in z["seqs"]])
 eng.upload(codes, off, lens); eng.prof_set_scoring(sm)
 root, _, st = eng.align_tree(z["merges"], z["gaps"], want_paths=False); eng.prof_drop([root])
+import ctypes as C
+if os.environ.get('FAMSA_FUSED_TIMING'):
+    eng.lib.famsa_debug_fused_phases((C.c_double * 8)())
 torch.cuda.cudart().cudaProfilerStart()
 root, _, st = eng.align_tree(z["merges"], z["gaps"], want_paths=False)
 torch.cuda.cudart().cudaProfilerStop()
 print(st)
+import ctypes as C
+if os.environ.get('FAMSA_FUSED_TIMING'):
+    out = (C.c_double * 8)()
+    eng.lib.famsa_debug_fused_phases(out)
+    names = ['leaf', 'prep', 'fill', 'dirs->smem', 'trace', 'construct', 'whole_block', 'idle_before_launch']
+    print({k: round(v / 1e3, 1) for k, v in zip(names, out)}, 'us total; levels:', st['n_batches'])
