@@ -367,7 +367,18 @@ def bench_c3(eng, torch, dist, world, rank, stream, l2_flush):
             want = pyoracle.lcs_rows(codes, offsets, lens, [int(ref)], cols)[0]
             got = full[tri(int(ref)) + torch.from_numpy(cols).cuda()].cpu().numpy().astype(np.uint32)
             spot = spot and bool(np.array_equal(got, want))
+    upgma = None
+    if rank == 0:
+        try:
+            t0 = time.time()
+            tree = eng.upgma(0, False, full.data_ptr(), 2)
+            upgma = {"ms": 1e3 * (time.time() - t0), "merges": int(len(tree)),
+                     "note": "UPGMA on the gathered triangle (famsa_lcs_upgma_from_triangle) on rank 0: float distances + agglomeration on the device"}
+        except Exception as e:
+            upgma = {"error": str(e)}
+    dist.barrier()
     out = {"metric": METRIC, "unit": UNIT, "scaling": "strong", "value": tri(n) / (ms / 1e3), "ms_per_step": ms, "steps": steps, "warmup": 1,
+           "upgma_tree": upgma,
            "config": {"workload": f"LCS triangle, {n} x {LEN} aa synthetic family (seed {C3_SEED}), rows sharded over {world} GPUs, "
                                   "exchange overlapped in 8 pieces per rank", "pairs_per_step": tri(n)},
            "gathered_triangle_identical_on_all_ranks": bool(lo.item() == hi.item()), "oracle_spot_check": spot}
@@ -819,6 +830,19 @@ def main():
                                                  "the reference builds it in cpu_baseline's LCS time plus its Prim loop"}
             except Exception as e:                     # never let the extra leg break the contract line
                 line["guide_tree_sl"] = {"error": str(e)}
+            # informational: the UPGMA guide tree (-gt upgma) end to end -- famsa_lcs_upgma = LCS triangle + float Transform +
+            # UPGMA<>::computeTree's agglomeration, all on the device, only the n-1 merges return
+            try:
+                eng.upgma(0)
+                t0 = time.time()
+                tree = eng.upgma(0)
+                wall = time.time() - t0
+                tot, lcs_ms, _ = eng.last_timing()
+                line["guide_tree_upgma"] = {"ms": 1e3 * wall, "device_ms": tot, "lcs_kernels_ms": lcs_ms, "n_seqs": int(n), "merges": int(len(tree)),
+                                            "checksum": int((tree.astype(np.int64) * np.arange(1, 2 * len(tree) + 1).reshape(-1, 2)).sum()),
+                                            "note": "UPGMA<indel075_div_lcs>::run of the bench set through famsa_lcs_upgma (no n^2 D2H)"}
+            except Exception as e:
+                line["guide_tree_upgma"] = {"error": str(e)}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 EXPORTED_SYMBOLS = [
     "famsa_abi_version", "famsa_create", "famsa_destroy", "famsa_last_error", "famsa_kernel_launches",
     "famsa_lcs_upload", "famsa_lcs_n_seqs", "famsa_lcs_triangle", "famsa_lcs_triangle_device",
-    "famsa_lcs_rows", "famsa_lcs_rows_device", "famsa_lcs_assign", "famsa_lcs_assign_shard", "famsa_lcs_prim", "famsa_transform_f64", "famsa_transform_f32",
+    "famsa_lcs_rows", "famsa_lcs_rows_device", "famsa_lcs_assign", "famsa_lcs_assign_shard", "famsa_lcs_upgma", "famsa_lcs_upgma_from_triangle", "famsa_lcs_prim", "famsa_transform_f64", "famsa_transform_f32",
     "famsa_lcs_last_timing", "famsa_dp_align_batch", "famsa_dp_align_batch_device", "famsa_dp_last_timing",
     "famsa_prof_set_scoring", "famsa_prof_put", "famsa_prof_merge_batch", "famsa_prof_get", "famsa_prof_drop",
     "famsa_prof_last_timing", "famsa_prof_stats", "famsa_prof_align_tree", "famsa_prof_tree_paths",
@@ -82,6 +82,8 @@ def load_library() -> C.CDLL:
     lib.famsa_lcs_rows_device.argtypes = [vp, vp, u32, vp, u32, vp, i32, vp]
     lib.famsa_lcs_prim.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.famsa_lcs_assign.argtypes = [vp, vp, u32, i32, vp, vp]
+    lib.famsa_lcs_upgma.argtypes = [vp, i32, i32, vp]
+    lib.famsa_lcs_upgma_from_triangle.argtypes = [vp, i32, i32, vp, i32, vp]
     lib.famsa_lcs_assign_shard.argtypes = [vp, vp, u32, i32, u32, u32, vp, vp]
     lib.famsa_transform_f64.argtypes = [i32, u32, u32, u32]
     lib.famsa_transform_f64.restype = C.c_double
@@ -185,6 +187,16 @@ class Engine:
         d = np.zeros(m, dtype=np.float64); o = np.zeros(max(self.n, 1), dtype=np.int32)
         self._check(self.lib.famsa_lcs_prim(self.h, kind, _ptr(f), _ptr(t), _ptr(d), _ptr(o)))
         return f[:self.n - 1], t[:self.n - 1], d[:self.n - 1], o[:self.n]
+
+    def upgma(self, kind: int = 0, modified: bool = False, d_triangle_ptr: int = 0, elem_bytes: int = 2) -> np.ndarray:
+        """famsa_lcs_upgma[_from_triangle]: the UPGMA guide tree of the uploaded set, (n-1, 2) child ids of the internal
+        nodes; d_triangle_ptr: a packed LCS triangle already on the device (else it is computed)."""
+        t = np.zeros((max(self.n - 1, 1), 2), dtype=np.int32)
+        if d_triangle_ptr:
+            self._check(self.lib.famsa_lcs_upgma_from_triangle(self.h, kind, int(modified), C.c_void_p(d_triangle_ptr), elem_bytes, _ptr(t)))
+        else:
+            self._check(self.lib.famsa_lcs_upgma(self.h, kind, int(modified), _ptr(t)))
+        return t[:self.n - 1]
 
     def assign(self, seed_ids, kind: int = 0) -> tuple[np.ndarray, np.ndarray]:
         """FastTree<>::makeEvaluation's assignment loop: (assignments uint32[n], min_dist float32[n])."""

@@ -351,6 +351,39 @@ int famsa_lcs_assign(famsa_ctx* ctx, const uint32_t* seed_ids, uint32_t n_seeds,
     return finish_timing(ctx);
 }
 
+int famsa_lcs_upgma(famsa_ctx* ctx, int distance_kind, int modified, int32_t* tree)
+{
+    FB_CHECK_CTX(ctx);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->lcs.n < 2) { set_error("famsa_lcs_upgma needs at least two uploaded sequences"); return FAMSA_E_STATE; }
+    if (!tree) { set_error("NULL argument"); return FAMSA_E_INVALID; }
+    if (distance_kind < 0 || distance_kind > 2) { set_error("distance_kind must be 0, 1 or 2"); return FAMSA_E_INVALID; }
+    FB_CUDA(cudaSetDevice(ctx->device));
+    int rc = fb::scratch_acquire(ctx, ctx->stream);
+    if (rc) return rc;
+    rc = fb::lcs_upgma(ctx, distance_kind, modified, tree);
+    if (rc) return rc;
+    fb::scratch_release(ctx, ctx->stream, true);
+    return finish_timing(ctx);
+}
+
+int famsa_lcs_upgma_from_triangle(famsa_ctx* ctx, int distance_kind, int modified, const void* d_triangle, int elem_bytes, int32_t* tree)
+{
+    FB_CHECK_CTX(ctx);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->lcs.n < 2) { set_error("famsa_lcs_upgma needs at least two uploaded sequences"); return FAMSA_E_STATE; }
+    if (!tree || !d_triangle) { set_error("NULL argument"); return FAMSA_E_INVALID; }
+    if (distance_kind < 0 || distance_kind > 2) { set_error("distance_kind must be 0, 1 or 2"); return FAMSA_E_INVALID; }
+    if (elem_bytes != 2 && elem_bytes != 4) { set_error("elem_bytes must be 2 or 4"); return FAMSA_E_INVALID; }
+    FB_CUDA(cudaSetDevice(ctx->device));
+    int rc = fb::scratch_acquire(ctx, ctx->stream);
+    if (rc) return rc;
+    rc = fb::lcs_upgma(ctx, distance_kind, modified, tree, d_triangle, elem_bytes);
+    if (rc) return rc;
+    fb::scratch_release(ctx, ctx->stream, true);
+    return finish_timing(ctx);
+}
+
 int famsa_lcs_assign_shard(famsa_ctx* ctx, const uint32_t* seed_ids, uint32_t n_seeds, int distance_kind, uint32_t shard,
                            uint32_t n_shards, int64_t* d_packed, void* stream)
 {

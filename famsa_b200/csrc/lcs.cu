@@ -705,6 +705,134 @@ __global__ void __launch_bounds__(256) k_mst_combine(uint32_t n, uint32_t n_chun
     best[j].d = d; best[j].k = k;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// UPGMA on the resident triangle (UPGMA<>::computeTree, UPGMA.cpp:114-295).
+//
+// The reference's agglomeration is MUSCLE's nearest-neighbour-cache UPGMA: every live row keeps (MinDist, NearestNeighbor);
+// an iteration picks the live row with the smallest MinDist (first such row), merges it with its cached neighbour,
+// overwrites the row of the left child with the averaged distances and re-labels -- but does not re-evaluate -- the
+// caches of the other rows (UPGMA.cpp:229-262: a row whose neighbour was the right child now points at the left child
+// and keeps the OLD distance).  Results depend on that, so it is reproduced step for step; what is parallel is the inside
+// of a step: both scans (arg-min over the rows, update + arg-min over the new row) are grid-wide reductions of packed
+// (float bits, index) words -- distances are >= 0, so unsigned order is value order and ties go to the lowest index,
+// exactly what the strict < of the sequential scans does.  One cooperative kernel, two grid barriers per merge.
+// ------------------------------------------------------------------------------------------------
+constexpr float kUpgmaBig = 1e29f;                                  // UPGMA::BIG_DIST (UPGMA.h:82)
+constexpr unsigned long long kNoCand = ~0ull;
+
+// Transform<float, Distance> of every pair: the float triangle computeDistances fills (UPGMA.cpp:75-109)
+__global__ void __launch_bounds__(256) k_upgma_dist(const void* __restrict__ tri, int eb, uint32_t n, const uint32_t* __restrict__ lens,
+                                                    const float* __restrict__ pow075, int kind, float never, float* __restrict__ out)
+{
+    const uint32_t i = blockIdx.x + 1;
+    const size_t base = (size_t)i * (i - 1) / 2;
+    const uint32_t li = lens[i];
+    for (uint32_t j = threadIdx.x; j < i; j += blockDim.x) {
+        const uint32_t l = eb == 2 ? static_cast<const uint16_t*>(tri)[base + j] : static_cast<const uint32_t*>(tri)[base + j];
+        out[base + j] = transform_f32(kind, l, li, lens[j], pow075, never);
+    }
+}
+
+__device__ __forceinline__ unsigned long long pack_cand(float d, uint32_t j) { return ((unsigned long long)__float_as_uint(d) << 32) | j; }
+__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v, unsigned long long* sh)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 16; o; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, v, o); v = x < v ? x : v; }
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t nw = blockDim.x / 32;
+        v = lane < nw ? sh[lane] : kNoCand;
+        for (int o = 16; o; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, v, o); v = x < v ? x : v; }
+    }
+    return v;                                                        // valid in warp 0
+}
+
+// initial (MinDist, NearestNeighbor) of every row (UPGMA.cpp:183-203): partners are met in ascending index order and
+// only a strictly smaller distance replaces the cache, so the cache is the arg-min with the lowest partner on ties
+__global__ void __launch_bounds__(256) k_upgma_init(const float* __restrict__ dist, uint32_t n, float* __restrict__ mind, uint32_t* __restrict__ nn,
+                                                    int* __restrict__ node)
+{
+    __shared__ unsigned long long sh[32];
+    const uint32_t r = blockIdx.x;
+    unsigned long long best = kNoCand;
+    const size_t base = (size_t)r * (r ? r - 1 : 0) / 2;
+    for (uint32_t p = threadIdx.x; p < n; p += blockDim.x) {
+        if (p == r) continue;
+        const float d = p < r ? dist[base + p] : dist[(size_t)p * (p - 1) / 2 + r];
+        if (d < kUpgmaBig) { const unsigned long long c = pack_cand(d, p); best = c < best ? c : best; }
+    }
+    best = block_min_u64(best, sh);
+    if (threadIdx.x == 0) {
+        mind[r] = best == kNoCand ? kUpgmaBig : __uint_as_float((unsigned)(best >> 32));
+        nn[r] = best == kNoCand ? 0x7fffffffu : (uint32_t)best;
+        node[r] = (int)r;
+    }
+}
+
+template <bool MODIFIED>
+__global__ void __launch_bounds__(1024) k_upgma(float* __restrict__ dist, uint32_t n, float* __restrict__ mind, uint32_t* __restrict__ nn,
+                                                int* __restrict__ node, unsigned long long* __restrict__ cand, int* __restrict__ out_tree,
+                                                int* __restrict__ status)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned long long sh[32];
+    __shared__ unsigned long long sh_pick;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t gtid = blockIdx.x * blockDim.x + tid, gthreads = gridDim.x * blockDim.x, nblk = gridDim.x;
+    auto tri_at = [](uint32_t a, uint32_t b) -> size_t { const uint32_t hi = a > b ? a : b, lo = a > b ? b : a; return (size_t)hi * (hi - 1) / 2 + lo; };
+    // every block reduces the nblk published candidates of buffer `buf` for itself: all agree without a second barrier
+    auto gather = [&](uint32_t buf) -> unsigned long long {
+        unsigned long long v = kNoCand;
+        if (warp == 0) {
+            for (uint32_t b = lane; b < nblk; b += 32) { const unsigned long long x = cand[(size_t)buf * nblk + b]; v = x < v ? x : v; }
+            for (int o = 16; o; o >>= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, v, o); v = x < v ? x : v; }
+            if (lane == 0) sh_pick = v;
+        }
+        __syncthreads();
+        return sh_pick;
+    };
+    for (uint32_t it = 0; it + 1 < n; ++it) {
+        // ---- the live row with the smallest cached distance (first such row)
+        unsigned long long best = kNoCand;
+        for (uint32_t j = gtid; j < n; j += gthreads)
+            if (node[j] >= 0) { const float d = mind[j]; if (d < kUpgmaBig) { const unsigned long long c = pack_cand(d, j); best = c < best ? c : best; } }
+        best = block_min_u64(best, sh);
+        if (tid == 0) cand[(size_t)0 * nblk + blockIdx.x] = best;
+        grid.sync();
+        const unsigned long long pick = gather(0);
+        if (pick == kNoCand) { if (gtid == 0) *status = 1; return; }     // no finite distance left: the reference would index out of range
+        const uint32_t L = (uint32_t)pick, R = nn[L];
+        // ---- distances to the new node overwrite the row of L; the arg-min of the new row becomes L's cache
+        unsigned long long nbest = kNoCand;
+        for (uint32_t j = gtid; j < n; j += gthreads) {
+            if (j == L || j == R || node[j] < 0) continue;
+            const size_t vL = tri_at(L, j), vR = tri_at(R, j);
+            const float dL = dist[vL], dR = dist[vR];
+            const float nd = MODIFIED ? __fadd_rn(__fmul_rn(0.05f, __fadd_rn(dL, dR)), __fmul_rn(0.9f, dR < dL ? dR : dL))
+                                      : __fmul_rn(__fadd_rn(dL, dR), 0.5f);
+            if (nn[j] == R) nn[j] = L;
+            dist[vL] = nd;
+            if (nd < kUpgmaBig) { const unsigned long long c = pack_cand(nd, j); nbest = c < nbest ? c : nbest; }
+        }
+        nbest = block_min_u64(nbest, sh);
+        if (tid == 0) cand[(size_t)1 * nblk + blockIdx.x] = nbest;
+        grid.sync();
+        const unsigned long long npick = gather(1);
+        if (gtid == 0) {
+            out_tree[2 * it] = node[L];
+            out_tree[2 * it + 1] = node[R];
+            node[L] = (int)(n + it);
+            nn[L] = npick == kNoCand ? 0x7fffffffu : (uint32_t)npick;
+            mind[L] = npick == kNoCand ? kUpgmaBig : __uint_as_float((unsigned)(npick >> 32));
+            node[R] = -1;
+        }
+        grid.sync();                                                     // the caches of L and R are read by the next scan
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1262,6 +1390,60 @@ int lcs_assign(famsa_ctx* ctx, const uint32_t* h_seed_ids, uint32_t n_seeds, int
     FB_CUDA(cudaMemcpyAsync(h_assign, S.d_assign.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, st));
     FB_CUDA(cudaMemcpyAsync(h_mind, S.d_mind.p, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
     FB_CUDA(cudaStreamSynchronize(st));
+    return FAMSA_OK;
+}
+
+
+// famsa_lcs_upgma: LCS triangle (row = seq0, as calculateDistanceVector builds it) -> float distances -> the agglomeration
+int lcs_upgma(famsa_ctx* ctx, int kind, int modified, int32_t* h_tree, const void* d_tri_in, int tri_eb)
+{
+    LcsState& S = ctx->lcs;
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = S.n;
+    const int eb = d_tri_in ? tri_eb : (S.max_len < 65536 ? 2 : 4);
+    const size_t pairs = (size_t)n * (n - 1) / 2;
+    const void* d_tri = d_tri_in;
+    if (!d_tri) {
+        FB_TRY(S.d_prim_tri.reserve(std::max<size_t>(pairs, 1) * eb));
+        FB_TRY(lcs_triangle(ctx, 0, n, S.d_prim_tri.p, eb, st));
+        d_tri = S.d_prim_tri.p;
+    } else {
+        S.last_pairs = 0;
+        FB_CUDA(cudaEventRecord(ctx->ev[0], st)); FB_CUDA(cudaEventRecord(ctx->ev[1], st)); FB_CUDA(cudaEventRecord(ctx->ev[2], st));
+    }
+    FB_TRY(S.d_prim_dtri.reserve(std::max<size_t>(pairs, 1) * sizeof(float)));
+    FB_TRY(S.d_prim_state.reserve((sizeof(float) + sizeof(uint32_t) + sizeof(int)) * (size_t)n + 64));
+    FB_TRY(S.d_prim_out.reserve(sizeof(int) * 2 * (size_t)n + 64));
+    float* d_dist = S.d_prim_dtri.as<float>();
+    float* d_mind = S.d_prim_state.as<float>();
+    uint32_t* d_nn = reinterpret_cast<uint32_t*>(d_mind + n);
+    int* d_node = reinterpret_cast<int*>(d_nn + n);
+    int* d_tree = S.d_prim_out.as<int>();
+    int* d_status = d_tree + 2 * (size_t)(n - 1);
+    const float never = (float)nextafter((double)FLT_MAX, 0.0);
+    k_upgma_dist<<<n - 1, 256, 0, st>>>(d_tri, eb, n, S.d_raw_len.as<uint32_t>(), S.d_pow075.as<float>(), kind, never, d_dist);
+    k_upgma_init<<<n, 256, 0, st>>>(d_dist, n, d_mind, d_nn, d_node);
+    FB_CUDA(cudaGetLastError());
+    FB_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+    ctx->launches += 2;
+    {
+        void* fn = modified ? (void*)k_upgma<true> : (void*)k_upgma<false>;
+        int per_sm = 0;
+        FB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 1024, 0));
+        const uint32_t nblk = std::max(1u, std::min((uint32_t)(ctx->sm_count * std::max(per_sm, 1)), (n + 1023) / 1024));
+        FB_TRY(S.d_prim_cand.reserve(sizeof(unsigned long long) * 2 * nblk));
+        uint32_t a_n = n;
+        unsigned long long* a_cand = S.d_prim_cand.as<unsigned long long>();
+        void* args[] = {&d_dist, &a_n, &d_mind, &d_nn, &d_node, &a_cand, &d_tree, &d_status};
+        FB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(nblk), dim3(1024), args, 0, st));
+        ctx->launches++;
+    }
+    FB_CUDA(cudaEventRecord(ctx->ev[3], st));
+    int status = 0;
+    FB_CUDA(cudaMemcpyAsync(h_tree, d_tree, sizeof(int) * 2 * (size_t)(n - 1), cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FB_CUDA(cudaStreamSynchronize(st));
+    if (status) { set_error("famsa_lcs_upgma: no finite distance left between two clusters (sequences without a common residue)"); return FAMSA_E_INVALID; }
     return FAMSA_OK;
 }
 

@@ -415,11 +415,12 @@ static int prof_launch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t 
             memcpy(hj, plan_jobs.data(), sizeof(DpJobDev) * n);          // (write-combined order does not matter: the launch orders it)
             FusedParams FP{fj, L.d_raw_codes.as<int8_t>(), L.d_raw_off.as<uint64_t>(), L.d_raw_len.as<uint32_t>(), P.d_sm.as<long long>(),
                            0, P.d_block_counter.as<unsigned>(), nullptr, 0};
-            if (host_mapped) { FP.h_done = P.h_done; FP.done_seq = ++P.done_seq; }
+            const bool nowait = host_mapped && getenv("FAMSA_TREE_NOWAIT");          // experiment: no host traffic at all (results stay stale)
+            if (host_mapped && !nowait) { FP.h_done = P.h_done; FP.done_seq = ++P.done_seq; }
             if (getenv("FAMSA_FUSED_TIMING")) { static int launch_no = 0; FP.timing = 2 + (++launch_no & 1); }   // development aid
             if (!host_mapped) { FB_CUDA(cudaEventRecord(P.ev[0], st)); FB_CUDA(cudaEventRecord(P.ev[1], st)); }
             FB_TRY(dp_fused_launch(ctx, hj, n, gaps, d_results, db + o_path, reinterpret_cast<DpMeta*>(db + o_meta), db + o_scr, db + o_skew,
-                                   host_mapped ? h_results : nullptr, host_mapped ? h_paths : nullptr, &FP, plan.cells, !host_mapped, st));
+                                   host_mapped && !nowait ? h_results : nullptr, host_mapped && !nowait ? h_paths : nullptr, &FP, plan.cells, !host_mapped, st));
             if (!host_mapped) { FB_CUDA(cudaEventRecord(P.ev[2], st)); P.timing_valid = true; }
             if (!host_mapped) {
                 FB_CUDA(cudaMemcpyAsync(h_results, d_results, sizeof(famsa_dp_result) * n, cudaMemcpyDeviceToHost, st));
@@ -428,7 +429,8 @@ static int prof_launch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t 
             for (uint32_t k = 0; k < n; ++k)
                 for (uint32_t c : {merges[k].child1, merges[k].child2})
                     if (!(c & FAMSA_PROF_LEAF)) FB_TRY(release_entry(ctx, c));
-            if (host_mapped) T->done_seq = FP.done_seq;
+            if (nowait) { T->done_seq = 0; T->done = nullptr; }
+            else if (host_mapped) T->done_seq = FP.done_seq;
             else { T->done = take_event(P); FB_CUDA(cudaEventRecord(T->done, st)); }
             T->n = n; T->h_results = h_results; T->h_paths = h_paths; T->path_bytes = plan.path_bytes; T->cells_bound = plan.cells;
             T->ring_host_end = P.h_ring.head; T->ring_dev_end = P.d_ring.head;
@@ -553,7 +555,7 @@ static int prof_collect(famsa_ctx* ctx, ProfTicket* T)
         }
         std::atomic_thread_fence(std::memory_order_acquire);
         T->done_seq = 0;
-    } else {
+    } else if (T->done) {
         FB_CUDA(cudaEventSynchronize(T->done));
         P.free_events.push_back(T->done);
         T->done = nullptr;
@@ -678,7 +680,7 @@ int prof_align_tree(famsa_ctx* ctx, const int32_t* tree, uint32_t n_leaves, cons
     for (size_t lv = 0; lv < levels.size() && rc == FAMSA_OK; ++lv) {
         const std::vector<uint32_t>& level = levels[lv];
         // collect whatever has finished already (tightens the bounds for free)
-        auto finished = [&](const ProfTicket& t) { return t.done_seq ? *P.h_done >= t.done_seq : cudaEventQuery(t.done) == cudaSuccess; };
+        auto finished = [&](const ProfTicket& t) { return t.done_seq ? *P.h_done >= t.done_seq : (!t.done || cudaEventQuery(t.done) == cudaSuccess); };
         while (!q.empty() && finished(q.front().t) && rc == FAMSA_OK) rc = collect_front();
         if (rc) break;
         auto level_cost = [&](uint64_t* bound_cells, uint64_t* path_need) {

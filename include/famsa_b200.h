@@ -139,6 +139,19 @@ int famsa_lcs_assign_shard(famsa_ctx* ctx, const uint32_t* seed_ids, uint32_t n_
 int famsa_lcs_prim(famsa_ctx* ctx, int distance_kind, int32_t* edge_from, int32_t* edge_to, double* edge_dist,
                    int32_t* prim_order);
 
+/* The UPGMA guide tree (-gt upgma / -gt upgma_modified): UPGMA<>::run (src/tree/UPGMA.cpp:39-51) = computeDistances (:75-109, the
+ * float Transform of every pair of the triangle) + computeTree<MODIFIED> (:114-295, MUSCLE's nearest-neighbour-cache
+ * agglomeration with the plain or the MAFFT-style "modified" average, :24-35), on the LCS triangle kept in HBM: no n^2 data
+ * leaves the device, only the n-1 merges return.  tree[2k], tree[2k+1] = children of internal node n_seqs + k (node ids as
+ * in tree_structure: leaves 0..n-1 in caller order, which must be the order the reference builds the tree on -- length
+ * descending, src/msa.cpp:245-256); the result is the reference's tree pair for pair, including the stale-cache behaviour
+ * of its scans.  distance_kind as in famsa_transform_f32 (0 or 1 are what UPGMA is instantiated for).  HOST pointer. */
+int famsa_lcs_upgma(famsa_ctx* ctx, int distance_kind, int modified, int32_t* tree);
+/* Same on a packed LCS triangle that is already in HBM (DEVICE pointer; layout and elem_bytes as famsa_lcs_triangle_device
+ * writes it for rows 0..n_seqs) -- e.g. the triangle a multi-GPU run has just all-gathered. */
+int famsa_lcs_upgma_from_triangle(famsa_ctx* ctx, int distance_kind, int modified, const void* d_triangle, int elem_bytes,
+                                  int32_t* tree);
+
 /* Host-side Transform<T, Distance> (AbstractTreeGenerator.hpp:28-82), provided so bindings that
  * are not C++ get bit-identical distances.  kind: 0 indel075_div_lcs, 1 indel_div_lcs,
  * 2 pairwise_identity. */

@@ -243,6 +243,53 @@ def test_gpu_driven_upgma_tree(engine, modified):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("modified", [False, True])
+@pytest.mark.parametrize("case", ["family400", "ragged", "big"])
+def test_device_upgma_tree(engine, modified, case):
+    """famsa_lcs_upgma (distances + agglomeration on the device, SURVEY 8f-1): the tree is the reference's UPGMA<>::run
+    tree pair for pair, plain and MAFFT-modified average, on a family, on a ragged random set full of distance ties and on
+    3000 sequences (several thread blocks per scan)."""
+    if case == "family400":
+        codes, offsets, lens = seqio.synth_family(400, 150, seed=21)
+    elif case == "ragged":
+        cl = random_set(np.random.default_rng(5), 500, 20, 90, alphabet=4)
+        cl.sort(key=lambda c: -len(c))
+        codes, offsets, lens = seqio.pack(cl)
+    else:
+        codes, offsets, lens = seqio.synth_family(3000, 120, seed=23)
+    n = len(lens)
+    engine.upload(codes, offsets, lens)
+    got = engine.upgma(0, modified)
+    letters = [seqio.decode(codes[int(o):int(o) + int(ln)]) for o, ln in zip(offsets, lens)]
+    want = pyoracle.RefSeqSet(letters).upgma_tree(modified, n_threads=8)[n:]
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_device_upgma_golden(engine):
+    """The golden UPGMA tree of adeno_fiber (test/adeno_fiber/upgma.dnd, held as merges in the fixture): same clades."""
+    z = np.load(os.path.join(GOLDEN, "adeno_upgma_merges.npz"))
+    seqs = [str(s) for s in z["seqs"]]
+    codes, offsets, lens = seqio.pack([seqio.encode(s) for s in seqs])
+    n = len(seqs)
+    engine.upload(codes, offsets, lens)
+
+    def clades(merges):
+        members = {i: frozenset([i]) for i in range(n)}
+        out = set()
+        for k, (a, b) in enumerate(merges):
+            members[n + k] = members[int(a)] | members[int(b)]
+            out.add(members[n + k])
+        return out
+    # the fixture's leaves are in the tree file's order, UPGMA needs FAMSA's own (length-descending) order: re-order
+    order = sorted(range(n), key=lambda i: (-len(seqs[i]), seqio.encode(seqs[i]).tobytes()))
+    codes, offsets, lens = seqio.pack([seqio.encode(seqs[i]) for i in order])
+    engine.upload(codes, offsets, lens)
+    got = engine.upgma(0, False)
+    remap = lambda m: [(order[a] if a < n else a, order[b] if b < n else b) for a, b in m]
+    assert clades(remap([(int(a), int(b)) for a, b in got])) == clades([(int(a), int(b)) for a, b in z["merges"]])
+
+
 def test_gpu_distances_match_golden_dist_sq(engine, adeno):
     """test/adeno_fiber/dist_sq.csv: GPU LCS + host float Transform reproduce every printed distance."""
     n = len(adeno["lens"])
