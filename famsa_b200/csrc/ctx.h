@@ -108,6 +108,7 @@ struct Ring {
         return off;
     }
     void release_to(size_t pos) { tail = pos; if (tail == head) empty = true; }
+    bool fits(size_t need) const { Ring r = *this; return r.alloc(need) != (size_t)-1; }
 };
 
 // Host-side sub-allocator over a few large device chunks for the resident profile tables.  Everything that touches a
@@ -120,6 +121,9 @@ struct DevArena {
     std::map<char*, std::pair<size_t, int>> free_by_addr;          // start -> (bytes, chunk)
     std::multimap<size_t, char*> free_by_size;
     size_t chunk_bytes = 256u << 20;
+    bool defer = false;                                             // free() only queues (see FusedAccum)
+    std::vector<std::pair<void*, size_t>> deferred;
+    void flush_deferred() { defer = false; for (auto& d : deferred) free(d.first, d.second); deferred.clear(); }
     void* alloc(size_t n);                                          // nullptr when the device is out of memory
     void free(void* p, size_t n);
     void release_all();
@@ -229,7 +233,8 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext,
 int dp_fused_plan(const famsa_dp_job* jobs, const DpJobExt* ext, uint32_t n, bool align16, DpJobDev* out, DpFusedPlan* plan);
 int dp_fused_launch(famsa_ctx* ctx, const DpJobDev* jobs, uint32_t n, const int64_t gaps[4], famsa_dp_result* d_results, uint8_t* d_path,
                     DpMeta* d_meta, uint8_t* d_scratch, uint8_t* d_skew, famsa_dp_result* h_results, uint8_t* h_path,
-                    const void* fused_params, uint64_t cells, bool record_events, cudaStream_t st);
+                    const void* fused_params, uint32_t grid, uint64_t cells, bool record_events, cudaStream_t st);
+unsigned long long dp_scratch_bytes(uint32_t w1, uint32_t w2);
 // prof.cu
 int prof_set_scoring(famsa_ctx* ctx, const int64_t* sm);
 int prof_put(famsa_ctx* ctx, const famsa_dp_profile* profs, uint32_t n, uint32_t* ids);

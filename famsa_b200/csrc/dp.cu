@@ -214,8 +214,8 @@ __device__ __forceinline__ void prep_body(const DpParams& P, uint32_t jid)
     // device memory; the widths in the job are then only upper bounds that size the buffers.
     uint32_t w1 = J.w1, w2 = J.w2;
     int child_bad = 0;
-    if (J.w1_src) { const uint32_t v = *J.w1_src; child_bad |= v == kWidthBad || v == 0 || v > J.w1; if (!child_bad) w1 = v; }
-    if (J.w2_src) { const uint32_t v = *J.w2_src; const int b = v == kWidthBad || v == 0 || v > J.w2; child_bad |= b; if (!b) w2 = v; }
+    if (J.w1_src) { const uint32_t v = __ldcg(J.w1_src); child_bad |= v == kWidthBad || v == 0 || v > J.w1; if (!child_bad) w1 = v; }
+    if (J.w2_src) { const uint32_t v = __ldcg(J.w2_src); const int b = v == kWidthBad || v == 0 || v > J.w2; child_bad |= b; if (!b) w2 = v; }
     if (child_bad) {
         // nothing below may trust the tables: report the failure and leave a 1 x 1 job behind for the other kernels
         if (tid == 0) {
@@ -995,7 +995,7 @@ __global__ void __launch_bounds__(kTraceWarps * 32) k_dp_trace(const DpParams P)
 // traceback and the merged tables, phase after phase with block barriers instead of kernel boundaries.  For the
 // chain-like parts of a guide tree, where a level is one small merge and five launches cost more than the work.
 // ------------------------------------------------------------------------------------------------
-constexpr int kFusedWarps = 4;
+constexpr int kFusedWarps = 8;
 __device__ unsigned long long g_fused_phase_ns[8];          // development aid (FAMSA_FUSED_TIMING): per phase, the sum over launches of
 __device__ unsigned long long g_fused_phase_max[2][8];      // the slowest block's time; [launch parity][phase] collects one launch
 __device__ __forceinline__ unsigned long long globaltimer_ns()
@@ -1006,9 +1006,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 }
 #define FB_PHASE(k)                                                                     \
     do {                                                                                \
-        if (F.timing && threadIdx.x == 0) {                                             \
+        if (F.timing && threadIdx.x == 0 && blockIdx.x == 0) {                          \
             const unsigned long long now__ = globaltimer_ns();                          \
-            atomicMax(&g_fused_phase_max[F.timing & 1][k], now__ - t_phase);            \
+            g_fused_phase_max[F.timing & 1][k] += now__ - t_phase;                      \
             t_phase = now__;                                                            \
         }                                                                               \
     } while (0)
@@ -1027,7 +1027,8 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_merge_fused(const DpPar
     __shared__ __align__(16) unsigned char sm_tile[64 * 32];
     __shared__ ConShared sm_con;
     const uint32_t warp = threadIdx.x / 32;
-    const uint32_t jid = blockIdx.x;
+    for (uint32_t lv = 0; lv < F.n_levels; ++lv) {
+    for (uint32_t jid = F.level_start[lv] + blockIdx.x; jid < F.level_start[lv + 1]; jid += gridDim.x) {
     const FusedJob fj = F.jobs[jid];
     for (int side = 0; side < 2; ++side)
         if (fj.leaf[side].seq != 0xffffffffu) leaf_body(fj.leaf[side], F.codes, F.off, F.len, F.sm, P.go, P.ge, P.to, P.te);
@@ -1061,13 +1062,36 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_merge_fused(const DpPar
     if (con_resolve(fj.con, P.meta[jid], P.results[jid], P.path, J))
         for (uint32_t k0 = 0; k0 <= J.W; k0 += kConTile) construct_tile(J, k0, sm_con, P.go, P.ge, P.to, P.te);
     FB_PHASE(5);
-    if (F.timing && threadIdx.x == 0) atomicMax(&g_fused_phase_max[F.timing & 1][6], globaltimer_ns() - t_begin);   // whole block
+    __syncthreads();                                                 // the next job of this block reuses the shared memory
+    }
+    if (lv + 1 < F.n_levels) {
+        // grid barrier: the next level reads what this one wrote (merged tables, widths)
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(F.block_counter + 1, 1u);
+            const unsigned target = (lv + 1) * gridDim.x;
+            unsigned seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(F.block_counter + 1) : "memory");
+                if (seen < target) __nanosleep(40);
+            } while (seen < target);
+        }
+        __syncthreads();
+        FB_PHASE(7 - 1);                                             // (slot 6: time spent at the barriers)
+    }
+    }
+    if (!F.h_done && F.n_levels > 1) {
+        __syncthreads();
+        if (threadIdx.x == 0 && atomicAdd(F.block_counter, 1u) == gridDim.x - 1) { F.block_counter[0] = 0; F.block_counter[1] = 0; }
+    }
     if (F.h_done) {
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence_system();                                  // this block's records and paths are in host memory
             if (atomicAdd(F.block_counter, 1u) == gridDim.x - 1) {
-                *F.block_counter = 0;
+                F.block_counter[0] = 0;
+                F.block_counter[1] = 0;
                 __threadfence_system();
                 *F.h_done = F.done_seq;
             }
@@ -1158,6 +1182,8 @@ static uint32_t max_cluster4(famsa_ctx* ctx)
     return (uint32_t)v;
 }
 
+unsigned long long dp_scratch_bytes(uint32_t w1, uint32_t w2) { return Scratch(w1, w2).total; }
+
 // ---- the fused path (k_merge_fused): planning and launch are separate so that the caller can place the descriptors in
 // mapped host memory and every device buffer in its own ring (no copy, no allocator call per batch)
 int dp_fused_plan(const famsa_dp_job* jobs, const DpJobExt* ext, uint32_t n, bool align16, DpJobDev* out, DpFusedPlan* plan)
@@ -1185,7 +1211,7 @@ int dp_fused_plan(const famsa_dp_job* jobs, const DpJobExt* ext, uint32_t n, boo
 
 int dp_fused_launch(famsa_ctx* ctx, const DpJobDev* jobs, uint32_t n, const int64_t gaps[4], famsa_dp_result* d_results, uint8_t* d_path,
                     DpMeta* d_meta, uint8_t* d_scratch, uint8_t* d_skew, famsa_dp_result* h_results, uint8_t* h_path,
-                    const void* fused_params, uint64_t cells, bool record_events, cudaStream_t st)
+                    const void* fused_params, uint32_t grid, uint64_t cells, bool record_events, cudaStream_t st)
 {
     static std::atomic<bool> configured[64];
     if (!configured[ctx->device & 63].load(std::memory_order_acquire)) {
@@ -1205,7 +1231,7 @@ int dp_fused_launch(famsa_ctx* ctx, const DpJobDev* jobs, uint32_t n, const int6
     P.h_results = h_results;
     P.h_path = h_path;
     if (record_events) { FB_CUDA(cudaEventRecord(ctx->ev[0], st)); FB_CUDA(cudaEventRecord(ctx->ev[1], st)); }
-    k_merge_fused<<<n, kFusedWarps * 32, kFusedWarps * sizeof(WarpShared), st>>>(P, *static_cast<const FusedParams*>(fused_params));
+    k_merge_fused<<<grid, kFusedWarps * 32, kFusedWarps * sizeof(WarpShared), st>>>(P, *static_cast<const FusedParams*>(fused_params));
     FB_CUDA(cudaGetLastError());
     ctx->launches++;
     if (record_events) { FB_CUDA(cudaEventRecord(ctx->ev[2], st)); FB_CUDA(cudaEventRecord(ctx->ev[3], st)); }

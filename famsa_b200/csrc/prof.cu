@@ -101,6 +101,7 @@ void* DevArena::alloc(size_t n)
 
 void DevArena::free(void* ptr, size_t n)
 {
+    if (defer) { deferred.emplace_back(ptr, n); return; }
     n = (std::max<size_t>(n, 256) + 511) & ~(size_t)511;
     char* p = static_cast<char*>(ptr);
     int chunk = -1;
@@ -277,39 +278,17 @@ static cudaEvent_t take_event(ProfState& P)
 // (dp.cu), merged tables (k_prof_construct), then one copy of the result records and paths into h_results / h_paths
 // (pinned memory makes that copy asynchronous too).  Children may be profiles of batches that are still queued -- their
 // widths are then upper bounds on the host and are resolved on the device.  The merged profiles are sized for w1 + w2.
-static int ensure_rings(famsa_ctx* ctx)
-{
-    ProfState& P = ctx->prof;
-    if (P.h_ring_mem) return FAMSA_OK;
-    const size_t hcap = 8u << 20, dcap = 512u << 20;
-    FB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&P.h_ring_mem), hcap, cudaHostAllocMapped));
-    P.h_ring.cap = hcap;
-    FB_TRY(P.d_ring_mem.reserve(dcap));
-    P.d_ring.cap = dcap;
-    FB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(const_cast<unsigned long long**>(&P.h_done)), 64, cudaHostAllocMapped));
-    *P.h_done = 0;
-    FB_TRY(P.d_block_counter.reserve(64));
-    FB_CUDA(cudaMemsetAsync(P.d_block_counter.p, 0, 64, ctx->stream));
-    return FAMSA_OK;
-}
-
-// host_mapped: h_results / h_paths are mapped pinned memory the device may write to directly (and path slots are 16-byte
-// aligned: job k's path at the running sum of align16(w1 + w2))
-static int prof_launch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t n, const int64_t gaps[4],
-                       famsa_dp_result* h_results, uint8_t* h_paths, uint64_t path_cap, bool host_mapped, ProfTicket* T)
+// Children of a batch of merges -> DP jobs: resident profiles by their tables (and, while they are still queued, the device
+// slot their width will appear in), leaves by a descriptor for later materialisation.
+static int prof_resolve(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t n, std::vector<famsa_dp_job>& jobs, std::vector<DpJobExt>& ext,
+                        std::vector<LeafDesc>& leaves, std::vector<std::pair<uint32_t, int>>& leaf_slot, size_t& leaf_bytes,
+                        uint64_t& path_need, uint64_t& cells)
 {
     ProfState& P = ctx->prof;
     LcsState& L = ctx->lcs;
-    cudaStream_t st = ctx->stream;
-
-    // resolve the children; leaves get scratch tables for the duration of the batch
-    std::vector<famsa_dp_job> jobs(n);
-    std::vector<DpJobExt> ext(n);
-    std::vector<LeafDesc> leaves;
-    std::vector<std::pair<uint32_t, int>> leaf_slot;                 // (job, side) per leaf, in `leaves` order
+    jobs.assign(n, famsa_dp_job{});
+    ext.assign(n, DpJobExt{nullptr, nullptr, nullptr});
     std::vector<uint8_t> seen(P.entries.size(), 0);
-    size_t leaf_bytes = 0;
-    uint64_t path_need = 0, cells = 0;
     for (uint32_t k = 0; k < n; ++k) {
         for (int side = 0; side < 2; ++side) {
             const uint32_t c = side ? merges[k].child2 : merges[k].child1;
@@ -338,15 +317,195 @@ static int prof_launch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t 
         path_need += (uint64_t)jobs[k].p1.width + jobs[k].p2.width;
         cells += (uint64_t)jobs[k].p1.width * jobs[k].p2.width;
     }
-    // A batch of small merges only (the chain-like parts of a guide tree: every level one or a few short merges) runs
-    // every merge whole in one block of k_merge_fused instead of five launches.
-    bool fused = n <= 4096;
-    for (uint32_t k = 0; k < n && fused; ++k) {
-        const famsa_dp_job& j = jobs[k];
+    return FAMSA_OK;
+}
+
+static bool fused_eligible(const std::vector<famsa_dp_job>& jobs)
+{
+    if (jobs.size() > 4096) return false;
+    for (const famsa_dp_job& j : jobs) {
         const uint32_t rows = j.p1.card == 1 ? j.p1.width : (j.p2.card == 1 ? j.p2.width : std::min(j.p1.width, j.p2.width));
-        fused = rows <= 256 && std::max(j.p1.width, j.p2.width) <= 8192;
+        if (rows > 512 || std::max(j.p1.width, j.p2.width) > 8192) return false;
     }
-    if (const char* e = getenv("FAMSA_PROF_FUSED")) fused = fused && atoi(e) != 0;                  // development knob
+    if (const char* e = getenv("FAMSA_PROF_FUSED")) return atoi(e) != 0;                            // development knob
+    return true;
+}
+
+// Dependency levels of small merges accumulated for ONE launch of k_merge_fused (every merge whole in one block: leaves,
+// prep, fill, traceback, merged tables; a grid barrier between the levels).  add() does the host bookkeeping of a level
+// right away -- merged profiles get their ids and (upper-bound sized) tables, consumed children are released -- so that
+// the next level can name them; flush() places everything and launches.
+struct FusedAccum {
+    std::vector<famsa_dp_job> jobs;
+    std::vector<DpJobExt> ext;
+    std::vector<LeafDesc> leaves;
+    std::vector<std::pair<uint32_t, int>> leaf_slot;                 // (job, side), job index over the whole accumulation
+    std::vector<uint32_t> level_start{0};
+    std::vector<uint32_t> merged_ids, merged_gen;
+    std::vector<ConJobDev> con;
+    size_t leaf_bytes = 0, dev_bytes_est = 0;
+    uint64_t path_bytes = 0;                                         // host path slots used (16-byte aligned when host_mapped)
+    uint32_t max_level = 0;
+    bool empty() const { return jobs.empty(); }
+};
+
+static size_t fused_dev_estimate(const famsa_dp_job& j)
+{
+    return sizeof(famsa_dp_result) + sizeof(DpMeta) + align_up((uint64_t)j.p1.width + j.p2.width, 16) + 2 * 384ull * (std::max(j.p1.width, j.p2.width) + 2) +
+           dp_scratch_bytes(j.p1.width, j.p2.width) + skew_elems(j.p1.width, j.p2.width) + 1024;
+}
+
+// may the level (already resolved into `jobs`) join the accumulation?  Checks the rings conservatively.
+static bool fused_fits(famsa_ctx* ctx, const FusedAccum& A, const std::vector<famsa_dp_job>& jobs)
+{
+    ProfState& P = ctx->prof;
+    size_t dev = A.dev_bytes_est;
+    for (const famsa_dp_job& j : jobs) dev += fused_dev_estimate(j);
+    const size_t host = (A.jobs.size() + jobs.size()) * (sizeof(DpJobDev) + sizeof(FusedJob)) + (A.level_start.size() + 2) * sizeof(uint32_t) + 1024;
+    return P.d_ring.fits(dev + 4096) && P.h_ring.fits(host);
+}
+
+static int fused_add(famsa_ctx* ctx, FusedAccum& A, const famsa_prof_merge* merges, uint32_t n, std::vector<famsa_dp_job>& jobs, std::vector<DpJobExt>& ext,
+                     std::vector<LeafDesc>& leaves, std::vector<std::pair<uint32_t, int>>& leaf_slot, size_t leaf_bytes, bool align16)
+{
+    ProfState& P = ctx->prof;
+    const uint32_t base = (uint32_t)A.jobs.size();
+    size_t slab_bytes = 0;
+    for (uint32_t k = 0; k < n; ++k) slab_bytes += table_bytes(jobs[k].p1.width + jobs[k].p2.width);
+    int slab;
+    FB_TRY(new_slab(ctx, slab_bytes, &slab));
+    size_t cur = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const uint32_t ub = jobs[k].p1.width + jobs[k].p2.width;
+        const uint32_t id = new_entry(P);
+        place(P, id, slab, &cur, ub, jobs[k].p1.card + jobs[k].p2.card);
+        P.entries[id].pending = true;
+        A.merged_ids.push_back(id);
+        A.merged_gen.push_back(P.entries[id].gen);
+        ext[k].w_dst = P.d_widths.as<uint32_t>() + id;
+        A.con.push_back(ConJobDev{P.entries[id].scores, P.entries[id].counters, base + k, 0});
+        A.dev_bytes_est += fused_dev_estimate(jobs[k]);
+        A.path_bytes += align16 ? align_up((uint64_t)jobs[k].p1.width + jobs[k].p2.width, 16) : (uint64_t)jobs[k].p1.width + jobs[k].p2.width;
+    }
+    for (auto& ls : leaf_slot) ls.first += base;
+    A.jobs.insert(A.jobs.end(), jobs.begin(), jobs.end());
+    A.ext.insert(A.ext.end(), ext.begin(), ext.end());
+    A.leaves.insert(A.leaves.end(), leaves.begin(), leaves.end());
+    A.leaf_slot.insert(A.leaf_slot.end(), leaf_slot.begin(), leaf_slot.end());
+    A.leaf_bytes += leaf_bytes;
+    A.level_start.push_back((uint32_t)A.jobs.size());
+    A.max_level = std::max(A.max_level, n);
+    // the children are consumed (msa.cpp:406-407).  Their storage must not be handed out again before this launch has
+    // been queued: inside one launch there is no kernel boundary that would invalidate a stale L1 line
+    P.arena.defer = true;
+    for (uint32_t k = 0; k < n; ++k)
+        for (uint32_t c : {merges[k].child1, merges[k].child2})
+            if (!(c & FAMSA_PROF_LEAF)) FB_TRY(release_entry(ctx, c));
+    return FAMSA_OK;
+}
+
+static int fused_flush(famsa_ctx* ctx, FusedAccum& A, const int64_t gaps[4], famsa_dp_result* h_results, uint8_t* h_paths, bool host_mapped, ProfTicket* T)
+{
+    ProfState& P = ctx->prof;
+    LcsState& L = ctx->lcs;
+    cudaStream_t st = ctx->stream;
+    const uint32_t n = (uint32_t)A.jobs.size(), n_levels = (uint32_t)A.level_start.size() - 1;
+    std::vector<DpJobDev> plan_jobs(n);
+    DpFusedPlan plan;
+    FB_TRY(dp_fused_plan(A.jobs.data(), A.ext.data(), n, host_mapped, plan_jobs.data(), &plan));
+    const size_t ho_fj = align_up(sizeof(DpJobDev) * n, 256);
+    const size_t ho_lv = align_up(ho_fj + sizeof(FusedJob) * n, 256);
+    const size_t h_bytes = ho_lv + sizeof(uint32_t) * (n_levels + 1);
+    const size_t o_res = 0;
+    const size_t o_meta = align_up(o_res + sizeof(famsa_dp_result) * n, 256);
+    const size_t o_path = align_up(o_meta + sizeof(DpMeta) * n, 256);
+    const size_t o_leaf = align_up(o_path + std::max<uint64_t>(plan.path_bytes, 1), 256);
+    const size_t o_scr = align_up(o_leaf + A.leaf_bytes, 256);
+    const size_t o_skew = align_up(o_scr + plan.scratch_bytes, 256);
+    const size_t d_bytes = o_skew + plan.skew_bytes;
+    const size_t h_off = P.h_ring.alloc(h_bytes), d_off = P.d_ring.alloc(d_bytes);
+    if (h_off == (size_t)-1 || d_off == (size_t)-1) { set_error("internal: the fused batch does not fit its rings"); return FAMSA_E_NOMEM; }
+    unsigned char* hb = P.h_ring_mem + h_off;
+    unsigned char* db = P.d_ring_mem.as<unsigned char>() + d_off;
+    DpJobDev* hj = reinterpret_cast<DpJobDev*>(hb);
+    FusedJob* fj = reinterpret_cast<FusedJob*>(hb + ho_fj);
+    uint32_t* hl = reinterpret_cast<uint32_t*>(hb + ho_lv);
+    famsa_dp_result* d_results = reinterpret_cast<famsa_dp_result*>(db + o_res);
+    for (uint32_t k = 0; k < n; ++k) { fj[k].leaf[0].seq = fj[k].leaf[1].seq = 0xffffffffu; fj[k].con = A.con[k]; }
+    size_t cur = 0;
+    for (size_t a = 0; a < A.leaves.size(); ++a) {
+        const uint32_t k = A.leaf_slot[a].first;
+        const int side = A.leaf_slot[a].second;
+        const uint32_t w = side ? A.jobs[k].p2.width : A.jobs[k].p1.width;
+        char* base = reinterpret_cast<char*>(db + o_leaf + cur);
+        LeafDesc ld = A.leaves[a];
+        ld.scores = reinterpret_cast<long long*>(base);
+        ld.counters = reinterpret_cast<int*>(base + ((size_t)w + 1) * kRows * sizeof(long long));
+        (side ? plan_jobs[k].s2 : plan_jobs[k].s1) = ld.scores;
+        (side ? plan_jobs[k].c2 : plan_jobs[k].c1) = ld.counters;
+        fj[k].leaf[side] = ld;
+        cur += table_bytes(w);
+    }
+    memcpy(hj, plan_jobs.data(), sizeof(DpJobDev) * n);
+    memcpy(hl, A.level_start.data(), sizeof(uint32_t) * (n_levels + 1));
+    FusedParams FP{fj, hl, n_levels, L.d_raw_codes.as<int8_t>(), L.d_raw_off.as<uint64_t>(), L.d_raw_len.as<uint32_t>(), P.d_sm.as<long long>(),
+                   0, P.d_block_counter.as<unsigned>(), nullptr, 0};
+    if (host_mapped) { FP.h_done = P.h_done; FP.done_seq = ++P.done_seq; }
+    if (getenv("FAMSA_FUSED_TIMING")) { static int launch_no = 0; FP.timing = 2 + (++launch_no & 1); }   // development aid
+    if (!host_mapped) { FB_CUDA(cudaEventRecord(P.ev[0], st)); FB_CUDA(cudaEventRecord(P.ev[1], st)); }
+    const uint32_t grid = std::max(1u, std::min(A.max_level, (uint32_t)ctx->sm_count));      // co-resident: the levels meet at a spin barrier
+    FB_TRY(dp_fused_launch(ctx, hj, n, gaps, d_results, db + o_path, reinterpret_cast<DpMeta*>(db + o_meta), db + o_scr, db + o_skew,
+                           host_mapped ? h_results : nullptr, host_mapped ? h_paths : nullptr, &FP, grid, plan.cells, !host_mapped, st));
+    if (!host_mapped) {
+        FB_CUDA(cudaEventRecord(P.ev[2], st));
+        P.timing_valid = true;
+        FB_CUDA(cudaMemcpyAsync(h_results, d_results, sizeof(famsa_dp_result) * n, cudaMemcpyDeviceToHost, st));
+        if (plan.path_bytes) FB_CUDA(cudaMemcpyAsync(h_paths, db + o_path, plan.path_bytes, cudaMemcpyDeviceToHost, st));
+        T->done = take_event(P);
+        FB_CUDA(cudaEventRecord(T->done, st));
+    } else T->done_seq = FP.done_seq;
+    // storage of the consumed children may be handed out again from here on (everything later is behind this launch)
+    P.arena.flush_deferred();
+    T->merged_ids = A.merged_ids; T->merged_gen = A.merged_gen;
+    T->n = n; T->h_results = h_results; T->h_paths = h_paths; T->path_bytes = plan.path_bytes; T->cells_bound = plan.cells;
+    T->ring_host_end = P.h_ring.head; T->ring_dev_end = P.d_ring.head;
+    A = FusedAccum();
+    return FAMSA_OK;
+}
+
+static int ensure_rings(famsa_ctx* ctx)
+{
+    ProfState& P = ctx->prof;
+    if (P.h_ring_mem) return FAMSA_OK;
+    const size_t hcap = 8u << 20, dcap = 512u << 20;
+    FB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&P.h_ring_mem), hcap, cudaHostAllocMapped));
+    P.h_ring.cap = hcap;
+    FB_TRY(P.d_ring_mem.reserve(dcap));
+    P.d_ring.cap = dcap;
+    FB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(const_cast<unsigned long long**>(&P.h_done)), 64, cudaHostAllocMapped));
+    *P.h_done = 0;
+    FB_TRY(P.d_block_counter.reserve(64));
+    FB_CUDA(cudaMemsetAsync(P.d_block_counter.p, 0, 64, ctx->stream));
+    return FAMSA_OK;
+}
+
+// host_mapped: h_results / h_paths are mapped pinned memory the device may write to directly (and path slots are 16-byte
+// aligned: job k's path at the running sum of align16(w1 + w2))
+static int prof_launch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t n, const int64_t gaps[4],
+                       famsa_dp_result* h_results, uint8_t* h_paths, uint64_t path_cap, bool host_mapped, ProfTicket* T)
+{
+    ProfState& P = ctx->prof;
+    LcsState& L = ctx->lcs;
+    cudaStream_t st = ctx->stream;
+
+    // resolve the children; leaves get scratch tables for the duration of the batch
+    std::vector<famsa_dp_job> jobs;
+    std::vector<DpJobExt> ext;
+    std::vector<LeafDesc> leaves;
+    std::vector<std::pair<uint32_t, int>> leaf_slot;                 // (job, side) per leaf, in `leaves` order
+    size_t leaf_bytes = 0;
+    uint64_t path_need = 0, cells = 0;
+    FB_TRY(prof_resolve(ctx, merges, n, jobs, ext, leaves, leaf_slot, leaf_bytes, path_need, cells));
     if (host_mapped) {
         path_need = 0;
         for (uint32_t k = 0; k < n; ++k) path_need += align_up((uint64_t)jobs[k].p1.width + jobs[k].p2.width, 16);
@@ -356,88 +515,17 @@ static int prof_launch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t 
         return FAMSA_E_INVALID;
     }
     FB_TRY(ensure_widths(ctx, P.entries.size() + n));
+    // A batch of small merges only (the chain-like parts of a guide tree: every level one or a few short merges) runs
+    // every merge whole in one block of k_merge_fused instead of five launches.
+    bool fused = fused_eligible(jobs);
     if (fused) {
-        // ---- ring-backed fast path: descriptors in mapped host memory, every device buffer from the device ring, results and
-        // paths written to the host by the kernel itself when the caller's buffers allow it; one launch, no copy, no allocator call
         FB_TRY(ensure_rings(ctx));
-        std::vector<DpJobDev> plan_jobs(n);
-        DpFusedPlan plan;
-        FB_TRY(dp_fused_plan(jobs.data(), ext.data(), n, host_mapped, plan_jobs.data(), &plan));
-        const size_t h_bytes = align_up(sizeof(DpJobDev) * n, 256) + sizeof(FusedJob) * n;
-        const size_t o_res = 0;
-        const size_t o_meta = align_up(o_res + sizeof(famsa_dp_result) * n, 256);
-        const size_t o_path = align_up(o_meta + sizeof(DpMeta) * n, 256);
-        const size_t o_leaf = align_up(o_path + std::max<uint64_t>(plan.path_bytes, 1), 256);
-        const size_t o_scr = align_up(o_leaf + leaf_bytes, 256);
-        const size_t o_skew = align_up(o_scr + plan.scratch_bytes, 256);
-        const size_t d_bytes = o_skew + plan.skew_bytes;
-        const Ring h_save = P.h_ring, d_save = P.d_ring;
-        const size_t h_off = P.h_ring.alloc(h_bytes);
-        const size_t d_off = h_off == (size_t)-1 ? (size_t)-1 : P.d_ring.alloc(d_bytes);
-        if (h_off == (size_t)-1 || d_off == (size_t)-1) { P.h_ring = h_save; P.d_ring = d_save; fused = false; }
-        else {
-            int slab;
-            size_t slab_bytes = 0;
-            for (uint32_t k = 0; k < n; ++k) slab_bytes += table_bytes(jobs[k].p1.width + jobs[k].p2.width);
-            FB_TRY(new_slab(ctx, slab_bytes, &slab));
-            unsigned char* hb = P.h_ring_mem + h_off;
-            unsigned char* db = P.d_ring_mem.as<unsigned char>() + d_off;
-            DpJobDev* hj = reinterpret_cast<DpJobDev*>(hb);
-            FusedJob* fj = reinterpret_cast<FusedJob*>(hb + align_up(sizeof(DpJobDev) * n, 256));
-            famsa_dp_result* d_results = reinterpret_cast<famsa_dp_result*>(db + o_res);
-            for (uint32_t k = 0; k < n; ++k) fj[k].leaf[0].seq = fj[k].leaf[1].seq = 0xffffffffu;
-            size_t cur = 0;
-            for (size_t a = 0; a < leaves.size(); ++a) {
-                const uint32_t k = leaf_slot[a].first;
-                const int side = leaf_slot[a].second;
-                const uint32_t w = side ? jobs[k].p2.width : jobs[k].p1.width;
-                char* base = reinterpret_cast<char*>(db + o_leaf + cur);
-                leaves[a].scores = reinterpret_cast<long long*>(base);
-                leaves[a].counters = reinterpret_cast<int*>(base + ((size_t)w + 1) * kRows * sizeof(long long));
-                (side ? plan_jobs[k].s2 : plan_jobs[k].s1) = leaves[a].scores;
-                (side ? plan_jobs[k].c2 : plan_jobs[k].c1) = leaves[a].counters;
-                fj[k].leaf[side] = leaves[a];
-                cur += table_bytes(w);
-            }
-            T->merged_ids.assign(n, 0);
-            T->merged_gen.assign(n, 0);
-            cur = 0;
-            for (uint32_t k = 0; k < n; ++k) {
-                const uint32_t ub = jobs[k].p1.width + jobs[k].p2.width;
-                const uint32_t id = new_entry(P);
-                place(P, id, slab, &cur, ub, jobs[k].p1.card + jobs[k].p2.card);
-                P.entries[id].pending = true;
-                T->merged_ids[k] = id;
-                T->merged_gen[k] = P.entries[id].gen;
-                plan_jobs[k].w_dst = P.d_widths.as<uint32_t>() + id;
-                fj[k].con.os = P.entries[id].scores; fj[k].con.oc = P.entries[id].counters; fj[k].con.job = k; fj[k].con.tile0 = 0;
-            }
-            memcpy(hj, plan_jobs.data(), sizeof(DpJobDev) * n);          // (write-combined order does not matter: the launch orders it)
-            FusedParams FP{fj, L.d_raw_codes.as<int8_t>(), L.d_raw_off.as<uint64_t>(), L.d_raw_len.as<uint32_t>(), P.d_sm.as<long long>(),
-                           0, P.d_block_counter.as<unsigned>(), nullptr, 0};
-            const bool nowait = host_mapped && getenv("FAMSA_TREE_NOWAIT");          // experiment: no host traffic at all (results stay stale)
-            if (host_mapped && !nowait) { FP.h_done = P.h_done; FP.done_seq = ++P.done_seq; }
-            if (getenv("FAMSA_FUSED_TIMING")) { static int launch_no = 0; FP.timing = 2 + (++launch_no & 1); }   // development aid
-            if (!host_mapped) { FB_CUDA(cudaEventRecord(P.ev[0], st)); FB_CUDA(cudaEventRecord(P.ev[1], st)); }
-            FB_TRY(dp_fused_launch(ctx, hj, n, gaps, d_results, db + o_path, reinterpret_cast<DpMeta*>(db + o_meta), db + o_scr, db + o_skew,
-                                   host_mapped && !nowait ? h_results : nullptr, host_mapped && !nowait ? h_paths : nullptr, &FP, plan.cells, !host_mapped, st));
-            if (!host_mapped) { FB_CUDA(cudaEventRecord(P.ev[2], st)); P.timing_valid = true; }
-            if (!host_mapped) {
-                FB_CUDA(cudaMemcpyAsync(h_results, d_results, sizeof(famsa_dp_result) * n, cudaMemcpyDeviceToHost, st));
-                if (plan.path_bytes) FB_CUDA(cudaMemcpyAsync(h_paths, db + o_path, plan.path_bytes, cudaMemcpyDeviceToHost, st));
-            }
-            for (uint32_t k = 0; k < n; ++k)
-                for (uint32_t c : {merges[k].child1, merges[k].child2})
-                    if (!(c & FAMSA_PROF_LEAF)) FB_TRY(release_entry(ctx, c));
-            if (nowait) { T->done_seq = 0; T->done = nullptr; }
-            else if (host_mapped) T->done_seq = FP.done_seq;
-            else { T->done = take_event(P); FB_CUDA(cudaEventRecord(T->done, st)); }
-            T->n = n; T->h_results = h_results; T->h_paths = h_paths; T->path_bytes = plan.path_bytes; T->cells_bound = plan.cells;
-            T->ring_host_end = P.h_ring.head; T->ring_dev_end = P.d_ring.head;
-            return FAMSA_OK;
+        FusedAccum A;
+        if (fused_fits(ctx, A, jobs)) {
+            FB_TRY(fused_add(ctx, A, merges, n, jobs, ext, leaves, leaf_slot, leaf_bytes, host_mapped));
+            return fused_flush(ctx, A, gaps, h_results, h_paths, host_mapped, T);
         }
     }
-
     // merged tables: one slab per batch, every profile sized for the widest alignment possible (w1 + w2 columns)
     size_t slab_bytes = 0;
     for (uint32_t k = 0; k < n; ++k) slab_bytes += table_bytes(jobs[k].p1.width + jobs[k].p2.width);
@@ -509,9 +597,7 @@ static int prof_launch(famsa_ctx* ctx, const famsa_prof_merge* merges, uint32_t 
     // DP + traceback on the resident tables (dp.cu)
     DpMeta* d_meta = nullptr;
     void* dp_blob = nullptr;
-    FusedParams FP{reinterpret_cast<const FusedJob*>(blob + o_con), L.d_raw_codes.as<int8_t>(), L.d_raw_off.as<uint64_t>(),
-                   L.d_raw_len.as<uint32_t>(), P.d_sm.as<long long>(), getenv("FAMSA_FUSED_TIMING") ? 1 : 0};
-    FB_TRY(dp_run_device(ctx, jobs.data(), ext.data(), n, gaps, d_results, d_path, nullptr, &d_meta, &dp_blob, st, fused ? &FP : nullptr));
+    FB_TRY(dp_run_device(ctx, jobs.data(), ext.data(), n, gaps, d_results, d_path, nullptr, &d_meta, &dp_blob, st));
     FB_CUDA(cudaEventRecord(P.ev[1], st));
     if (!fused) {
         k_prof_construct<<<tiles, kConThreads, 0, st>>>(reinterpret_cast<const ConJobDev*>(blob + o_con), n, d_meta, d_results, d_path,
@@ -654,6 +740,8 @@ int prof_align_tree(famsa_ctx* ctx, const int32_t* tree, uint32_t n_leaves, cons
     constexpr size_t kMaxInFlight = 8;
     FB_CUDA(cudaEventRecord(P.ev_tree[0], ctx->stream));
     double t_collect = 0, t_launch = 0;
+    uint32_t max_exact = 0;                                         // widest profile whose real width is known
+    for (uint32_t i = 0; i < n_leaves; ++i) max_exact = std::max(max_exact, width[i]);
     auto now = []() { return std::chrono::steady_clock::now(); };
     auto collect_front = [&]() -> int {
         InFlight& f = q.front();
@@ -666,6 +754,7 @@ int prof_align_tree(famsa_ctx* ctx, const int32_t* tree, uint32_t n_leaves, cons
             r.path_offset += f.path_base;
             results[k] = r;
             width[n_leaves + k] = r.path_len;
+            max_exact = std::max(max_exact, r.path_len);
             cells += (uint64_t)r.rows_width * r.cols_width;
         }
         q.pop_front();
@@ -675,10 +764,106 @@ int prof_align_tree(famsa_ctx* ctx, const int32_t* tree, uint32_t n_leaves, cons
     // paths of all merges: one pinned arena, grown only while nothing is in flight
     uint64_t arena_need = 0;
     for (uint32_t i = 0; i < n_leaves; ++i) arena_need += width[i];
-    arena_need = arena_need * 4 + (1u << 20);
+    arena_need = arena_need * 8 + (64u << 20);
     FB_TRY(pinned_reserve(reinterpret_cast<void**>(&P.h_tree_paths), &P.h_tree_paths_cap, arena_need));
+    // Consecutive levels of small merges are accumulated into ONE launch of the fused kernel (a grid barrier between the
+    // levels instead of a kernel boundary): the chain-like stretches of a guide tree are a single merge per level.
+    FB_TRY(ensure_rings(ctx));
+    FusedAccum acc;
+    std::vector<uint32_t> acc_merges;
+    uint64_t acc_path_base = 0;
+    size_t acc_res_base = 0;
+    uint32_t acc_levels = 0;
+    constexpr uint32_t kMaxFusedLevels = 32;
+    auto flush_acc = [&]() -> int {
+        if (acc.empty()) return FAMSA_OK;
+        // at most two fused launches uncollected: the widths of everything older become exact, which keeps the upper bounds
+        // of the levels being accumulated (sums over the uncollected part of a chain) from running away
+        while (q.size() >= 2) { const int r = collect_front(); if (r) return r; }
+        q.emplace_back();
+        InFlight& f = q.back();
+        f.merge_ids = acc_merges;
+        f.path_base = acc_path_base;
+        f.res_base = acc_res_base;
+        if (getenv("FAMSA_DP_DEBUG")) fprintf(stderr, "[tree] fused launch: %u levels, %zu merges\n", acc_levels, acc.jobs.size());
+        const auto t0 = now();
+        const int r = fused_flush(ctx, acc, gaps, P.h_tree_results + acc_res_base, P.h_tree_paths + acc_path_base, true, &f.t);
+        t_launch += std::chrono::duration<double, std::micro>(now() - t0).count();
+        if (r) { q.pop_back(); return r; }
+        acc_merges.clear();
+        acc_levels = 0;
+        ++n_batches;
+        max_in_flight = std::max<uint32_t>(max_in_flight, (uint32_t)q.size());
+        return FAMSA_OK;
+    };
     for (size_t lv = 0; lv < levels.size() && rc == FAMSA_OK; ++lv) {
         const std::vector<uint32_t>& level = levels[lv];
+        {
+            // small merges: join the accumulation when the level fits
+            auto finished = [&](const ProfTicket& t) { return t.done_seq ? *P.h_done >= t.done_seq : (!t.done || cudaEventQuery(t.done) == cudaSuccess); };
+            while (!q.empty() && finished(q.front().t) && rc == FAMSA_OK) rc = collect_front();
+            if (rc) break;
+            // A queued child is known by an upper bound only (the sum of its children's bounds), and along a chain the bounds
+            // add up level after level however many older levels have been collected since.  Once a bound has drifted far
+            // from anything real, wait for the device: every width becomes exact again.
+            bool drifted = false;
+            for (uint32_t k : level)
+                for (int side = 0; side < 2; ++side) {
+                    const uint32_t c = (uint32_t)tree[2 * k + side];
+                    if (c >= n_leaves && P.entries[handle[c]].pending && width[c] > 1024 + 2 * max_exact) drifted = true;
+                }
+            if (drifted) {
+                rc = flush_acc();
+                while (!q.empty() && rc == FAMSA_OK) rc = collect_front();
+                if (rc) break;
+                ++n_drains;
+            }
+            std::vector<famsa_prof_merge> mg(level.size());
+            for (size_t a = 0; a < level.size(); ++a) {
+                const uint32_t k = level[a];
+                mg[a].child1 = handle[(uint32_t)tree[2 * k]];
+                mg[a].child2 = handle[(uint32_t)tree[2 * k + 1]];
+            }
+            std::vector<famsa_dp_job> jobs;
+            std::vector<DpJobExt> ext;
+            std::vector<LeafDesc> leaves;
+            std::vector<std::pair<uint32_t, int>> leaf_slot;
+            size_t leaf_bytes = 0;
+            uint64_t pn = 0, cl = 0;
+            rc = prof_resolve(ctx, mg.data(), (uint32_t)mg.size(), jobs, ext, leaves, leaf_slot, leaf_bytes, pn, cl);
+            if (rc) break;
+            uint64_t path_need = 0;
+            for (const famsa_dp_job& j : jobs) path_need += align_up((uint64_t)j.p1.width + j.p2.width, 16);
+            if (fused_eligible(jobs) && path_cursor + path_need <= P.h_tree_paths_cap) {
+                if (!(acc_levels < kMaxFusedLevels && acc.jobs.size() + jobs.size() <= 8192 && fused_fits(ctx, acc, jobs))) {
+                    rc = flush_acc();
+                    if (rc) break;
+                    while (q.size() >= kMaxInFlight && rc == FAMSA_OK) rc = collect_front();
+                    while (!fused_fits(ctx, acc, jobs) && !q.empty() && rc == FAMSA_OK) rc = collect_front();   // ring space comes back in order
+                    if (rc) break;
+                }
+                if (fused_fits(ctx, acc, jobs)) {
+                    if (acc.empty()) { acc_path_base = path_cursor; acc_res_base = res_cursor; }
+                    const size_t first = acc.merged_ids.size();
+                    rc = fused_add(ctx, acc, mg.data(), (uint32_t)mg.size(), jobs, ext, leaves, leaf_slot, leaf_bytes, true);
+                    if (rc) break;
+                    for (size_t a = 0; a < level.size(); ++a) {
+                        const uint32_t k = level[a];
+                        handle[n_leaves + k] = acc.merged_ids[first + a];
+                        width[n_leaves + k] = P.entries[acc.merged_ids[first + a]].width;   // the bound w1 + w2
+                    }
+                    acc_merges.insert(acc_merges.end(), level.begin(), level.end());
+                    path_cursor += path_need;
+                    res_cursor += level.size();
+                    ++acc_levels;
+                    peak_bytes = std::max(peak_bytes, P.resident_bytes);
+                    continue;
+                }
+            }
+            if (getenv("FAMSA_DP_DEBUG")) fprintf(stderr, "[tree] level %zu (%zu merges) not fused: eligible %d, path room %d\n", lv, level.size(), (int)fused_eligible(jobs), (int)(path_cursor + path_need <= P.h_tree_paths_cap)), fprintf(stderr, "        first job: %u (card %u) x %u (card %u)\n", jobs[0].p1.width, jobs[0].p1.card, jobs[0].p2.width, jobs[0].p2.card);
+            rc = flush_acc();                                         // this level goes launch by launch: everything before it first
+            if (rc) break;
+        }
         // collect whatever has finished already (tightens the bounds for free)
         auto finished = [&](const ProfTicket& t) { return t.done_seq ? *P.h_done >= t.done_seq : (!t.done || cudaEventQuery(t.done) == cudaSuccess); };
         while (!q.empty() && finished(q.front().t) && rc == FAMSA_OK) rc = collect_front();
@@ -745,6 +930,7 @@ int prof_align_tree(famsa_ctx* ctx, const int32_t* tree, uint32_t n_leaves, cons
         max_in_flight = std::max<uint32_t>(max_in_flight, (uint32_t)q.size());
         peak_bytes = std::max(peak_bytes, P.resident_bytes);
     }
+    if (rc == FAMSA_OK) rc = flush_acc();
     while (!q.empty()) { const int r2 = collect_front(); if (rc == FAMSA_OK) rc = r2; }
     if (rc) return rc;
     if (getenv("FAMSA_DP_DEBUG"))

@@ -62,12 +62,14 @@ struct FusedJob {
 };
 struct FusedParams {
     const FusedJob* jobs;
+    const uint32_t* level_start;                                    // n_levels + 1 job indices: the launch runs these dependency levels
+    uint32_t n_levels;                                              // one after the other, a grid barrier in between
     const int8_t* codes; const uint64_t* off; const uint32_t* len;   // the uploaded sequences (caller order)
     const long long* sm;                                            // 24 x 24 score matrix
     int timing;                                                     // development aid: accumulate per-phase times
     // completion without a CUDA event (an event record between two short kernels costs more than the kernels' launch gap):
     // the last block to finish publishes `done_seq` in mapped host memory, after everybody's results have been fenced
-    unsigned* block_counter;                                        // device, zero between launches
+    unsigned* block_counter;                                        // device, two words, zero between launches: [0] finished blocks, [1] barrier arrivals
     volatile unsigned long long* h_done;                            // mapped host memory, or NULL
     unsigned long long done_seq;
 };

@@ -38,5 +38,5 @@ import ctypes as C
 if os.environ.get('FAMSA_FUSED_TIMING'):
     out = (C.c_double * 8)()
     eng.lib.famsa_debug_fused_phases(out)
-    names = ['leaf', 'prep', 'fill', 'dirs->smem', 'trace', 'construct', 'whole_block', 'idle_before_launch']
+    names = ['leaf', 'prep', 'fill', 'dirs->smem', 'trace', 'construct', 'barrier_wait', 'idle_before_launch']
     print({k: round(v / 1e3, 1) for k, v in zip(names, out)}, 'us total; levels:', st['n_batches'])
