@@ -181,11 +181,13 @@ def dp_verify_batch(eng, rows, n_paths=48):
         m, total = dp.align(p1, p2, 1)
         ok_tot += int(total == got[k]["total"])
         if k < n_paths:
-            want = pyoracle.path_from_rows(dp.rows(m), na, nb, got[k]["swapped"])
-            ok_path += int(len(want) == len(got[k]["path"]) and np.array_equal(want, got[k]["path"]))
+            # whole traceback path against the C restatement of CProfile::Align (oracle/dp_oracle.c, itself pinned to the
+            # reference's goldens and to the live reference by tests/test_oracle_dp.py) on the reference's own tables
+            want = pyoracle.dp_align(*jobs[k], np.array(DP_GAPS, dtype=np.int64))
+            ok_path += int(want["total"] == total and want["swapped"] == got[k]["swapped"] and np.array_equal(want["path"], got[k]["path"]))
         dp.free(m)
     dp.close()
-    return {"totals_equal": ok_tot, "of": len(rows), "paths_equal": ok_path, "paths_checked": min(n_paths, len(rows))}
+    return {"totals_equal_to_reference": ok_tot, "of": len(rows), "paths_equal_to_pinned_oracle": ok_path, "paths_checked": min(n_paths, len(rows))}
 
 
 def bench_dp(eng, torch, dist, world, rank, steps, warmup, l2_flush, stream, want_cpu):

@@ -360,6 +360,57 @@ __global__ void k_lcs_exact(const uint8_t* __restrict__ codes, const uint32_t* _
     else static_cast<uint32_t*>(out)[idx] = lcs;
 }
 
+// All special rows of a call in ONE launch: blockIdx.y = the row, its 64-bit masks are built in shared memory by the
+// block itself, X[] lives in the thread (local memory, L1-resident) -- for rows of at most kExactWords * 64 residues.
+// rows[r] = {sorted position of the row, out_base (element offset of the row's first result), n_col, only_long_cols}.
+constexpr int kExactWords = 64;
+struct ExactRow { uint32_t sp, n_col, only_long, pad; unsigned long long out_base; };
+__global__ void __launch_bounds__(128) k_lcs_exact_batch(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ code_off,
+                                                         const uint32_t* __restrict__ len_sorted, const uint32_t* __restrict__ invperm,
+                                                         const ExactRow* __restrict__ rows, const uint32_t* __restrict__ col_ids,
+                                                         const uint32_t* __restrict__ group_nl, void* __restrict__ out, int elem_bytes)
+{
+    __shared__ unsigned long long masks[kMaskRows * kExactWords];
+    const ExactRow R = rows[blockIdx.y];
+    if (blockIdx.x * blockDim.x >= R.n_col) return;
+    const uint32_t rlen = len_sorted[R.sp], nw = rlen ? (rlen + 63) / 64 : 1;
+    const uint8_t* rsrc = codes + (size_t)code_off[R.sp] * 16;
+    for (uint32_t i = threadIdx.x; i < kMaskRows * nw; i += blockDim.x) masks[i] = 0;
+    __syncthreads();
+    for (uint32_t pos = threadIdx.x; pos < rlen; pos += blockDim.x) {
+        const uint32_t c = rsrc[pos];
+        if (c < 20) atomicOr(&masks[c * nw + pos / 64], 1ull << (pos % 64));
+    }
+    __syncthreads();
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= R.n_col) return;
+    const uint32_t col = col_ids ? col_ids[k] : k;
+    const uint32_t sq = invperm[col];
+    if (R.only_long && group_nl[sq / 32] != 0) return;
+    const uint32_t len = len_sorted[sq];
+    const uint8_t* src = codes + (size_t)code_off[sq] * 16;
+    unsigned long long x[kExactWords];
+    for (uint32_t w = 0; w < nw; ++w) x[w] = ~0ull;
+    for (uint32_t t = 0; t < len; ++t) {
+        const uint32_t c = src[t];
+        if (c >= 20) continue;
+        const unsigned long long* m = masks + c * nw;
+        unsigned long long carry = 0;
+        for (uint32_t w = 0; w < nw; ++w) {
+            const unsigned long long v = x[w];
+            const unsigned long long tb = v & m[w];
+            const unsigned long long sum = v + tb + carry;
+            carry = sum < v;
+            x[w] = sum | (v - tb);
+        }
+    }
+    uint32_t lcs = 0;
+    for (uint32_t w = 0; w < nw; ++w) lcs += __popcll(~x[w]);
+    const size_t idx = R.out_base + k;
+    if (elem_bytes == 2) static_cast<uint16_t*>(out)[idx] = (uint16_t)lcs;
+    else static_cast<uint32_t*>(out)[idx] = lcs;
+}
+
 // ------------------------------------------------------------------------------------------------
 // medoid assignment: float Transform + running arg-min over the seed rows (FastTree.cpp:309-324)
 // ------------------------------------------------------------------------------------------------
@@ -794,11 +845,20 @@ __global__ void __launch_bounds__(1024) k_upgma(float* __restrict__ dist, uint32
         __syncthreads();
         return sh_pick;
     };
+    // what the previous merge changed (row L got a new cache, row R died): every thread knows it from the reductions, so the
+    // scan below does not have to wait for thread 0's writes to become visible -- two grid barriers per merge, not three
+    uint32_t pL = 0xffffffffu, pR = 0xffffffffu;
+    unsigned long long pN = kNoCand;
     for (uint32_t it = 0; it + 1 < n; ++it) {
         // ---- the live row with the smallest cached distance (first such row)
         unsigned long long best = kNoCand;
-        for (uint32_t j = gtid; j < n; j += gthreads)
-            if (node[j] >= 0) { const float d = mind[j]; if (d < kUpgmaBig) { const unsigned long long c = pack_cand(d, j); best = c < best ? c : best; } }
+        for (uint32_t j = gtid; j < n; j += gthreads) {
+            if (j == pR) continue;
+            float d;
+            if (j == pL) { if (pN == kNoCand) continue; d = __uint_as_float((unsigned)(pN >> 32)); }
+            else { if (node[j] < 0) continue; d = mind[j]; }
+            if (d < kUpgmaBig) { const unsigned long long c = pack_cand(d, j); best = c < best ? c : best; }
+        }
         best = block_min_u64(best, sh);
         if (tid == 0) cand[(size_t)0 * nblk + blockIdx.x] = best;
         grid.sync();
@@ -827,9 +887,9 @@ __global__ void __launch_bounds__(1024) k_upgma(float* __restrict__ dist, uint32
             node[L] = (int)(n + it);
             nn[L] = npick == kNoCand ? 0x7fffffffu : (uint32_t)npick;
             mind[L] = npick == kNoCand ? kUpgmaBig : __uint_as_float((unsigned)(npick >> 32));
-            node[R] = -1;
+            node[R] = -1;                                                // (visible to everybody after the next barrier)
         }
-        grid.sync();                                                     // the caches of L and R are read by the next scan
+        pL = L; pR = R; pN = npick;
     }
 }
 
@@ -1063,6 +1123,37 @@ static int exact_row(famsa_ctx* ctx, uint32_t row, const uint32_t* d_col_ids, ui
     return FAMSA_OK;
 }
 
+// The exact recomputation of many rows: rows of at most kExactWords * 64 residues go through one launch of
+// k_lcs_exact_batch (masks in shared memory, X[] in the thread); longer ones keep the per-row global-memory path.
+struct ExactReq { uint32_t row, n_col; int only_long; size_t out_base; };
+static int exact_rows(famsa_ctx* ctx, const std::vector<ExactReq>& reqs, const uint32_t* d_col_ids, void* d_out, int elem_bytes, cudaStream_t st)
+{
+    LcsState& S = ctx->lcs;
+    std::vector<ExactRow> batch;
+    uint32_t max_cols = 0;
+    for (const ExactReq& q : reqs) {
+        if (!q.n_col) continue;
+        const uint32_t sp = S.h_invperm[q.row];
+        if (S.h_len_sorted[sp] <= (uint32_t)kExactWords * 64) {
+            batch.push_back(ExactRow{sp, q.n_col, (uint32_t)q.only_long, 0, (unsigned long long)q.out_base});
+            max_cols = std::max(max_cols, q.n_col);
+        } else FB_TRY(exact_row(ctx, q.row, d_col_ids, q.n_col, q.only_long, d_out, q.out_base, elem_bytes, st));
+    }
+    if (batch.empty()) return FAMSA_OK;
+    const uint32_t* d_group_nl = reinterpret_cast<const uint32_t*>(S.d_group_blob.as<uint64_t>() + S.n_groups);
+    for (size_t b0 = 0; b0 < batch.size(); b0 += 65535) {            // gridDim.y limit
+        const size_t nb = std::min<size_t>(65535, batch.size() - b0);
+        FB_TRY(S.d_masks64.reserve(sizeof(ExactRow) * nb));
+        FB_CUDA(cudaMemcpyAsync(S.d_masks64.p, batch.data() + b0, sizeof(ExactRow) * nb, cudaMemcpyHostToDevice, st));
+        k_lcs_exact_batch<<<dim3((max_cols + 127) / 128, (unsigned)nb), 128, 0, st>>>(
+            S.d_codes.as<uint8_t>(), S.d_code_off.as<uint32_t>(), S.d_len_sorted.as<uint32_t>(), S.d_invperm.as<uint32_t>(),
+            S.d_masks64.as<ExactRow>(), d_col_ids, d_group_nl, d_out, elem_bytes);
+        FB_CUDA(cudaGetLastError());
+        ctx->launches++;
+    }
+    return FAMSA_OK;
+}
+
 // Rows [row_begin, row_end) of the packed triangle.  With `bounds` (n_blocks + 1 ascending row indices spanning the
 // range) the work is issued block by block and block_events[b] is recorded after block b, so that a caller can
 // start copying finished blocks while later ones are still being computed; every tile list is uploaded up front.
@@ -1116,11 +1207,15 @@ int lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_o
             FB_TRY(launch_tile_nl(ctx, nl, P, (uint32_t)v.size(), st));
             at += v.size();
         }
+        // rows the tile kernel cannot answer for: dropped-carry rows entirely; over-long rows only against over-long columns
+        // (their pairs with shorter sequences were computed with the shorter one as the mask side -- the true LCS is symmetric)
+        std::vector<ExactReq> reqs;
         for (uint32_t row : special) {
             if (row < bounds[b] || row >= bounds[b + 1] || row == 0) continue;
-            const size_t base = (size_t)row * (row - 1) / 2 - P.tri_base;
-            FB_TRY(exact_row(ctx, row, nullptr, row, 0, d_out, base, elem_bytes, st));
+            const bool quirky = quirk_fixups && std::binary_search(S.h_quirky.begin(), S.h_quirky.end(), row);
+            reqs.push_back(ExactReq{row, row, quirky ? 0 : 1, (size_t)row * (row - 1) / 2 - (size_t)P.tri_base});
         }
+        FB_TRY(exact_rows(ctx, reqs, nullptr, d_out, elem_bytes, st));
         if (block_events) FB_CUDA(cudaEventRecord(block_events[b], st));
     }
     FB_CUDA(cudaEventRecord(ctx->ev[2], st));
@@ -1187,14 +1282,17 @@ int lcs_rows(famsa_ctx* ctx, const uint32_t* d_ref_ids, const uint32_t* h_ref_id
         ctx->launches++;
     }
     // exact fix-ups: dropped-carry / over-long reference rows entirely, over-long columns for the rest
-    for (uint32_t r = 0; r < n_ref; ++r) {
-        const uint32_t row = h_ref_ids[r];
-        const bool special = std::binary_search(S.h_quirky.begin(), S.h_quirky.end(), row) ||
-                             std::binary_search(S.h_long.begin(), S.h_long.end(), row);
-        if (special)
-            FB_TRY(exact_row(ctx, row, d_col_ids, n_col, 0, d_out, (size_t)r * n_col, elem_bytes, st));
-        else if (!S.h_long.empty())
-            FB_TRY(exact_row(ctx, row, d_col_ids, n_col, 1, d_out, (size_t)r * n_col, elem_bytes, st));
+    {
+        std::vector<ExactReq> reqs;
+        for (uint32_t r = 0; r < n_ref; ++r) {
+            const uint32_t row = h_ref_ids[r];
+            const bool quirky = std::binary_search(S.h_quirky.begin(), S.h_quirky.end(), row);
+            const bool is_long = std::binary_search(S.h_long.begin(), S.h_long.end(), row);
+            // (an over-long reference row is the streamed side of the tiles, so only its over-long columns are missing)
+            if (quirky) reqs.push_back(ExactReq{row, n_col, 0, (size_t)r * n_col});
+            else if (is_long || !S.h_long.empty()) reqs.push_back(ExactReq{row, n_col, 1, (size_t)r * n_col});
+        }
+        FB_TRY(exact_rows(ctx, reqs, d_col_ids, d_out, elem_bytes, st));
     }
     (void)d_ref_ids;
     (void)n;

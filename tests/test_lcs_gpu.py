@@ -97,6 +97,29 @@ def test_edge_cases(engine):
         engine.triangle(0, 5)
 
 
+@pytest.mark.parametrize("sort", [True, False])
+def test_over_long_and_quirky_sequences(engine, sort):
+    """5 % of the set longer than the register-resident kernel handles as the mask side (> 2048 aa, up to 4500 aa, one of
+    7000 aa beyond the batched exact kernel), a few with a dropped-carry word: over-long x shorter pairs come from the tile
+    kernel (shorter sequence as the mask side), over-long x over-long and dropped-carry rows from the exact kernels --
+    triangle and row calls against the oracle."""
+    rng = np.random.default_rng(91)
+    cl = random_set(rng, 170, 40, 400, alphabet=6)
+    cl += random_set(rng, 8, 2100, 4500, alphabet=6)
+    cl += random_set(rng, 1, 7000, 7000, alphabet=6)
+    q = np.full(300, 3, dtype=np.int8); q[70:90] = rng.integers(0, 6, 20)          # positions 128..191 all the same residue
+    cl += [q, np.concatenate([np.full(64, 2, dtype=np.int8), rng.integers(0, 6, 2300).astype(np.int8)])]
+    order = rng.permutation(len(cl))
+    cl = [cl[i] for i in order]
+    if sort:
+        cl.sort(key=lambda c: -len(c))
+    codes, offsets, lens = seqio.pack(cl)
+    engine.upload(codes, offsets, lens)
+    assert np.array_equal(engine.triangle(dtype=np.uint32), pyoracle.lcs_triangle(codes, offsets, lens))
+    refs = [0, 3, 57, len(cl) - 1] + [int(i) for i in np.argsort(-lens.astype(np.int64))[:4]]
+    assert np.array_equal(engine.rows(refs), pyoracle.lcs_rows(codes, offsets, lens, refs))
+
+
 def test_full_size_properties(engine):
     """BASELINE config 2 shape (10k x 400 aa): size-independent properties + oracle spot checks."""
     codes, offsets, lens = seqio.synth_family(10000, 400, seed=1)
