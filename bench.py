@@ -49,7 +49,7 @@ def workload(n_gpus: int):
     return seqio.synth_family(n, LEN, SEED), n
 
 
-from famsa_b200.sharding import (row_shards, shard_sizes, tri, triangle_allgather_pipelined, assign_allreduce)  # noqa: E402
+from famsa_b200.sharding import (row_shards, shard_sizes, tri, PeerTriangle, assign_allreduce)  # noqa: E402
 
 
 def config_for(n: int, world: int) -> dict:
@@ -57,8 +57,9 @@ def config_for(n: int, world: int) -> dict:
     return {"workload": f"LCS triangle, {n} x {LEN} aa synthetic family (seed {SEED})",
             "n_seqs": n, "len": LEN, "pairs_per_step": tri(n),
             "out": "uint16 packed lower triangle", "l2": "flushed between timed iterations (192 MiB write)",
-            "multi_gpu": ("row shards with equal pairs, each computed in 4 pieces; every finished piece is broadcast (NCCL) into its "
-                          "place of the full packed triangle while the next piece is computed") if world > 1 else "none"}
+            "multi_gpu": ("row shards with equal pairs, each computed in 8 pieces; every finished piece is copied into its place of "
+                          "every peer's full packed triangle (CUDA IPC, copy engines over NVLink) while the next piece is computed; "
+                          "a one-element NCCL all-reduce ends the step") if world > 1 else "none"}
 
 
 class ClockSampler:
@@ -335,14 +336,12 @@ def bench_c3(eng, torch, dist, world, rank, stream, l2_flush):
     codes, offsets, lens = seqio.synth_family(C3_N, LEN, C3_SEED)
     n = len(lens)
     eng.upload(codes, offsets, lens)
-    bounds = row_shards(n, world)
-    full = torch.empty(tri(n), dtype=torch.int16, device="cuda")
-
-    def compute_rows(r0, r1, view):
-        eng.triangle_device(r0, r1, view.data_ptr(), 2, stream)
+    pt = PeerTriangle(eng, n, 2, rank, world, dist)
+    full = pt.tensor(torch)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
 
     def step():
-        triangle_allgather_pipelined(compute_rows, bounds, rank, dist, full, n_sub=8)
+        pt.step(torch, stream, 8, flag)
 
     step()
     dist.barrier(); torch.cuda.synchronize()
@@ -382,9 +381,11 @@ def bench_c3(eng, torch, dist, world, rank, stream, l2_flush):
     out = {"metric": METRIC, "unit": UNIT, "scaling": "strong", "value": tri(n) / (ms / 1e3), "ms_per_step": ms, "steps": steps, "warmup": 1,
            "upgma_tree": upgma,
            "config": {"workload": f"LCS triangle, {n} x {LEN} aa synthetic family (seed {C3_SEED}), rows sharded over {world} GPUs, "
-                                  "exchange overlapped in 8 pieces per rank", "pairs_per_step": tri(n)},
+                                  "every rank's rows computed in 8 pieces, each finished piece copied into every peer's full triangle "
+                                  "(CUDA IPC, copy engines over NVLink) while the next is computed", "pairs_per_step": tri(n)},
            "gathered_triangle_identical_on_all_ranks": bool(lo.item() == hi.item()), "oracle_spot_check": spot}
     del full
+    pt.close(torch)
     torch.cuda.empty_cache()
     return out
 
@@ -655,20 +656,19 @@ def main():
     eng = famsa_b200.Engine(local)
     eng.upload(codes, offsets, lens)                       # resident inputs for the `value` leg
     d_block = torch.empty(max(max_shard, 1), dtype=torch.int16, device="cuda")
-    d_full = torch.empty(total_pairs, dtype=torch.int16, device="cuda") if world > 1 else None   # the gathered packed triangle
+    pt = PeerTriangle(eng, n, 2, rank, world, dist) if world > 1 else None   # every rank's full packed triangle, mapped by its peers
+    d_full = pt.tensor(torch) if pt else None
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
     side = torch.cuda.Stream()                             # non-default stream shared by our kernels and NCCL
     torch.cuda.set_stream(side)
     stream = side.cuda_stream
     l2_flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
-    def compute_rows(r0, r1, view):
-        eng.triangle_device(r0, r1, view.data_ptr(), 2, stream)
-
     def step_device():
         if world == 1:
             eng.triangle_device(rb, re, d_block.data_ptr(), 2, stream)
         else:
-            triangle_allgather_pipelined(compute_rows, bounds, rank, dist, d_full, n_sub=4)
+            pt.step(torch, stream, 8, flag)                # own rows in 8 pieces + peer copies, then a one-element all-reduce
 
     def barrier():
         if world > 1:
@@ -721,8 +721,15 @@ def main():
         chk = d_full.view(torch.int16).to(torch.int64).sum().reshape(1)
         lo, hi = chk.clone(), chk.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        whole = torch.empty(total_pairs, dtype=torch.int16, device="cuda")        # untimed: the whole triangle on this GPU alone
+        eng.triangle_device(0, n, whole.data_ptr(), 2, stream)
+        torch.cuda.synchronize()
+        same = torch.tensor([int(torch.equal(whole, d_full))], dtype=torch.int32, device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        del whole
         exchange = {"compute_only_ms_per_step": comp_ms / args.steps, "all_gather_exposed_ms_per_step": (dev_ms - comp_ms) / args.steps,
-                    "gathered_bytes_per_rank": int(total_pairs * 2), "gathered_triangle_identical_on_all_ranks": bool(lo.item() == hi.item())}
+                    "gathered_bytes_per_rank": int(total_pairs * 2), "gathered_triangle_identical_on_all_ranks": bool(lo.item() == hi.item()),
+                    "gathered_triangle_equals_single_gpu_triangle_on_every_rank": bool(same.item() == 1)}
 
     # dominant kernel, timed live with CUDA events on its launch stream (single launch class at this config)
     kern_ms = []
@@ -808,6 +815,9 @@ def main():
     dp = bench_dp(eng, torch, dist, world, rank, max(2, args.steps // 2), args.warmup, l2_flush, stream,
                   want_cpu=(world == 1 and not args.no_cpu_baseline))
     dp_tree = bench_dp_tree(eng, torch, dist, world, rank, max(3, args.steps), want_cpu=(world == 1 and not args.no_cpu_baseline))
+    if pt:
+        d_full = None
+        pt.close(torch)
     c3 = bench_c3(eng, torch, dist, world, rank, stream, l2_flush) if world > 1 else None
     c5 = bench_c5(eng, torch, dist, world, rank, stream, max(2, args.steps // 2))
     if rank == 0:

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 EXPORTED_SYMBOLS = [
     "famsa_abi_version", "famsa_create", "famsa_destroy", "famsa_last_error", "famsa_kernel_launches",
     "famsa_lcs_upload", "famsa_lcs_n_seqs", "famsa_lcs_triangle", "famsa_lcs_triangle_device",
+    "famsa_device_alloc", "famsa_device_free", "famsa_ipc_export", "famsa_ipc_open", "famsa_ipc_close", "famsa_lcs_triangle_exchange",
     "famsa_lcs_rows", "famsa_lcs_rows_device", "famsa_lcs_assign", "famsa_lcs_assign_shard", "famsa_lcs_upgma", "famsa_lcs_upgma_from_triangle", "famsa_lcs_prim", "famsa_transform_f64", "famsa_transform_f32",
     "famsa_lcs_last_timing", "famsa_dp_align_batch", "famsa_dp_align_batch_device", "famsa_dp_last_timing",
     "famsa_prof_set_scoring", "famsa_prof_put", "famsa_prof_merge_batch", "famsa_prof_get", "famsa_prof_drop",
@@ -78,6 +79,12 @@ def load_library() -> C.CDLL:
     lib.famsa_lcs_n_seqs.restype = u32
     lib.famsa_lcs_triangle.argtypes = [vp, u32, u32, vp, i32]
     lib.famsa_lcs_triangle_device.argtypes = [vp, u32, u32, vp, i32, vp]
+    lib.famsa_device_alloc.argtypes = [vp, u64, C.POINTER(vp)]
+    lib.famsa_device_free.argtypes = [vp, vp]
+    lib.famsa_ipc_export.argtypes = [vp, vp, vp]
+    lib.famsa_ipc_open.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.famsa_ipc_close.argtypes = [vp, vp]
+    lib.famsa_lcs_triangle_exchange.argtypes = [vp, u32, u32, vp, vp, u32, i32, u32, vp]
     lib.famsa_lcs_rows.argtypes = [vp, vp, u32, vp, u32, vp, i32]
     lib.famsa_lcs_rows_device.argtypes = [vp, vp, u32, vp, u32, vp, i32, vp]
     lib.famsa_lcs_prim.argtypes = [vp, i32, vp, vp, vp, vp]
@@ -168,6 +175,35 @@ class Engine:
     def triangle_device(self, row_begin: int, row_end: int, d_out_ptr: int, elem_bytes: int, stream: int = 0):
         self._check(self.lib.famsa_lcs_triangle_device(self.h, row_begin, row_end, C.c_void_p(d_out_ptr),
                                                        elem_bytes, C.c_void_p(stream) if stream else None))
+
+    # multi-GPU exchange over peer memory (famsa_lcs_triangle_exchange)
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.famsa_device_alloc(self.h, nbytes, C.byref(p)))
+        return int(p.value)
+
+    def device_free(self, d_ptr: int):
+        self._check(self.lib.famsa_device_free(self.h, C.c_void_p(d_ptr)))
+
+    def ipc_export(self, d_ptr: int) -> bytes:
+        h = (C.c_uint8 * 64)()
+        self._check(self.lib.famsa_ipc_export(self.h, C.c_void_p(d_ptr), h))
+        return bytes(h)
+
+    def ipc_open(self, handle: bytes) -> int:
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        self._check(self.lib.famsa_ipc_open(self.h, h, C.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, d_ptr: int):
+        self._check(self.lib.famsa_ipc_close(self.h, C.c_void_p(d_ptr)))
+
+    def triangle_exchange(self, row_begin: int, row_end: int, d_full: int, peers, elem_bytes: int, n_pieces: int = 8,
+                          stream: int = 0):
+        arr = (C.c_void_p * max(len(peers), 1))(*[C.c_void_p(p) for p in peers])
+        self._check(self.lib.famsa_lcs_triangle_exchange(self.h, row_begin, row_end, C.c_void_p(d_full), arr, len(peers),
+                                                         elem_bytes, n_pieces, C.c_void_p(stream) if stream else None))
 
     def rows(self, ref_ids, col_ids=None, n_col: int | None = None, dtype=np.uint32) -> np.ndarray:
         ref = np.ascontiguousarray(ref_ids, dtype=np.uint32)

@@ -2,6 +2,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <new>
 
 #include "ctx.h"
@@ -69,6 +70,7 @@ int famsa_create(int device, famsa_ctx** out_ctx)
         for (auto& ev : ctx->ev) FB_CUDA(cudaEventCreate(&ev));
         FB_CUDA(cudaEventCreateWithFlags(&ctx->ev_busy, cudaEventDisableTiming));
         FB_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        FB_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
         for (auto& e : ctx->ev_join) FB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& a : ctx->aux_stream) FB_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
         // per-call scratch and resident profiles are stream-ordered allocations: the pool keeps what it has
@@ -108,6 +110,7 @@ void famsa_destroy(famsa_ctx* ctx)
         if (ev) cudaEventDestroy(ev);
     if (ctx->ev_busy) cudaEventDestroy(ctx->ev_busy);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     for (auto& e : ctx->ev_join)
         if (e) cudaEventDestroy(e);
     for (auto& a : ctx->aux_stream)
@@ -209,6 +212,7 @@ int famsa_lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, voi
     for (int b = 1; b < n_blocks; ++b) {
         const double target = (double)tri(row_begin) + (double)pairs * b / n_blocks;
         uint32_t r = (uint32_t)((1.0 + std::sqrt(1.0 + 8.0 * target)) / 2.0);
+        r = (r + 16) / 32 * 32;                                        // on a mask-group boundary: no group is computed twice
         bounds[b] = std::min(std::max(r, bounds[b - 1]), row_end);
     }
     bounds[n_blocks] = row_end;
@@ -223,7 +227,7 @@ int famsa_lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, voi
     if ((rc = fb::scratch_acquire(ctx, ctx->stream))) return rc;
     FB_CUDA(cudaEventRecord(ctx->ev_host[0], ctx->stream));
     float main_ms = 0.f;
-    rc = fb::lcs_triangle(ctx, row_begin, row_end, d_out, elem_bytes, ctx->stream, bounds, n_blocks, ctx->ev_block);
+    rc = fb::lcs_triangle(ctx, row_begin, row_end, d_out, elem_bytes, ctx->stream, bounds, n_blocks, ctx->ev_block, true, true);
     if (rc) return rc;
     if (!ctx->lcs.identity_perm && n_blocks == 1) FB_CUDA(cudaEventRecord(ctx->ev_block[0], ctx->stream));
     FB_CUDA(cudaEventRecord(ctx->ev_host[1], ctx->stream));
@@ -242,6 +246,116 @@ int famsa_lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, voi
     ctx->lcs.last_main_ms = main_ms;
     ctx->lcs.last_pairs = pairs;
     return FAMSA_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU exchange over peer memory
+
+int famsa_device_alloc(famsa_ctx* ctx, uint64_t bytes, void** d_ptr)
+{
+    FB_CHECK_CTX(ctx);
+    if (!d_ptr) { set_error("d_ptr is NULL"); return FAMSA_E_INVALID; }
+    FB_CUDA(cudaSetDevice(ctx->device));
+    *d_ptr = nullptr;
+    const cudaError_t e = cudaMalloc(d_ptr, std::max<uint64_t>(bytes, 1));   // a whole allocation: exportable as it is
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); set_error("out of device memory (" + std::to_string(bytes) + " bytes)"); return FAMSA_E_NOMEM; }
+    FB_CUDA(e);
+    return FAMSA_OK;
+}
+
+int famsa_device_free(famsa_ctx* ctx, void* d_ptr)
+{
+    FB_CHECK_CTX(ctx);
+    FB_CUDA(cudaSetDevice(ctx->device));
+    FB_CUDA(cudaDeviceSynchronize());
+    FB_CUDA(cudaFree(d_ptr));
+    return FAMSA_OK;
+}
+
+int famsa_ipc_export(famsa_ctx* ctx, void* d_ptr, uint8_t handle[64])
+{
+    FB_CHECK_CTX(ctx);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    if (!d_ptr || !handle) { set_error("NULL argument"); return FAMSA_E_INVALID; }
+    FB_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    FB_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle, &h, 64);
+    return FAMSA_OK;
+}
+
+int famsa_ipc_open(famsa_ctx* ctx, const uint8_t handle[64], void** d_ptr)
+{
+    FB_CHECK_CTX(ctx);
+    if (!d_ptr || !handle) { set_error("NULL argument"); return FAMSA_E_INVALID; }
+    FB_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    FB_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return FAMSA_OK;
+}
+
+int famsa_ipc_close(famsa_ctx* ctx, void* d_ptr)
+{
+    FB_CHECK_CTX(ctx);
+    FB_CUDA(cudaSetDevice(ctx->device));
+    FB_CUDA(cudaDeviceSynchronize());
+    FB_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return FAMSA_OK;
+}
+
+int famsa_lcs_triangle_exchange(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_full, void* const* d_peer_full,
+                                uint32_t n_peers, int elem_bytes, uint32_t n_pieces, void* stream)
+{
+    FB_CHECK_CTX(ctx);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    constexpr uint32_t kPieces = sizeof(ctx->ev_block) / sizeof(ctx->ev_block[0]);
+    if (ctx->lcs.n == 0) { set_error("famsa_lcs_upload has not been called"); return FAMSA_E_STATE; }
+    if (row_begin > row_end || row_end > ctx->lcs.n) { set_error("row range out of bounds"); return FAMSA_E_INVALID; }
+    if (!d_full || (n_peers && !d_peer_full)) { set_error("NULL triangle buffer"); return FAMSA_E_INVALID; }
+    for (uint32_t k = 0; k < n_peers; ++k)
+        if (!d_peer_full[k]) { set_error("NULL peer buffer"); return FAMSA_E_INVALID; }
+    int rc = check_elem(ctx, elem_bytes);
+    if (rc) return rc;
+    FB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : ctx->stream;
+    if (!ctx->copy_stream) {
+        FB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (auto& e : ctx->ev_block) FB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : ctx->ev_host) FB_CUDA(cudaEventCreate(&e));
+    }
+    auto tri = [](uint64_t r) { return r ? r * (r - 1) / 2 : 0; };
+    // pieces with equal numbers of pairs (a non-identity order cannot be cut by rows: one piece)
+    const uint32_t np = ctx->lcs.identity_perm ? std::min(std::max(n_pieces, 1u), kPieces) : 1u;
+    uint32_t bounds[kPieces + 1];
+    bounds[0] = row_begin;
+    const uint64_t pairs = tri(row_end) - tri(row_begin);
+    for (uint32_t b = 1; b < np; ++b) {
+        const double target = (double)tri(row_begin) + (double)pairs * b / np;
+        uint32_t r = (uint32_t)((1.0 + std::sqrt(1.0 + 8.0 * target)) / 2.0);
+        r = (r + 16) / 32 * 32;                                        // on a mask-group boundary: no group is computed twice
+        bounds[b] = std::min(std::max(r, bounds[b - 1]), row_end);
+    }
+    bounds[np] = row_end;
+    if ((rc = fb::scratch_acquire(ctx, st))) return rc;
+    char* own = static_cast<char*>(d_full) + tri(row_begin) * elem_bytes;    // lcs_triangle indexes from its first row
+    rc = fb::lcs_triangle(ctx, row_begin, row_end, own, elem_bytes, st, bounds, (int)np, ctx->ev_block, true, true);
+    if (rc) return rc;
+    // every finished piece goes to the same place of every peer's triangle while the next pieces are being computed: copy
+    // engines over NVLink, no SM and no collective kernel involved
+    if (n_peers) {
+        for (uint32_t b = 0; b < np; ++b) {
+            const uint64_t off = tri(bounds[b]) * elem_bytes, bytes = (tri(bounds[b + 1]) - tri(bounds[b])) * elem_bytes;
+            if (!bytes) continue;
+            FB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_block[b], 0));
+            for (uint32_t k = 0; k < n_peers; ++k)
+                FB_CUDA(cudaMemcpyAsync(static_cast<char*>(d_peer_full[k]) + off, static_cast<char*>(d_full) + off, bytes,
+                                        cudaMemcpyDeviceToDevice, ctx->copy_stream));
+        }
+        FB_CUDA(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));     // the caller's stream continues after the last copy
+        FB_CUDA(cudaStreamWaitEvent(st, ctx->ev_copy, 0));
+    }
+    if (!stream) { FB_CUDA(cudaStreamSynchronize(st)); fb::scratch_release(ctx, st, true); return finish_timing(ctx); }
+    return fb::scratch_release(ctx, st, false);
 }
 
 static int rows_common(famsa_ctx* ctx, const uint32_t* d_ref_ids, const uint32_t* h_ref_ids, uint32_t n_ref,

@@ -184,6 +184,7 @@ struct famsa_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;                 // D2H of finished row blocks (famsa_lcs_triangle)
     cudaEvent_t ev_block[8] = {};
+    cudaEvent_t ev_copy = nullptr;                      // end of the peer copies of famsa_lcs_triangle_exchange
     cudaEvent_t ev_host[2] = {};
     // The context-owned scratch (tile lists, DP scratch, ...) is shared by every call.  A *_device call on a caller
     // stream returns while its kernels are still queued, so it leaves `ev_busy` recorded behind them and the next call
@@ -210,7 +211,7 @@ int lcs_upload(famsa_ctx* ctx, const int8_t* codes, const uint64_t* offsets, con
                uint32_t n);
 int lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_out, int elem_bytes,
                  cudaStream_t stream, const uint32_t* bounds = nullptr, int n_blocks = 1,
-                 cudaEvent_t* block_events = nullptr, bool quirk_fixups = true);
+                 cudaEvent_t* block_events = nullptr, bool quirk_fixups = true, bool piece_streams = false);
 int lcs_rows(famsa_ctx* ctx, const uint32_t* d_ref_ids, const uint32_t* h_ref_ids, uint32_t n_ref,
              const uint32_t* d_col_ids, uint32_t n_col, void* d_out, int elem_bytes,
              cudaStream_t stream, uint32_t g_begin = 0, uint32_t g_end = 0xffffffffu);

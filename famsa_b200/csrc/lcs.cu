@@ -1158,7 +1158,7 @@ static int exact_rows(famsa_ctx* ctx, const std::vector<ExactReq>& reqs, const u
 // range) the work is issued block by block and block_events[b] is recorded after block b, so that a caller can
 // start copying finished blocks while later ones are still being computed; every tile list is uploaded up front.
 int lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_out, int elem_bytes, cudaStream_t st,
-                 const uint32_t* bounds, int n_blocks, cudaEvent_t* block_events, bool quirk_fixups)
+                 const uint32_t* bounds, int n_blocks, cudaEvent_t* block_events, bool quirk_fixups, bool piece_streams)
 {
     LcsState& S = ctx->lcs;
     const uint32_t n = S.n;
@@ -1196,15 +1196,25 @@ int lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_o
     if (quirk_fixups) std::set_union(S.h_quirky.begin(), S.h_quirky.end(), S.h_long.begin(), S.h_long.end(), std::back_inserter(special));
     else special = S.h_long;         // true LCS everywhere: only the rows the tile kernel cannot reach
     FB_CUDA(cudaEventRecord(ctx->ev[1], st));
+    // Blocks in one stream would each end with a partly filled last wave (half a wave of tiles per block boundary: 0.4 ms at
+    // C2).  Issued round-robin on the auxiliary streams instead, the block scheduler fills the tail of block b with the first
+    // tiles of block b+1 and the blocks still finish in order.  (The exact kernels share one scratch: single stream then.)
+    constexpr int kAux = sizeof(ctx->aux_stream) / sizeof(ctx->aux_stream[0]);
+    const bool fan = piece_streams && n_blocks > 1 && special.empty();
+    if (fan) {
+        FB_CUDA(cudaEventRecord(ctx->ev_fork, st));
+        for (int a = 0; a < std::min(kAux, n_blocks); ++a) FB_CUDA(cudaStreamWaitEvent(ctx->aux_stream[a], ctx->ev_fork, 0));
+    }
     size_t at = 0;
     for (int b = 0; b < n_blocks; ++b) {
+        const cudaStream_t bst = fan ? ctx->aux_stream[b % kAux] : st;
         P.row_begin = bounds[b];
         P.row_end = bounds[b + 1];
         for (uint32_t nl = 1; nl <= (uint32_t)kMaxNL; ++nl) {
             auto& v = tiles[b][nl];
             if (v.empty()) continue;
             P.tiles = S.d_tiles.as<uint3>() + at;
-            FB_TRY(launch_tile_nl(ctx, nl, P, (uint32_t)v.size(), st));
+            FB_TRY(launch_tile_nl(ctx, nl, P, (uint32_t)v.size(), bst));
             at += v.size();
         }
         // rows the tile kernel cannot answer for: dropped-carry rows entirely; over-long rows only against over-long columns
@@ -1215,9 +1225,14 @@ int lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_o
             const bool quirky = quirk_fixups && std::binary_search(S.h_quirky.begin(), S.h_quirky.end(), row);
             reqs.push_back(ExactReq{row, row, quirky ? 0 : 1, (size_t)row * (row - 1) / 2 - (size_t)P.tri_base});
         }
-        FB_TRY(exact_rows(ctx, reqs, nullptr, d_out, elem_bytes, st));
-        if (block_events) FB_CUDA(cudaEventRecord(block_events[b], st));
+        FB_TRY(exact_rows(ctx, reqs, nullptr, d_out, elem_bytes, bst));
+        if (block_events) FB_CUDA(cudaEventRecord(block_events[b], bst));
     }
+    if (fan)
+        for (int a = 0; a < std::min(kAux, n_blocks); ++a) {
+            FB_CUDA(cudaEventRecord(ctx->ev_join[a], ctx->aux_stream[a]));
+            FB_CUDA(cudaStreamWaitEvent(st, ctx->ev_join[a], 0));
+        }
     FB_CUDA(cudaEventRecord(ctx->ev[2], st));
     FB_CUDA(cudaEventRecord(ctx->ev[3], st));
     return FAMSA_OK;

@@ -9,14 +9,17 @@ def tri(r: int) -> int:
     return r * (r - 1) // 2 if r else 0
 
 
-def row_shards(n: int, parts: int) -> list[int]:
+def row_shards(n: int, parts: int, align: int = 32) -> list[int]:
     """Row boundaries b[0]=0 <= ... <= b[parts]=n giving every rank (almost) the same number of pairs
-    (row i holds i pairs, so boundaries sit at n*sqrt(r/parts))."""
+    (row i holds i pairs, so boundaries sit at n*sqrt(r/parts)), rounded to the 32-row mask groups of the LCS kernel so
+    that no group's tiles are computed by two ranks."""
     total = tri(n)
     bounds = [0]
     for r in range(1, parts):
         target = total * r / parts
         b = int(round((1 + math.sqrt(1 + 8 * target)) / 2))
+        if align > 1 and n >= 4 * align * parts:
+            b = (b + align // 2) // align * align
         bounds.append(min(max(b, bounds[-1]), n))
     bounds.append(n)
     return bounds
@@ -101,6 +104,52 @@ def triangle_allgather_pipelined(compute_rows, bounds, rank, dist, full, n_sub: 
     if cuda:
         main.wait_stream(_side_stream)
     return full
+
+
+class PeerTriangle:
+    """The N>1 triangle with the exchange folded into the computation (famsa_lcs_triangle_exchange): every rank owns a
+    device buffer for the full packed triangle, exported through CUDA IPC and mapped by every other rank, so a finished
+    piece of a rank's rows is copied straight into every peer's buffer over NVLink by the copy engines while the next
+    piece is computed -- no collective kernel, no staging, no padding.  `dist` only carries the 64-byte handles once and
+    the barrier that ends a step."""
+
+    def __init__(self, eng, n: int, elem_bytes: int, rank: int, world: int, dist):
+        self.eng, self.n, self.elem_bytes, self.rank, self.world, self.dist = eng, n, elem_bytes, rank, world, dist
+        self.nbytes = max(tri(n) * elem_bytes, 1)
+        self.ptr = eng.device_alloc(self.nbytes)
+        handles = [None] * world
+        dist.all_gather_object(handles, eng.ipc_export(self.ptr))
+        self.peers = [eng.ipc_open(handles[r]) for r in range(world) if r != rank]
+        self.bounds = row_shards(n, world)
+
+    def tensor(self, torch):
+        """The local buffer as a torch tensor (zero copy)."""
+        class _Arr:
+            pass
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (max(tri(self.n), 1),), "typestr": "<i2" if self.elem_bytes == 2 else "<i4",
+                                      "data": (self.ptr, False), "version": 2}
+        return torch.as_tensor(a, device="cuda")[:tri(self.n)]
+
+    def step(self, torch, stream: int = 0, n_pieces: int = 8, flag=None):
+        """Queues this rank's rows + their copies on `stream`, then the barrier: with a CUDA `flag` tensor a one-element
+        all-reduce ordered on the current stream (NCCL), else a host barrier after a device synchronise (gloo)."""
+        rb, re = self.bounds[self.rank], self.bounds[self.rank + 1]
+        self.eng.triangle_exchange(rb, re, self.ptr, self.peers, self.elem_bytes, n_pieces, stream)
+        if flag is not None and flag.is_cuda:
+            self.dist.all_reduce(flag)
+        else:
+            torch.cuda.synchronize()
+            self.dist.barrier()
+
+    def close(self, torch):
+        torch.cuda.synchronize()
+        self.dist.barrier()                        # nobody unmaps a buffer a peer may still be writing to
+        for p in self.peers:
+            self.eng.ipc_close(p)
+        self.dist.barrier()
+        self.eng.device_free(self.ptr)
+        self.peers, self.ptr = [], 0
 
 
 def group_slice(n_groups: int, shard: int, n_shards: int) -> tuple[int, int]:

@@ -88,6 +88,23 @@ int famsa_lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, voi
 int famsa_lcs_triangle_device(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_out,
                               int elem_bytes, void* stream);
 
+/* The triangle on several GPUs ("rows are sharded, one all-gather at the end"), with the exchange step
+ * folded into the computation.  One process per GPU; every rank holds a buffer for the FULL packed triangle of all n_seqs
+ * rows (famsa_device_alloc, layout as famsa_lcs_triangle_device writes it for rows 0..n_seqs) and has opened its peers'
+ * buffers (famsa_ipc_export -> hand the 64 bytes to the other processes by any means -> famsa_ipc_open).  This call
+ * computes rows [row_begin, row_end) into their place of d_full in n_pieces pieces (<= 8, equal numbers of pairs) and, as
+ * soon as a piece is finished, copies it into the same place of every d_peer_full[k] over NVLink (copy engines; no SM time,
+ * no collective kernel) while the next pieces are being computed.  Work queued on `stream` after the call runs after the
+ * last copy has landed; once every rank has got there (any barrier, e.g. a one-element NCCL all-reduce on that stream) all
+ * buffers hold the whole triangle.  stream: cudaStream_t or NULL (the context's stream, synchronised). */
+int famsa_device_alloc(famsa_ctx* ctx, uint64_t bytes, void** d_ptr);
+int famsa_device_free(famsa_ctx* ctx, void* d_ptr);
+int famsa_ipc_export(famsa_ctx* ctx, void* d_ptr, uint8_t handle[64]);             /* cudaIpcGetMemHandle */
+int famsa_ipc_open(famsa_ctx* ctx, const uint8_t handle[64], void** d_ptr);        /* another process's buffer, mapped here */
+int famsa_ipc_close(famsa_ctx* ctx, void* d_ptr);
+int famsa_lcs_triangle_exchange(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_full,
+                                void* const* d_peer_full, uint32_t n_peers, int elem_bytes, uint32_t n_pieces, void* stream);
+
 /* n_ref reference rows against a column list: out[r * n_col + k] = LCS length with sequence
  * ref_ids[r] as the row (seq0) and sequence col_ids[k] streamed.  col_ids == NULL means columns
  * 0..n_col-1 (calculateDistanceVector's prefix shape).  This is calculateDistanceRange /

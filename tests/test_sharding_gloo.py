@@ -120,7 +120,9 @@ def test_row_shards_balance():
         sizes = sharding.shard_sizes(b)
         assert sum(sizes) == n * (n - 1) // 2
         if n >= 1000:
-            assert max(sizes) <= 1.01 * (sum(sizes) / parts)
+            # boundaries sit on 32-row mask groups (the kernel's unit of work: a group split between two ranks is computed by both)
+            assert max(sizes) <= 1.02 * (sum(sizes) / parts)
+            assert all(x % 32 == 0 for x in b[1:-1])
 
 
 def test_schedule_levels_and_shards():
