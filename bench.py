@@ -298,12 +298,16 @@ def bench_dp(eng, torch, dist, world, rank, steps, warmup, l2_flush, stream, wan
                "config": {"workload": f"{n} independent profile-profile merges per GPU, {DP_CARD[0]}-{DP_CARD[1]} sequences x "
                                       f"{DP_WIDTH[0]}-{DP_WIDTH[1]} columns each (seed {DP_SEED}), unbanded AlignProfProf + traceback",
                           "cells_per_step_per_gpu": cells, "multi_gpu": "merges sharded across ranks, no collective (replicas per merge)"},
-               "e2e": {"value": cells * world * steps / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": h2d,
-                       "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / steps},
-               "e2e_resident": {"value": cells * world * steps / res_s, "unit": "cells/s", "ms_per_step": 1e3 * res_s / steps,
-                                "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": d2h, "construct_kernel_ms": construct_ms,
-                                "note": "famsa_prof_merge_batch: child profiles resident in HBM (outputs of the previous "
-                                        "level), merged tables built on the device, only results + paths return"},
+               "e2e": {"value": cells * world * steps / res_s, "unit": "cells/s", "ms_per_step": 1e3 * res_s / steps,
+                       "h2d_bytes_per_step": 8 * n, "d2h_bytes_per_step": d2h, "construct_kernel_ms": construct_ms,
+                       "note": "famsa_prof_merge_batch, the path INTEGRATION.md wires into ComputeAlignment: child profiles "
+                               "resident in HBM (outputs of the previous level), merged tables built on the device "
+                               "(ConstructProfile's share, which the CPU baseline also contains), only results + paths return"},
+               "e2e_host_tables": {"value": cells * world * steps / e2e_s, "unit": "cells/s", "h2d_bytes_per_step": h2d,
+                                   "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / steps,
+                                   "note": "compatibility entry famsa_dp_align_batch: both children's tables cross PCIe on "
+                                           "every call (bound by the H2D copy and the host-side packing, does not scale with "
+                                           "ranks sharing one host); kept for callers that hold profiles on the host"},
                "gpu_launches": int(launches),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "traffic": dp_traffic, "peak_source": peak_src, "kernel": "fb::k_dp_prep + k_dp_fill<NW,CL> + k_dp_trace",

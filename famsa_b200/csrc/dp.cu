@@ -75,9 +75,14 @@ struct __align__(16) WarpShared {
     Cell brow[2][kChunk];                   // boundary-row cells of the current / next chunk
     long long col[kColFields][kRing];       // column records
     long long s2[2][kChunk][kS2Stride];     // the column profile's scores of the current / next chunk
-    long long t[kTRing][32];                // T ring: [wavefront step mod 64][lane]; viewed as int[64][32] when T fits 32 bits
     long long park[kChunk][3];              // (D, H, V) of the stripe's last row, one entry per step of the chunk (written by lane 31)
+    long long t[kTRing][32];                // T ring: [wavefront step mod 64][lane]; viewed as int[64][32] when T fits 32 bits.  LAST member:
+                                            // k_dp_fill_compact allocates only the half the 4-byte view needs (kCompactStride)
 };
+// per-warp shared memory of k_dp_fill_compact: everything but the upper half of the T ring (merges whose T needs 8 bytes are left to
+// a k_dp_fill launch that follows): 17.3 KB instead of 25.5 KB, i.e. 12 instead of 8 fill warps per SM
+constexpr size_t kCompactStride = sizeof(WarpShared) - sizeof(long long) * (kTRing / 2) * 32;
+static_assert(offsetof(WarpShared, t) + sizeof(long long) * kTRing * 32 == sizeof(WarpShared) && kCompactStride % 16 == 0, "T ring must end the struct");
 
 // scratch layout of one job (all sections 128-byte aligned); w1, w2 = the layout widths (upper bounds)
 struct Scratch {
@@ -198,6 +203,7 @@ struct DpParams {
     famsa_dp_result* results;
     famsa_dp_result* h_results;   // optional mapped host copies written by the traceback itself (no D2H copy afterwards)
     unsigned char* h_path;
+    uint32_t wide_only;           // k_dp_fill: skip merges whose T fits 32 bits (k_dp_fill_compact has done them)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -786,6 +792,7 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
 // is no barrier anywhere: a warp leaves when its stripes are done, the owner of cell (WR, WC) leaves (D, H, V) in the
 // job's scratch for k_dp_trace.
 // the stripes of merge `jid` that belong to team warp `team_warp` of `TW`
+template <bool ONLY32 = false>
 __device__ __forceinline__ void fill_body(const DpParams& P, uint32_t jid, uint32_t team_warp, uint32_t TW, WarpShared& W)
 {
     const DpJobDev J = P.jobs[jid];
@@ -800,9 +807,9 @@ __device__ __forceinline__ void fill_body(const DpParams& P, uint32_t jid, uint3
     long long* g_last = reinterpret_cast<long long*>(scratch + L.lastv);
     unsigned char* dirs = P.sdirs + J.t_off;
 #define FB_STRIPES(V, T) dp_stripes<V, T>(P, M, col, cstride, browg, dirs, team_warp, TW, g_last, W)
-    if (M.var == 0) { if (M.t32) FB_STRIPES(0, true); else FB_STRIPES(0, false); }
-    else if (M.var == 1) { if (M.t32) FB_STRIPES(1, true); else FB_STRIPES(1, false); }
-    else { if (M.t32) FB_STRIPES(2, true); else FB_STRIPES(2, false); }
+    if (M.var == 0) { if (ONLY32 || M.t32) FB_STRIPES(0, true); else FB_STRIPES(0, false); }
+    else if (M.var == 1) { if (ONLY32 || M.t32) FB_STRIPES(1, true); else FB_STRIPES(1, false); }
+    else { if (ONLY32 || M.t32) FB_STRIPES(2, true); else FB_STRIPES(2, false); }
 #undef FB_STRIPES
 }
 
@@ -821,7 +828,23 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32, 1) k_dp_fill(c
     const uint32_t TW = NW == 1 ? 1 : (uint32_t)NW * CL;
     const uint32_t slot = NW == 1 ? blockIdx.x * kDpWarps + warp : blockIdx.x / CL;
     if (slot >= P.n_jobs) return;                                    // whole warp (NW == 1) / whole team otherwise
+    if (P.wide_only && P.meta[P.order[slot]].t32) return;            // k_dp_fill_compact has done this one
     fill_body(P, P.order[slot], team_warp, TW, W);
+}
+
+// Throughput mode: the same stripes with 12 warps per SM instead of 8.  Two warps per SM sub-partition leave the issue slots
+// half empty (the recurrence is a chain of dependent 64-bit compares and selects: ncu smsp__issue_active 53 %); the third
+// needs the registers capped at 168 (ptxas spills 24 bytes) and the T ring in its 4-byte form.  One merge per block.
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, 384 / (NW * 32)) k_dp_fill_compact(const DpParams P)
+{
+    extern __shared__ __align__(16) unsigned char sm_dyn[];
+    const uint32_t warp = threadIdx.x / 32;
+    WarpShared& W = *reinterpret_cast<WarpShared*>(sm_dyn + warp * kCompactStride);
+    if (blockIdx.x >= P.n_jobs) return;
+    const uint32_t jid = P.order[blockIdx.x];
+    if (!P.meta[jid].t32) return;                                    // left to the k_dp_fill launch that follows
+    fill_body<true>(P, jid, warp, NW, W);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -831,7 +854,16 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32, 1) k_dp_fill(c
 // its rows are kept inside a stripe: the warp copies it with 16-byte loads, lane 0 walks inside it, repeat.
 // ------------------------------------------------------------------------------------------------
 constexpr int kTraceWarps = 4;
-// one warp; tile: 64 x 32 bytes of shared memory; all_dirs: the merge's whole skewed direction matrix already in shared
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned lds_u8(uint32_t a)
+{
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+constexpr int kTraceWin = 96;               // wavefront steps per traceback window (3 KB); two windows per warp
+constexpr int kSpecSlack = 16;              // columns the speculative window has to spare on either side of the diagonal
+// one warp; tile: 2 * kTraceWin x 32 bytes of shared memory; all_dirs: the merge's whole skewed direction matrix already in shared
 // memory (small merges in the fused kernel), or NULL
 __device__ __forceinline__ void trace_body(const DpParams& P, uint32_t jid, unsigned char* tile, const unsigned char* all_dirs = nullptr)
 {
@@ -897,52 +929,86 @@ __device__ __forceinline__ void trace_body(const DpParams& P, uint32_t jid, unsi
         dir = __shfl_sync(0xffffffffu, dir, 0);
         n = __shfl_sync(0xffffffffu, n, 0);
     }
+    // Window = a run of wavefront steps [wsb, wsb + wn) of one stripe in shared memory; cell (l, j) of the stripe (l = row
+    // inside it) sits at ((j + l) - wsb) * 32 + l, so the three moves are constant index steps: D -65, H -32, V -33.  While
+    // lane 0 walks in one window, the loads of the NEXT one are already in flight: a path that keeps to the diagonal leaves
+    // the stripe through its first row at column p = tj - (l_top + 1), so the steps around (stripe - 1, row 31, p) are fetched
+    // into the other buffer with kSpecSlack columns to spare on both sides; a walk that ends elsewhere loads synchronously.
+    unsigned char* const buf[2] = {tile, tile + kTraceWin * 32};
+    int cur = 0;
+    bool spec_ok = false;
+    uint32_t ss = 0, ssb = 0, sn = 0;
     while (ti || tj) {
-        // rows [row_lo, ti] (inside the stripe of ti), columns [j0, tj]
-        const uint32_t stripe = ti ? (ti - 1) >> 5 : 0, l_top = ti ? (ti - 1) & 31 : 0;
-        const uint32_t row_lo = ti ? stripe * 32 + 1 : 0;
-        const uint32_t j0 = tj >= 31 ? tj - 31 : 0;
-        if (ti) {
-            const uint4* src = reinterpret_cast<const uint4*>(dirs + ((size_t)stripe * steps + j0) * 32);
-            const uint32_t n16 = (tj + l_top - j0 + 1) * 2;         // 16-byte units
-            uint4* dst = reinterpret_cast<uint4*>(tile);
-            for (uint32_t q = lane; q < n16; q += 32) dst[q] = __ldcg(src + q);
-        }
-        __syncwarp();
-        if (lane == 0) {
-            if (!ti) {
-                // row 0 (CDPMatrix::set_dir_all: every byte of row 0 is all-H)
+        if (!ti) {
+            // row 0 (CDPMatrix::set_dir_all: every byte of row 0 is all-H)
+            if (lane == 0) {
                 uint32_t jj = tj;
-                while (jj && jj >= j0) {
+                while (jj) {
                     tmp_path[n++] = (unsigned char)dir;
                     if (dir != 1) { jj = 0; break; }                 // cannot happen for a valid matrix
                     dir = (0x15 >> (2 * dir)) & 3;
                     --jj;
                 }
-                tj = jj;
-            } else {
-                // In the skewed tile cell (i, j) sits at idx = (j - j0 + l) * 32 + l, l = (i - 1) & 31, so the three moves are
-                // constant index steps: D -65, H -32, V -33.  The cell visited next depends only on the current state and
-                // the state after that on the current cell's byte, so the next byte is requested before the current one
-                // is decoded.
-                int l = (int)l_top, cj = (int)(tj - j0);
-                int idx = (cj + l) * 32 + l;
-                unsigned b = tile[idx];
-                unsigned char* out = tmp_path + n;
-                for (;;) {
-                    *out++ = (unsigned char)dir;
-                    const int di = dir != 1, dj = dir != 2;
-                    l -= di; cj -= dj; idx -= 32 * dj + 33 * di;
-                    const bool inside = (l | cj) >= 0;
-                    const unsigned nb = inside ? tile[idx] : 0;
-                    dir = (int)((b >> (2 * dir)) & 3);
-                    b = nb;
-                    if (!inside) break;
-                }
-                n = (uint32_t)(out - tmp_path);
-                ti = l < 0 ? row_lo - 1 : row_lo + (uint32_t)l;
-                tj = cj < 0 ? (j0 ? j0 - 1 : 0) : j0 + (uint32_t)cj;
             }
+            dir = __shfl_sync(0xffffffffu, dir, 0);
+            tj = 0;
+            break;
+        }
+        const uint32_t stripe = (ti - 1) >> 5, l_top = (ti - 1) & 31, row_lo = stripe * 32 + 1;
+        const uint32_t st_hi = tj + l_top;
+        uint32_t wsb;
+        if (spec_ok && ss == stripe && st_hi >= ssb && st_hi < ssb + sn) { cur ^= 1; wsb = ssb; }
+        else {
+            wsb = st_hi >= 63 ? st_hi - 63 : 0;
+            const uint4* src = reinterpret_cast<const uint4*>(dirs + ((size_t)stripe * steps + wsb) * 32);
+            const uint32_t n16 = (st_hi - wsb + 1) * 2;              // 16-byte units
+            uint4* dst = reinterpret_cast<uint4*>(buf[cur]);
+            for (uint32_t q = lane; q < n16; q += 32) dst[q] = __ldcg(src + q);
+            __syncwarp();
+        }
+        // the speculative window of the stripe above: requested now, stored after the walk
+        spec_ok = false;
+        uint4 r[kTraceWin * 2 / 32];
+        uint32_t s16 = 0;
+        if (stripe > 0 && tj >= l_top + 1) {
+            const uint32_t p = tj - (l_top + 1);
+            uint32_t hi = p + 31 + kSpecSlack;
+            if (hi > (uint32_t)steps - 1) hi = (uint32_t)steps - 1;
+            const uint32_t lo = hi >= (uint32_t)kTraceWin - 1 ? hi - (kTraceWin - 1) : 0;
+            ss = stripe - 1; ssb = lo; sn = hi - lo + 1; s16 = sn * 2; spec_ok = true;
+            const uint4* src = reinterpret_cast<const uint4*>(dirs + ((size_t)ss * steps + ssb) * 32);
+#pragma unroll
+            for (uint32_t q = 0; q < kTraceWin * 2 / 32; ++q)
+                if (lane + 32 * q < s16) r[q] = __ldcg(src + lane + 32 * q);
+        }
+        if (lane == 0) {
+            // one move = one shared-memory byte load in the dependent chain: the index of the next cell depends only on the
+            // current state, the state after that on the current cell's byte.  Per state: index step (D 65, H 32, V 33) and the
+            // packed (row, column) decrement, both looked up by shifting constants.
+            const uint32_t wbase = smem_addr(tile) + (uint32_t)cur * (kTraceWin * 32);
+            int l = (int)l_top, j = (int)tj;
+            int idx = (int)(st_hi - wsb) * 32 + l;
+            unsigned b = lds_u8(wbase + (uint32_t)idx);
+            uint32_t k = n;
+            for (;;) {
+                tmp_path[k++] = (unsigned char)dir;
+                idx -= (int)((0x212041u >> ((unsigned)dir * 8)) & 0xffu);   // index step per state: 0x41 = 65, 0x20 = 32, 0x21 = 33
+                l -= dir != 1; j -= dir != 2;
+                const bool inside = (l | j | idx) >= 0;              // still in the stripe, in the matrix and in the window
+                const unsigned nb = inside ? lds_u8(wbase + (uint32_t)idx) : 0;
+                dir = (int)((b >> (2 * dir)) & 3);
+                b = nb;
+                if (!inside) break;
+            }
+            n = k;
+            ti = l < 0 ? row_lo - 1 : row_lo + (uint32_t)l;
+            tj = j < 0 ? 0 : (uint32_t)j;
+        }
+        if (spec_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(buf[cur ^ 1]);
+#pragma unroll
+            for (uint32_t q = 0; q < kTraceWin * 2 / 32; ++q)
+                if (lane + 32 * q < s16) dst[lane + 32 * q] = r[q];
         }
         ti = __shfl_sync(0xffffffffu, ti, 0);
         tj = __shfl_sync(0xffffffffu, tj, 0);
@@ -983,7 +1049,7 @@ __device__ __forceinline__ void trace_body(const DpParams& P, uint32_t jid, unsi
 
 __global__ void __launch_bounds__(kTraceWarps * 32) k_dp_trace(const DpParams P)
 {
-    __shared__ __align__(16) unsigned char sm_tile[kTraceWarps][64 * 32];
+    __shared__ __align__(16) unsigned char sm_tile[kTraceWarps][2 * kTraceWin * 32];
     const uint32_t warp = threadIdx.x / 32;
     const uint32_t slot = blockIdx.x * kTraceWarps + warp;
     if (slot >= P.n_jobs) return;
@@ -1024,7 +1090,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_merge_fused(const DpPar
         g_fused_phase_max[q][7] = 0;
     }
     extern __shared__ __align__(16) unsigned char sm_dyn[];
-    __shared__ __align__(16) unsigned char sm_tile[64 * 32];
+    __shared__ __align__(16) unsigned char sm_tile[2 * kTraceWin * 32];
     __shared__ ConShared sm_con;
     const uint32_t warp = threadIdx.x / 32;
     for (uint32_t lv = 0; lv < F.n_levels; ++lv) {
@@ -1284,6 +1350,15 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext,
     FB_TRY((configure_fill<4, true>(ctx)));
     FB_TRY((configure_fill<kDpTeamWarps, true>(ctx)));
     {
+        static std::atomic<bool> compact_configured[64];
+        if (!compact_configured[ctx->device & 63].load(std::memory_order_acquire)) {
+            FB_CUDA(cudaFuncSetAttribute(k_dp_fill_compact<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kCompactStride)));
+            FB_CUDA(cudaFuncSetAttribute(k_dp_fill_compact<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * kCompactStride)));
+            FB_CUDA(cudaFuncSetAttribute(k_dp_fill_compact<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(6 * kCompactStride)));
+            compact_configured[ctx->device & 63].store(true, std::memory_order_release);
+        }
+    }
+    {
         static std::atomic<bool> configured[64];
         if (!configured[ctx->device & 63].load(std::memory_order_acquire)) {
             FB_CUDA(cudaFuncSetAttribute(k_merge_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kFusedWarps * sizeof(WarpShared))));
@@ -1408,6 +1483,21 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext,
             return (unsigned long long)dev[a].w1 * dev[a].w2 > (unsigned long long)dev[b].w1 * dev[b].w2;
         });
 
+        // Throughput mode: the first wave of blocks lands on the SMs in launch order, so deal the merges (sorted by size) in
+        // snake rows of one block per SM -- the SM that got the largest merge of a row gets the smallest of the next one.
+        if (!small_batch) {
+            const uint32_t sms = (uint32_t)ctx->sm_count;
+            for (uint32_t q0 = 0; q0 < m;) {
+                const int c = cls(order[q0]);
+                uint32_t q1 = q0;
+                while (q1 < m && cls(order[q1]) == c) ++q1;
+                if (c == 1)
+                    for (uint32_t r = q0 + sms, row = 1; r < q1; r += sms, ++row)
+                        if (row & 1) std::reverse(order.begin() + r, order.begin() + std::min(q1, r + sms));
+                q0 = q1;
+            }
+        }
+
         // one packed upload: order + tblock
         std::vector<unsigned char> pack(o_scratch - o_order);
         memcpy(pack.data(), order.data(), sizeof(uint32_t) * m);
@@ -1471,10 +1561,25 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext,
                 // Team size by how many merges there are: every SM holds 8 fill warps (shared memory), so a level with many
                 // block-class merges runs them with smaller teams -- 4 warps from 2 merges per SM on, 2 from 4 -- which lose
                 // less to the ramp-up / ramp-down of the stripe pipeline.
+                // From two merges per SM on, the compact kernel (12 warps per SM): 6, 4 or 2 warps per merge.
                 int nw = kDpTeamWarps;
-                if (Q.n_jobs >= 4u * (uint32_t)ctx->sm_count) nw = 2;
-                else if (Q.n_jobs >= 2u * (uint32_t)ctx->sm_count) nw = 4;
-                if (nw_forced) nw = nw_forced;
+                const uint32_t sms = (uint32_t)ctx->sm_count;
+                static const bool compact_ok = !getenv("FAMSA_DP_COMPACT") || atoi(getenv("FAMSA_DP_COMPACT")) != 0;   // development knob
+                bool compact = compact_ok && Q.n_jobs >= 2u * sms;
+                if (compact) nw = Q.n_jobs >= 6u * sms ? 2 : (Q.n_jobs >= 3u * sms ? 4 : 6);
+                else if (Q.n_jobs >= 4u * sms) nw = 2;
+                else if (Q.n_jobs >= 2u * sms) nw = 4;
+                if (nw_forced) { nw = nw_forced; compact = compact && (nw == 2 || nw == 4 || nw == 6); }
+                if (compact) {
+                    switch (nw) {
+                    case 2: k_dp_fill_compact<2><<<Q.n_jobs, 2 * 32, 2 * kCompactStride, st>>>(Q); break;
+                    case 4: k_dp_fill_compact<4><<<Q.n_jobs, 4 * 32, 4 * kCompactStride, st>>>(Q); break;
+                    default: k_dp_fill_compact<6><<<Q.n_jobs, 6 * 32, 6 * kCompactStride, st>>>(Q); nw = 4; break;
+                    }
+                    FB_CUDA(cudaGetLastError());
+                    ctx->launches++;
+                    Q.wide_only = 1;                                 // merges whose T needs 8 bytes: the launch below
+                }
                 switch (nw) {
                 case 2: k_dp_fill<2, false><<<Q.n_jobs, 2 * 32, 2 * sizeof(WarpShared), st>>>(Q); break;
                 case 4: k_dp_fill<4, false><<<Q.n_jobs, 4 * 32, 4 * sizeof(WarpShared), st>>>(Q); break;
