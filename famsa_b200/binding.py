@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 EXPORTED_SYMBOLS = [
     "famsa_abi_version", "famsa_create", "famsa_destroy", "famsa_last_error", "famsa_kernel_launches",
-    "famsa_lcs_upload", "famsa_lcs_n_seqs", "famsa_lcs_triangle", "famsa_lcs_triangle_device",
+    "famsa_lcs_upload", "famsa_lcs_upload_sorted", "famsa_lcs_sorted_order", "famsa_lcs_last_tiles", "famsa_lcs_n_seqs", "famsa_lcs_triangle", "famsa_lcs_triangle_device",
     "famsa_device_alloc", "famsa_device_free", "famsa_ipc_export", "famsa_ipc_open", "famsa_ipc_close", "famsa_lcs_triangle_exchange",
     "famsa_lcs_rows", "famsa_lcs_rows_device", "famsa_lcs_assign", "famsa_lcs_assign_shard", "famsa_lcs_upgma", "famsa_lcs_upgma_from_triangle", "famsa_lcs_prim", "famsa_transform_f64", "famsa_transform_f32",
     "famsa_lcs_last_timing", "famsa_dp_align_batch", "famsa_dp_align_batch_device", "famsa_dp_last_timing",
@@ -76,6 +76,10 @@ def load_library() -> C.CDLL:
     lib.famsa_kernel_launches.restype = u64
     lib.famsa_lcs_upload.argtypes = [vp, vp, vp, vp, u32]
     lib.famsa_lcs_n_seqs.argtypes = [vp]
+    lib.famsa_lcs_upload_sorted.argtypes = [vp, vp, vp, vp, u32]
+    lib.famsa_lcs_sorted_order.argtypes = [vp, vp]
+    lib.famsa_lcs_last_tiles.argtypes = [vp]
+    lib.famsa_lcs_last_tiles.restype = u64
     lib.famsa_lcs_n_seqs.restype = u32
     lib.famsa_lcs_triangle.argtypes = [vp, u32, u32, vp, i32]
     lib.famsa_lcs_triangle_device.argtypes = [vp, u32, u32, vp, i32, vp]
@@ -162,6 +166,21 @@ class Engine:
         lens = np.ascontiguousarray(lens, dtype=np.uint32)
         self._check(self.lib.famsa_lcs_upload(self.h, _ptr(codes), _ptr(offsets), _ptr(lens), len(lens)))
         self.n = len(lens)
+
+    def upload_sorted(self, codes: np.ndarray, offsets: np.ndarray, lens: np.ndarray) -> np.ndarray:
+        """famsa_lcs_upload_sorted: indices of later calls are positions in the length-descending order; returns
+        sorted_to_caller (position -> caller index)."""
+        codes = np.ascontiguousarray(codes, dtype=np.int8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        self._check(self.lib.famsa_lcs_upload_sorted(self.h, _ptr(codes), _ptr(offsets), _ptr(lens), len(lens)))
+        self.n = len(lens)
+        order = np.zeros(max(self.n, 1), dtype=np.uint32)
+        self._check(self.lib.famsa_lcs_sorted_order(self.h, _ptr(order)))
+        return order[:self.n]
+
+    def last_tiles(self) -> int:
+        return int(self.lib.famsa_lcs_last_tiles(self.h))
 
     def triangle(self, row_begin: int = 0, row_end: int | None = None, dtype=np.uint16,
                  out: np.ndarray | None = None) -> np.ndarray:

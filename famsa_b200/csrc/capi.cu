@@ -4,6 +4,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <numeric>
+#include <algorithm>
+#include <vector>
 
 #include "ctx.h"
 
@@ -135,8 +138,43 @@ int famsa_lcs_upload(famsa_ctx* ctx, const int8_t* codes, const uint64_t* offset
     if (rc) return rc;
     FB_CUDA(cudaStreamSynchronize(ctx->stream));
     fb::scratch_release(ctx, ctx->stream, true);
+    ctx->lcs.h_order.clear();
     return fb::lcs_upload(ctx, codes, offsets, lens, n_seqs);
 }
+
+int famsa_lcs_upload_sorted(famsa_ctx* ctx, const int8_t* codes, const uint64_t* offsets, const uint32_t* lens, uint32_t n_seqs)
+{
+    FB_CHECK_CTX(ctx);
+    if (n_seqs && (!codes || !offsets || !lens)) { set_error("NULL sequence arrays"); return FAMSA_E_INVALID; }
+    // the permutation the library would apply internally (length descending, ties in caller order), applied up front: every
+    // index of the calls that follow is then a position in that order
+    std::vector<uint32_t> order(n_seqs);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return lens[x] > lens[y]; });
+    std::vector<uint64_t> off(n_seqs);
+    std::vector<uint32_t> len(n_seqs);
+    uint64_t total = 0;
+    for (uint32_t p = 0; p < n_seqs; ++p) { off[p] = total; len[p] = lens[order[p]]; total += len[p]; }
+    std::vector<int8_t> packed(std::max<uint64_t>(total, 1));
+    for (uint32_t p = 0; p < n_seqs; ++p) memcpy(packed.data() + off[p], codes + offsets[order[p]], len[p]);
+    const int rc = famsa_lcs_upload(ctx, packed.data(), off.data(), len.data(), n_seqs);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->lcs.h_order = std::move(order);
+    return FAMSA_OK;
+}
+
+int famsa_lcs_sorted_order(famsa_ctx* ctx, uint32_t* sorted_to_caller)
+{
+    FB_CHECK_CTX(ctx);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!sorted_to_caller && ctx->lcs.n) { set_error("sorted_to_caller is NULL"); return FAMSA_E_INVALID; }
+    if (ctx->lcs.h_order.size() == ctx->lcs.n) std::copy(ctx->lcs.h_order.begin(), ctx->lcs.h_order.end(), sorted_to_caller);
+    else std::iota(sorted_to_caller, sorted_to_caller + ctx->lcs.n, 0u);          // plain famsa_lcs_upload: indices are the caller's
+    return FAMSA_OK;
+}
+
+uint64_t famsa_lcs_last_tiles(const famsa_ctx* ctx) { return ctx ? ctx->lcs.last_tiles : 0; }
 
 uint32_t famsa_lcs_n_seqs(const famsa_ctx* ctx) { return ctx ? ctx->lcs.n : 0; }
 

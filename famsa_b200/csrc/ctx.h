@@ -61,6 +61,8 @@ struct LcsState {
     // last-call timing
     float last_total_ms = 0.f, last_main_ms = 0.f;
     uint64_t last_pairs = 0;
+    uint64_t last_tiles = 0;                 // tiles launched by the most recent triangle call
+    std::vector<uint32_t> h_order;           // famsa_lcs_upload_sorted: position in the library's order -> caller index
 };
 
 struct DpState {

@@ -1181,6 +1181,7 @@ int lcs_triangle(famsa_ctx* ctx, uint32_t row_begin, uint32_t row_end, void* d_o
                 ++total;
             }
         }
+    S.last_tiles = total;
     std::vector<uint3> flat;
     flat.reserve(total);
     for (auto& blk : tiles)

@@ -75,6 +75,19 @@ uint64_t famsa_kernel_launches(const famsa_ctx* ctx);
 int famsa_lcs_upload(famsa_ctx* ctx, const int8_t* codes, const uint64_t* offsets,
                      const uint32_t* lens, uint32_t n_seqs);
 
+/* The same, for a set that is NOT in the order the reference works on (length descending, src/msa.cpp:245-256 -- e.g.
+ * -dist_export in input order, DistanceCalculator.cpp:42) and is to be sharded across GPUs: the library applies that order
+ * up front (stable: ties keep the caller's order) and every index of the calls that follow -- rows, columns, ids, the layout
+ * of the triangle -- is a POSITION IN THAT ORDER.  Row shards are then contiguous runs of the kernel's 32-sequence mask
+ * groups and a rank launches only its own tiles (with famsa_lcs_upload on unsorted input a row range cannot select tiles
+ * and every rank computes all of them).  famsa_lcs_sorted_order returns sorted_to_caller[position] = caller index
+ * (the identity after a plain famsa_lcs_upload); element (i, j) of the caller's order is element (pos[i], pos[j]).  Only
+ * the row/column roles of the dropped-carry corner (lcsbp_classic.h:55-56) follow positions instead of caller indices. */
+int famsa_lcs_upload_sorted(famsa_ctx* ctx, const int8_t* codes, const uint64_t* offsets, const uint32_t* lens, uint32_t n_seqs);
+int famsa_lcs_sorted_order(famsa_ctx* ctx, uint32_t* sorted_to_caller);
+/* tiles (32 mask sequences x 64 streamed sequences) launched by the most recent triangle call: the unit of LCS work */
+uint64_t famsa_lcs_last_tiles(const famsa_ctx* ctx);
+
 uint32_t famsa_lcs_n_seqs(const famsa_ctx* ctx);
 
 /* Lower triangle, rows [row_begin, row_end): for each row i and each j < i the LCS length with

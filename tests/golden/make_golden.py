@@ -201,19 +201,6 @@ def make_hemopexin_dups():
     print("hemopexin_dups.npz:", len(recs), "merges,", len(set(lseqs)), "distinct sequences of", len(lseqs))
 
 
-if __name__ == "__main__":
-    if len(sys.argv) > 1:
-        sys.path.insert(0, os.path.join(HERE, ".."))
-        globals()[sys.argv[1]]()
-        sys.exit(0)
-    main()
-    make_dp()
-    make_hemopexin()
-    make_hemopexin_sl()
-    make_hemopexin_dups()
-    make_sl_tree()
-
-
 def make_sl_tree():
     """adeno_sl_tree.npz -- the reference's DEFAULT guide tree golden, test/adeno_fiber/sl.dnd.
     Holds the set in FAMSA's own order (length-descending, msa.cpp:245-256), the MST edges in Prim order and the
@@ -254,3 +241,93 @@ def make_sl_tree():
     np.savez_compressed(os.path.join(HERE, "adeno_sl_tree.npz"), names=np.array(names), seqs=np.array(letters),
                         edge_from=ef, edge_to=et, edge_dist=ed, prim_order=po, tree=tree)
     print("adeno_sl_tree.npz:", n, "sequences, clades equal to sl.dnd")
+
+
+def clade_signatures(n_leaves, merges, leaf_hash):
+    """Order-free description of a binary tree on named leaves: the multiset of (size, sum of leaf hashes mod 2^64) over
+    its internal nodes -- what a set-of-clades comparison checks, in O(n) memory for 10^5 leaves."""
+    size = np.ones(n_leaves + len(merges), dtype=np.int64)
+    hsum = np.zeros(n_leaves + len(merges), dtype=np.uint64)
+    hsum[:n_leaves] = leaf_hash
+    for k, (a, b) in enumerate(merges):
+        size[n_leaves + k] = size[a] + size[b]
+        hsum[n_leaves + k] = hsum[a] + hsum[b]           # wraps mod 2^64
+    sig = np.stack([size[n_leaves:].astype(np.uint64), hsum[n_leaves:]], axis=1)
+    return sig[np.lexsort((sig[:, 1], sig[:, 0]))]
+
+
+def newick_merges_iterative(text):
+    """parse_newick without recursion (single-linkage trees of 10^5 leaves are 10^4 levels deep)."""
+    text = text.strip().rstrip(";")
+    leaves, merges, stack = [], [], []
+    pos, n = 0, len(text)
+    while pos < n:
+        c = text[pos]
+        if c == "(":
+            stack.append([]); pos += 1
+        elif c == ",":
+            pos += 1
+        elif c == ")":
+            kids = stack.pop()
+            pos += 1
+            while pos < n and text[pos] not in ",()":
+                pos += 1
+            cur = kids[0]
+            for k in kids[1:]:
+                merges.append((cur, k)); cur = ("i", len(merges) - 1)
+            if stack:
+                stack[-1].append(cur)
+        else:
+            start = pos
+            while text[pos] not in ",():":
+                pos += 1
+            name = text[start:pos]
+            while pos < n and text[pos] not in ",()":
+                pos += 1
+            leaves.append(name)
+            stack[-1].append(("l", len(leaves) - 1))
+    nl = len(leaves)
+    ident = lambda t: t[1] if t[0] == "l" else nl + t[1]
+    return leaves, [(ident(a), ident(b)) for a, b in merges]
+
+
+def make_lrr_sl():
+    """lrr_sl.npz -- the reference's large default-guide-tree golden, test/LRR/sl.dnd (124 140 leucine-rich-repeat
+    sequences, self-hosted.yml "LRR sl tree").  The fixture holds the set in FAMSA's order and the CRC32 of the
+    tree_structure the reference's own MSTPrim run (oracle/_ref) builds on it; generation asserts that the clades of that
+    tree are exactly those of sl.dnd.  The GPU test feeds famsa_lcs_prim's edges to the reference's mst_to_dendogram and
+    must arrive at the same tree.  Needs oracle/_ref; takes a few minutes of CPU."""
+    import zlib
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from oracle import pyoracle
+    T = os.path.join(REF, "LRR")
+    ids, seqs = seqio.read_fasta(os.path.join(T, "LRR"))
+    code_list = [seqio.encode(s) for s in seqs]
+    order = sorted(range(len(seqs)), key=lambda i: (-len(code_list[i]), code_list[i].tobytes()))
+    names = [ids[i] for i in order]
+    letters = [seqio.decode(code_list[i]) for i in order]
+    n = len(letters)
+    tree = pyoracle.RefSeqSet(letters).mst_prim_tree(16)
+    rng = np.random.default_rng(12345)
+    h = {nm: rng.integers(0, 2 ** 63, dtype=np.uint64) for nm in names}
+    mine = clade_signatures(n, [tuple(int(x) for x in r) for r in tree[n:]], np.array([h[nm] for nm in names], dtype=np.uint64))
+    gl, gm = newick_merges_iterative(open(os.path.join(T, "sl.dnd")).read())
+    gold = clade_signatures(len(gl), gm, np.array([h[nm] for nm in gl], dtype=np.uint64))
+    assert len(gl) == n and np.array_equal(mine, gold), "tree differs from the golden LRR/sl.dnd"
+    crc = zlib.crc32(np.ascontiguousarray(tree[n:], dtype=np.int32).tobytes())
+    np.savez_compressed(os.path.join(HERE, "lrr_sl.npz"), seqs=np.frombuffer("\n".join(letters).encode(), dtype=np.uint8),
+                        tree_crc=np.array([crc], dtype=np.uint64), n=np.array([n]))
+    print("lrr_sl.npz:", n, "sequences, clades equal to LRR/sl.dnd, tree crc", crc)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        sys.path.insert(0, os.path.join(HERE, ".."))
+        globals()[sys.argv[1]]()
+        sys.exit(0)
+    main()
+    make_dp()
+    make_hemopexin()
+    make_hemopexin_sl()
+    make_hemopexin_dups()
+    make_sl_tree()

@@ -10,7 +10,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, n, length, n_pieces, sort_desc, out_dir):
+def _worker(rank, world, port, n, length, n_pieces, sort_desc, out_dir, sorted_space=False):
     import torch
     import torch.distributed as dist
     from famsa_b200 import seqio, sharding
@@ -22,7 +22,9 @@ def _worker(rank, world, port, n, length, n_pieces, sort_desc, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     eng = Engine(dev)
     codes, offsets, lens = seqio.synth_family(n, length, seed=9, sort_desc=sort_desc)
-    eng.upload(codes, offsets, lens)
+    order = eng.upload_sorted(codes, offsets, lens) if sorted_space else None
+    if not sorted_space:
+        eng.upload(codes, offsets, lens)
     pt = sharding.PeerTriangle(eng, n, 2, rank, world, dist)
     full = pt.tensor(torch)
     ok = True
@@ -30,9 +32,20 @@ def _worker(rank, world, port, n, length, n_pieces, sort_desc, out_dir):
         full.fill_(-1)
         torch.cuda.synchronize(); dist.barrier()
         pt.step(torch, 0, n_pieces)
+        tiles = eng.last_tiles()
         got = full.cpu().numpy().astype(np.uint16)
         want = eng.triangle(0, n, dtype=np.uint16)
         ok = ok and bool(np.array_equal(got, want))
+        if sorted_space:
+            # a rank launches only its share of the tiles (+ at most the mask groups its boundaries cut) ...
+            ok = ok and tiles <= eng.last_tiles() / world * 1.05 + 4 * (n // 64 + 1)
+            # ... and element (i, j) of the caller's order is element (pos[i], pos[j]) of the gathered triangle
+            ref = Engine(dev); ref.upload(codes, offsets, lens)
+            caller = ref.triangle(0, n, dtype=np.uint16); ref.close()
+            pos = np.empty(n, dtype=np.int64); pos[order] = np.arange(n)
+            i, j = np.tril_indices(n, -1)
+            a, b = np.maximum(pos[i], pos[j]), np.minimum(pos[i], pos[j])
+            ok = ok and bool(np.array_equal(caller[i * (i - 1) // 2 + j], got[a * (a - 1) // 2 + b]))
     pt.close(torch)
     eng.close()
     open(os.path.join(out_dir, f"rank{rank}.txt"), "w").write("ok" if ok else "bad")
@@ -45,5 +58,16 @@ def test_triangle_exchange_over_ipc(tmp_path, world, n, length, n_pieces, sort_d
     import torch.multiprocessing as mp
     port = 29800 + world * 11 + (os.getpid() % 60)
     mp.spawn(_worker, args=(world, port, n, length, n_pieces, sort_desc, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f"rank{r}.txt").read() == "ok"
+
+
+def test_triangle_exchange_unsorted_input_sorted_space(tmp_path):
+    """famsa_lcs_upload_sorted: an unsorted set sharded in the library's own order -- every rank launches 1/N of the tiles
+    (checked through famsa_lcs_last_tiles) and the gathered triangle, read through the returned permutation, is the
+    caller-order triangle."""
+    import torch.multiprocessing as mp
+    world, port = 2, 29900 + (os.getpid() % 60)
+    mp.spawn(_worker, args=(world, port, 900, 110, 4, False, str(tmp_path), True), nprocs=world, join=True)
     for r in range(world):
         assert open(tmp_path / f"rank{r}.txt").read() == "ok"

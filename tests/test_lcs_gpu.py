@@ -1,11 +1,13 @@
 """GPU parity tests for HP-1 (all go through the C ABI).  Bit-exact: LCS lengths are integers."""
 import os
+import zlib
 
 import numpy as np
 import pytest
 
 from conftest import GOLDEN, QUIRK_LCS, QUIRK_SEQS, random_set
 from famsa_b200 import seqio
+from famsa_b200.binding import Engine
 from oracle import pyoracle
 
 pytestmark = pytest.mark.gpu
@@ -454,3 +456,27 @@ def test_gpu_prim_golden_sl_tree(engine, monkeypatch, sequential):
     ef, et, ed, order = engine.prim(0)
     assert np.array_equal(ef, z["edge_from"]) and np.array_equal(et, z["edge_to"])
     assert np.array_equal(ed, z["edge_dist"]) and np.array_equal(order, z["prim_order"])
+
+
+@pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref not built")
+def test_gpu_prim_lrr_golden_tree():
+    """The reference's large default-guide-tree golden, test/LRR/sl.dnd (124 140 sequences; fixture lrr_sl.npz: the set in
+    FAMSA's order and the CRC of the reference's MSTPrim tree, whose clades were checked against sl.dnd at generation).
+    famsa_lcs_prim keeps the 7.7 G-pair triangle in HBM (15 GB as u16 + 62 GB of float64 distances for the Boruvka
+    rounds); its edges, through the reference's own mst_to_dendogram, must give that tree."""
+    path = os.path.join(GOLDEN, "lrr_sl.npz")
+    if not os.path.exists(path):
+        pytest.skip("lrr_sl.npz not generated")
+    z = np.load(path)
+    seqs = bytes(z["seqs"]).decode().split("\n")
+    n = int(z["n"][0])
+    assert len(seqs) == n
+    codes, offsets, lens = seqio.pack([seqio.encode(s) for s in seqs])
+    eng = Engine()                                       # own context: tens of GB of scratch go away with it
+    try:
+        eng.upload(codes, offsets, lens)
+        ef, et, ed, order = eng.prim(0)
+    finally:
+        eng.close()
+    tree = pyoracle.mst_to_dendogram(ef, et, ed, order)
+    assert zlib.crc32(np.ascontiguousarray(tree[n:], dtype=np.int32).tobytes()) == int(z["tree_crc"][0])
