@@ -569,6 +569,72 @@ __device__ __forceinline__ void dp_step(WarpShared& W, const RowConst& R, const 
     if (lane == 31) { W.park[u][0] = out.D; W.park[u][1] = out.H; W.park[u][2] = out.V; }
 }
 
+// ---- producer / consumer split of a ProfProf stripe (k_dp_fill_duo) ---------------------------------------------
+// A warp that runs a stripe alone on its SM sub-partition issues an instruction every 2.2 cycles: the step is one long
+// schedule of dependent 64-bit operations.  Roughly two thirds of its instructions do not depend on the DP state at all:
+// staging, the tensor-core T tile, and per cell seven int64 terms that combine the column record with the row's counts
+// (profile_par.cpp:679-886).  A PRODUCER warp on the same sub-partition computes those into a shared-memory ring, one
+// chunk (8 steps x 7 terms x 32 lanes) at a time; the CONSUMER warp is left with the compare / select chain, the
+// shuffles and the boundary row.  Two mbarriers per buffer (full / empty), two buffers.
+constexpr int kTermFields = 7;
+struct __align__(16) DuoTerms { long long v[2][kChunk][kTermFields][32]; };
+struct __align__(16) DuoShared { WarpShared w; DuoTerms t; };
+
+__device__ __forceinline__ uint32_t smem_addr32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_addr32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity)
+{
+    const uint32_t a = smem_addr32(b);
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+}
+
+// the consumer's step: dp_step<2, ...> with the state-independent terms read from the ring
+template <bool GUARD>
+__device__ __forceinline__ void dp_step_duo(WarpShared& W, const RowConst& R, const long long* __restrict__ tv, const Cell* chunk, uint32_t u,
+                                            uint32_t s, uint32_t lane, uint32_t WC, Cell& cur, Cell& up, unsigned char* __restrict__ dk,
+                                            long long* last_out)
+{
+    const int j = (int)s - (int)lane;
+    const long long a1 = tv[0], a2 = tv[32], a3 = tv[64], gcH = tv[96], contH = tv[128], gcV = tv[160], contV = tv[192];
+    Cell U;
+    U.D = shfl_up_ll(cur.D); U.H = shfl_up_ll(cur.H); U.V = shfl_up_ll(cur.V);
+    if (lane == 0) { const Cell B = chunk[u]; U.D = B.D; U.H = B.H; U.V = B.V; }
+    const Cell Pd = up;
+    up = U;
+    const Cell L = cur;
+    const bool three = GUARD ? (R.row_gt1 && j > 1) : R.row_gt1;
+    Cell out;
+    out.pad = 0;
+    int db = pick3(Pd.D + a1, Pd.H + a2, Pd.V + a3, 0, 1, 2, out.D);
+    long long tD = L.D + gcH;
+    const long long tH = L.H + contH;
+    db |= pick3(tD, three ? L.V + gcH : kNever, tH, 0, 2 << 2, 1 << 2, out.H);
+    tD = U.D + gcV;
+    const long long tV = U.V + contV;
+    db |= pick3(tD, three ? U.H + gcV : kNever, tV, 0, 1 << 4, 2 << 4, out.V);
+    if (GUARD) {
+        const bool commit = j >= 1;
+        const bool active = R.valid && j >= 1 && j <= (int)WC;
+        cur.D = commit ? out.D : cur.D; cur.H = commit ? out.H : cur.H; cur.V = commit ? out.V : cur.V;
+        if (active) dk[(size_t)s * 32 + lane] = (unsigned char)db;
+        if (active && R.last_row && j == (int)WC) { last_out[0] = out.D; last_out[1] = out.H; last_out[2] = out.V; }
+    } else {
+        cur.D = out.D; cur.H = out.H; cur.V = out.V;
+        if (R.valid) dk[(size_t)s * 32 + lane] = (unsigned char)db;
+    }
+    if (lane == 31) { W.park[u][0] = out.D; W.park[u][1] = out.H; W.park[u][2] = out.V; }
+}
+
 // One team = NW warps (x CL thread blocks of a cluster) working on one merge.  Stripe k (rows 32k+1 .. 32k+32)
 // belongs to team warp k % (NW*CL).  A warp works through its stripe chunk by chunk.  The last row of a stripe is parked
 // in the job's boundary row (L2) as TAGGED words -- every 8-byte word carries the number of the stripe that wrote it in
@@ -576,11 +642,14 @@ __device__ __forceinline__ void dp_step(WarpShared& W, const RowConst& R, const 
 // ahead (the loads fly during the 8 steps of the current chunk), looks at the tags afterwards and simply reloads until
 // all of them are the ones it expects.  Its lane 0 needs column 8c+7 of the stripe above, which that stripe's lane 31
 // computes at wavefront step 8c+38: the natural lag between consecutive stripes is about six chunks, self-regulating.
-template <int VAR, bool T32>
+// ROLE 0: one warp does everything; 1: producer, 2: consumer of a duo (VAR == 2 only; DT, bars, gcount: the pair's ring, its four
+// mbarriers {full0, full1, empty0, empty1} and the running count of chunks both warps keep)
+template <int VAR, bool T32, int ROLE = 0>
 __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, const long long* __restrict__ col, uint32_t cstride,
                                            unsigned long long* __restrict__ browg,
                                            unsigned char* __restrict__ dirs, uint32_t team_warp, uint32_t TW,
-                                           long long* last_out, WarpShared& W)
+                                           long long* last_out, WarpShared& W, DuoTerms* DT = nullptr, unsigned long long* bars = nullptr,
+                                           uint32_t gcount = 0)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t WR = M.WR, WC = M.WC;
@@ -622,7 +691,7 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
         }
         // A fragments of the IMMA tile (counters of the stripe's rows as byte digits): h&1 = row +8, h>>1 = symbols 16..31
         unsigned afrag[2][2][4];
-        if (VAR == 2 && M.tmode < 2) {
+        if (VAR == 2 && M.tmode < 2 && ROLE != 2) {
             const uint32_t g = lane >> 2, t4 = lane & 3;
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt)
@@ -679,18 +748,20 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
                 dst[which] = (long long)((bw.x & 0xffffffffull) | (bw.y << 32));
             }
         };
-        brow_load(0);
-        request(0);
-        brow_land(0);
+        if (ROLE != 1) brow_load(0);
+        if (ROLE != 2) request(0);
+        if (ROLE != 1) brow_land(0);
         const bool stripe_parks = k * 32 + 32 < WR;                   // lane 31 holds a row that has a row below it
 
         for (uint32_t m = 0; m < S; ++m) {
             const bool has_next = (m + 1) * kChunk <= WC;
-            if (has_next) brow_load(m + 1);                           // in flight during the tile and the 8 steps below
+            if (ROLE != 1 && has_next) brow_load(m + 1);              // in flight during the tile and the 8 steps below
+            if (ROLE != 2) {
             cp_async_wait_all();
             __syncwarp();
+            }
             // ---- the chunk's tile of column-pair scores into the T ring
-            if (m * kChunk <= WC) {
+            if (ROLE != 2 && m * kChunk <= WC) {
                 const long long (*S2s)[kS2Stride] = W.s2[m & 1];
                 if (VAR == 2) {
                     if (M.tmode == 0) t_tile_mma<1, T32>(afrag, S2s, m, W.t);
@@ -735,10 +806,38 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
                     }
                 }
             }
+            if (ROLE != 2) {
             __syncwarp();
             if (has_next) request(m + 1);                             // static data: no dependence on the stripe above
-            const Cell* chunk = W.brow[m & 1];
+            }
             const uint32_t s_begin = m * kChunk;
+            const uint32_t tb = gcount & 1;                           // duo: buffer and use number of this chunk
+            if (ROLE == 1) {
+                // ---- producer: the seven state-independent terms of the chunk's 8 x 32 cells into the ring
+                if (gcount >= 2) mbar_wait(bars + 2 + tb, ((gcount >> 1) - 1) & 1);      // the consumer is done with the buffer's previous chunk
+#pragma unroll 2
+                for (uint32_t u = 0; u < (uint32_t)kChunk; ++u) {
+                    const uint32_t sst = s_begin + u;
+                    const uint32_t slot = (sst - lane) & (kRing - 1), tslot = sst & (kTRing - 1);
+                    const long long t = T32 ? (long long)tring32[tslot * 32 + lane] : W.t[tslot][lane];
+                    const long long cgo = W.col[0][slot], cge = W.col[1][slot], cto = W.col[2][slot], cte = W.col[3][slot];
+                    const long long b0 = W.col[5][slot], b1 = W.col[6][slot], b2 = W.col[7][slot];
+                    long long* tv = &DT->v[tb][u][0][lane];
+                    tv[0] = t;
+                    tv[32] = t + ((cge - cgo) * R.g1o + (cte - cto) * R.g1t);
+                    tv[64] = t + W.col[4][slot] * R.nongap1;
+                    tv[96] = cgo * R.s_o + cge * R.s_e + cto * R.s_to + cte * R.s_te;
+                    tv[128] = cge * R.k_e + cte * R.k_te;
+                    tv[160] = R.srgo * ulo32(b0) + R.srge * uhi32(b0) + R.srto * ulo32(b1) + R.srte * uhi32(b1);
+                    tv[192] = R.srge * ulo32(b2) + R.srte * uhi32(b2);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bars + tb);
+                ++gcount;
+                continue;
+            }
+            if (ROLE == 2) mbar_wait(bars + tb, (gcount >> 1) & 1);   // the chunk's terms are in the ring
+            const Cell* chunk = W.brow[m & 1];
             if (m == 0) {
                 // Column 0 of the stripe (profile_par.cpp:625-640) in closed form, so that the step below never sees
                 // j == 0:  D = H = NEG and V(i, 0) = max(D, V)(i-1, 0) + cost_i, a running sum down the rows (D(i-1, 0)
@@ -759,7 +858,18 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
             }
             // steady state: every lane strictly inside the matrix during the whole macro step (j >= 2 and j < WC)
             const uint32_t tbase = s_begin & (kTRing - 1);
-            if (m >= 5 && s_begin + kChunk - 1 < WC) {
+            if (ROLE == 2) {
+                const long long* tv0 = &DT->v[tb][0][0][lane];
+                if (m >= 5 && s_begin + kChunk - 1 < WC) {
+#pragma unroll
+                    for (uint32_t u = 0; u < (uint32_t)kChunk; ++u)
+                        dp_step_duo<false>(W, R, tv0 + u * (kTermFields * 32), chunk, u, s_begin + u, lane, WC, cur, up, dk, last_out);
+                } else {
+#pragma unroll 2
+                    for (uint32_t u = 0; u < (uint32_t)kChunk; ++u)
+                        dp_step_duo<true>(W, R, tv0 + u * (kTermFields * 32), chunk, u, s_begin + u, lane, WC, cur, up, dk, last_out);
+                }
+            } else if (m >= 5 && s_begin + kChunk - 1 < WC) {
 #pragma unroll
                 for (uint32_t u = 0; u < (uint32_t)kChunk; ++u)
                     dp_step<VAR, T32, false>(W, R, chunk, u, s_begin + u, lane, WC, tbase + u, cur, up, go, ge, to, te, dk, last_out);
@@ -769,6 +879,7 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
                     dp_step<VAR, T32, true>(W, R, chunk, u, s_begin + u, lane, WC, tbase + u, cur, up, go, ge, to, te, dk, last_out);
             }
             __syncwarp();
+            if (ROLE == 2) { if (lane == 0) mbar_arrive(bars + 2 + tb); ++gcount; }      // the ring buffer may be refilled
             // park the eight cells lane 31 produced: 24 lanes tag and store one 16-byte unit each (value `which` of step cq)
             if (stripe_parks && lane < 24) {
                 const int j = (int)(s_begin + cq) - 31;
@@ -830,6 +941,46 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32, 1) k_dp_fill(c
     if (slot >= P.n_jobs) return;                                    // whole warp (NW == 1) / whole team otherwise
     if (P.wide_only && P.meta[P.order[slot]].t32) return;            // k_dp_fill_compact has done this one
     fill_body(P, P.order[slot], team_warp, TW, W);
+}
+
+// Latency mode with producer / consumer pairs: eight warps per block, warp w < 4 consumes what warp w + 4 (same SM
+// sub-partition) produces.  ProfProf merges only; any other merge runs on the four consumer warps with the one-warp code.
+constexpr size_t kDuoSmem = 4 * sizeof(DuoShared) + 16 * sizeof(unsigned long long);
+__global__ void __launch_bounds__(256, 1) k_dp_fill_duo(const DpParams P)
+{
+    extern __shared__ __align__(16) unsigned char sm_dyn[];
+    const uint32_t warp = threadIdx.x / 32, pair = warp & 3, producer = warp >> 2;
+    DuoShared& DS = reinterpret_cast<DuoShared*>(sm_dyn)[pair];
+    unsigned long long* all_bars = reinterpret_cast<unsigned long long*>(sm_dyn + 4 * sizeof(DuoShared));
+    if (threadIdx.x < 16) mbar_init(all_bars + threadIdx.x, 1);
+    __syncthreads();
+    unsigned long long* bars = all_bars + pair * 4;
+    const uint32_t CL = cooperative_groups::this_cluster().num_blocks(), cta_rank = cooperative_groups::this_cluster().block_rank();
+    const uint32_t team_warp = pair * CL + cta_rank, TW = 4 * CL;
+    const uint32_t slot = blockIdx.x / CL;
+    if (slot >= P.n_jobs) return;
+    const uint32_t jid = P.order[slot];
+    const DpJobDev J = P.jobs[jid];
+    const DpMeta M = P.meta[jid];
+    if (M.bad == 2) return;
+    if (M.var != 2) {
+        if (!producer) fill_body(P, jid, team_warp, TW, DS.w);
+        return;
+    }
+    const Scratch L(J.w1, J.w2);
+    unsigned char* scratch = P.scratch + J.scratch_off;
+    const long long* col = reinterpret_cast<const long long*>(scratch + L.col);
+    const uint32_t cstride = (uint32_t)L.cstride;
+    unsigned long long* browg = reinterpret_cast<unsigned long long*>(scratch + L.brow);
+    long long* g_last = reinterpret_cast<long long*>(scratch + L.lastv);
+    unsigned char* dirs = P.sdirs + J.t_off;
+    if (producer) {
+        if (M.t32) dp_stripes<2, true, 1>(P, M, col, cstride, browg, dirs, team_warp, TW, g_last, DS.w, &DS.t, bars);
+        else dp_stripes<2, false, 1>(P, M, col, cstride, browg, dirs, team_warp, TW, g_last, DS.w, &DS.t, bars);
+    } else {
+        if (M.t32) dp_stripes<2, true, 2>(P, M, col, cstride, browg, dirs, team_warp, TW, g_last, DS.w, &DS.t, bars);
+        else dp_stripes<2, false, 2>(P, M, col, cstride, browg, dirs, team_warp, TW, g_last, DS.w, &DS.t, bars);
+    }
 }
 
 // Throughput mode: the same stripes with 12 warps per SM instead of 8.  Two warps per SM sub-partition leave the issue slots
@@ -1224,6 +1375,57 @@ static int launch_cluster_fill(famsa_ctx* ctx, const DpParams& Q, uint32_t cl, c
     return FAMSA_OK;
 }
 
+static int launch_duo_fill(famsa_ctx* ctx, const DpParams& Q, uint32_t cl, cudaStream_t st)
+{
+    static std::atomic<bool> configured[64];
+    if (!configured[ctx->device & 63].load(std::memory_order_acquire)) {
+        FB_CUDA(cudaFuncSetAttribute(k_dp_fill_duo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDuoSmem));
+        FB_CUDA(cudaFuncSetAttribute(k_dp_fill_duo, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        configured[ctx->device & 63].store(true, std::memory_order_release);
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(Q.n_jobs * cl);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = kDuoSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FB_CUDA(cudaLaunchKernelEx(&cfg, k_dp_fill_duo, Q));
+    ctx->launches++;
+    return FAMSA_OK;
+}
+
+// largest cluster size (<= 16) the duo kernel (one block per SM) can be launched with on this device
+static uint32_t max_cluster_duo(famsa_ctx* ctx)
+{
+    static std::atomic<int> cached[64];
+    int v = cached[ctx->device & 63].load(std::memory_order_acquire);
+    if (v) return (uint32_t)v;
+    cudaFuncSetAttribute(k_dp_fill_duo, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDuoSmem);
+    cudaFuncSetAttribute(k_dp_fill_duo, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    v = 1;
+    for (int cl : {2, 4, 8, 16}) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cl);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = kDuoSmem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, k_dp_fill_duo, &cfg) == cudaSuccess && n > 0) v = cl;
+        else { cudaGetLastError(); break; }
+    }
+    cached[ctx->device & 63].store(v, std::memory_order_release);
+    return (uint32_t)v;
+}
+
 // largest cluster size (<= 16) the 4-warp fill kernel can be launched with on this device
 static uint32_t max_cluster4(famsa_ctx* ctx)
 {
@@ -1464,6 +1666,8 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext,
         // throughput mode with only a handful of block-sized merges: give every merge with more than 8 stripes a cluster
         uint32_t cl_min = cluster_min;
         if (n_teamable * kDpCluster <= 2u * (uint32_t)ctx->sm_count) cl_min = std::min(cluster_min, std::max(team_min, 256u));
+        const bool duo_on = !getenv("FAMSA_DP_DUO") || atoi(getenv("FAMSA_DP_DUO")) != 0;       // development knob (0: one warp per stripe)
+        const uint32_t duo_cap = duo_on ? max_cluster_duo(ctx) : 1;
         auto cluster_of = [&](uint32_t a) {                       // latency mode: blocks (of 4 warps) for merge a
             const uint32_t want = (stripes_of(a) + 3) / 4;
             uint32_t cl = 1;
@@ -1472,7 +1676,13 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext,
         };
         auto cls = [&](uint32_t a) -> int {                       // sort key: larger = launched first
             const uint32_t w = std::min(dev[a].w1, dev[a].w2);
-            if (small_batch) return stripes_of(a) >= 2 ? 10 + (int)cluster_of(a) : 0;
+            if (small_batch) {
+                if (stripes_of(a) < 2) return 0;
+                const uint32_t cl = cluster_of(a);
+                // ProfProf merges wide enough for a cluster: producer / consumer pairs (k_dp_fill_duo)
+                if (duo_on && cl >= 2 && dev[a].card1 > 1 && dev[a].card2 > 1) return 100 + (int)std::min(cl, duo_cap);
+                return 10 + (int)cl;
+            }
             if (w > cl_min) return 2;
             return w > team_min ? 1 : 0;
         };
@@ -1548,6 +1758,8 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext,
                 k_dp_fill<1, false><<<(Q.n_jobs + kDpWarps - 1) / kDpWarps, kDpWarps * 32, kDpWarps * sizeof(WarpShared), st>>>(Q);
                 FB_CUDA(cudaGetLastError());
                 ctx->launches++;
+            } else if (c >= 100) {
+                FB_TRY(launch_duo_fill(ctx, Q, (uint32_t)c - 100, st));
             } else if (c >= 10) {
                 const uint32_t cl = (uint32_t)c - 10;
                 if (cl == 1) {
@@ -1564,8 +1776,8 @@ int dp_run_device(famsa_ctx* ctx, const famsa_dp_job* jobs, const DpJobExt* ext,
                 // From two merges per SM on, the compact kernel (12 warps per SM): 6, 4 or 2 warps per merge.
                 int nw = kDpTeamWarps;
                 const uint32_t sms = (uint32_t)ctx->sm_count;
-                static const bool compact_ok = !getenv("FAMSA_DP_COMPACT") || atoi(getenv("FAMSA_DP_COMPACT")) != 0;   // development knob
-                bool compact = compact_ok && Q.n_jobs >= 2u * sms;
+                const int compact_mode = getenv("FAMSA_DP_COMPACT") ? atoi(getenv("FAMSA_DP_COMPACT")) : 1;   // development knob: 0 never, 2 always
+                bool compact = compact_mode == 2 || (compact_mode == 1 && Q.n_jobs >= 2u * sms);
                 if (compact) nw = Q.n_jobs >= 6u * sms ? 2 : (Q.n_jobs >= 3u * sms ? 4 : 6);
                 else if (Q.n_jobs >= 4u * sms) nw = 2;
                 else if (Q.n_jobs >= 2u * sms) nw = 4;

@@ -178,10 +178,16 @@ def test_inconsistent_profile_is_rejected(engine):
         engine.dp_align_batch([(a[0], a[1], a[2], b[0], c, b[2])], gaps)
 
 
-def test_scores_beyond_32_bits(engine):
-    """k_dp_t has a 32 x 32 -> 64 bit path for tables whose scores fit in int32 (every realistic profile) and a
-    32 x 64 path otherwise; substitution scores of ~1e9 push the tables past 2^31 and exercise the latter."""
+@pytest.mark.parametrize("env", [{}, {"FAMSA_DP_LATENCY_MODE": "0", "FAMSA_DP_TEAM_MIN": "32", "FAMSA_DP_COMPACT": "2"},
+                                 {"FAMSA_DP_LATENCY_MODE": "1", "FAMSA_DP_DUO": "0"}])
+def test_scores_beyond_32_bits(engine, monkeypatch, env):
+    """The column-pair scores T have a tensor-core path for tables whose scores fit in int32 (every realistic profile) and a
+    scalar 32 x 64 path otherwise, and the T ring holds 4- or 8-byte entries; substitution scores of ~1e9 push the tables
+    past 2^31 and exercise the wide forms -- in the default launch shape, in the compact kernel (which must leave such merges
+    to the full kernel launched behind it) and in plain clusters."""
     from famsa_b200 import profiles
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     rng = np.random.default_rng(9)
     sm = profiles.synth_score_matrix(rng) * 300_000
     gaps = np.array([-14850, -1250, -660, -660], dtype=np.int64) * 300_000

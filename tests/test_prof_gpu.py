@@ -159,11 +159,17 @@ def test_prof_errors(engine):
                                  {"FAMSA_PROF_FUSED": "0", "FAMSA_DP_LATENCY_MODE": "0", "FAMSA_DP_TEAM_WARPS": "2"},
                                  {"FAMSA_PROF_FUSED": "0", "FAMSA_DP_LATENCY_MODE": "1", "FAMSA_DP_MAX_CLUSTER": "2"},
                                  {"FAMSA_PROF_FUSED": "0", "FAMSA_DP_LATENCY_MODE": "1"},
+                                 {"FAMSA_PROF_FUSED": "0", "FAMSA_DP_LATENCY_MODE": "1", "FAMSA_DP_DUO": "0"},
+                                 {"FAMSA_PROF_FUSED": "0", "FAMSA_DP_LATENCY_MODE": "1", "FAMSA_DP_MAX_CLUSTER": "2", "FAMSA_DP_DUO": "0"},
+                                 {"FAMSA_PROF_FUSED": "0", "FAMSA_DP_LATENCY_MODE": "0", "FAMSA_DP_TEAM_MIN": "32", "FAMSA_DP_COMPACT": "2"},
+                                 {"FAMSA_PROF_FUSED": "0", "FAMSA_DP_LATENCY_MODE": "0", "FAMSA_DP_TEAM_MIN": "32", "FAMSA_DP_COMPACT": "2", "FAMSA_DP_TEAM_WARPS": "2"},
+                                 {"FAMSA_PROF_FUSED": "0", "FAMSA_DP_LATENCY_MODE": "0", "FAMSA_DP_TEAM_MIN": "32", "FAMSA_DP_COMPACT": "2", "FAMSA_DP_TEAM_WARPS": "4"},
                                  {"FAMSA_PROF_FUSED": "1"}])
 def test_resident_launch_shapes(engine, monkeypatch, env):
     """The resident path through sub-batches of a few merges and through every launch shape of the fill kernel: the
-    throughput-mode cluster (8 x 8 warps), one warp per merge, 2-warp teams, and the latency-mode clusters of 4-warp
-    blocks, and the fused one-block-per-merge kernel (development knobs of dp.cu / prof.cu force each shape on an ordinary family)."""
+    throughput-mode cluster (8 x 8 warps), one warp per merge, 2-warp teams, the compact 12-warps-per-SM kernel with 6, 2 and 4
+    warps per merge, the latency-mode clusters of producer / consumer pairs and of plain 4-warp blocks, and the fused
+    one-block-per-merge kernel (development knobs of dp.cu / prof.cu force each shape on an ordinary family)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     rng = np.random.default_rng(41)
