@@ -575,28 +575,16 @@ __device__ __forceinline__ void dp_step(WarpShared& W, const RowConst& R, const 
 // staging, the tensor-core T tile, and per cell seven int64 terms that combine the column record with the row's counts
 // (profile_par.cpp:679-886).  A PRODUCER warp on the same sub-partition computes those into a shared-memory ring, one
 // chunk (8 steps x 7 terms x 32 lanes) at a time; the CONSUMER warp is left with the compare / select chain, the
-// shuffles and the boundary row.  Two mbarriers per buffer (full / empty), two buffers.
+// shuffles and the boundary row.  Two named barriers per buffer (full / empty), two buffers.
 constexpr int kTermFields = 7;
 struct __align__(16) DuoTerms { long long v[2][kChunk][kTermFields][32]; };
 struct __align__(16) DuoShared { WarpShared w; DuoTerms t; };
 
-__device__ __forceinline__ uint32_t smem_addr32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* b)
-{
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_addr32(b)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity)
-{
-    const uint32_t a = smem_addr32(b);
-    uint32_t done = 0;
-    while (!done)
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
-}
+// Named barriers (bar.sync / bar.arrive, 64 threads = the two warps of a pair): the producer ARRIVES on full[b] after it
+// has written buffer b and the consumer SYNCs on it before reading; the consumer arrives on empty[b] when it is done and the
+// producer syncs on that before it refills.  Four barrier ids per pair, sixteen per block -- all there are.
+__device__ __forceinline__ void pair_sync(uint32_t id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void pair_arrive(uint32_t id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
 // the consumer's step: dp_step<2, ...> with the state-independent terms read from the ring
 template <bool GUARD>
@@ -642,13 +630,13 @@ __device__ __forceinline__ void dp_step_duo(WarpShared& W, const RowConst& R, co
 // ahead (the loads fly during the 8 steps of the current chunk), looks at the tags afterwards and simply reloads until
 // all of them are the ones it expects.  Its lane 0 needs column 8c+7 of the stripe above, which that stripe's lane 31
 // computes at wavefront step 8c+38: the natural lag between consecutive stripes is about six chunks, self-regulating.
-// ROLE 0: one warp does everything; 1: producer, 2: consumer of a duo (VAR == 2 only; DT, bars, gcount: the pair's ring, its four
-// mbarriers {full0, full1, empty0, empty1} and the running count of chunks both warps keep)
+// ROLE 0: one warp does everything; 1: producer, 2: consumer of a duo (VAR == 2 only; DT, bars, gcount: the pair's ring, the first of
+// its four barrier ids {full0, full1, empty0, empty1} and the running count of chunks both warps keep)
 template <int VAR, bool T32, int ROLE = 0>
 __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, const long long* __restrict__ col, uint32_t cstride,
                                            unsigned long long* __restrict__ browg,
                                            unsigned char* __restrict__ dirs, uint32_t team_warp, uint32_t TW,
-                                           long long* last_out, WarpShared& W, DuoTerms* DT = nullptr, unsigned long long* bars = nullptr,
+                                           long long* last_out, WarpShared& W, DuoTerms* DT = nullptr, uint32_t bars = 0,
                                            uint32_t gcount = 0)
 {
     const uint32_t lane = threadIdx.x & 31;
@@ -814,7 +802,7 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
             const uint32_t tb = gcount & 1;                           // duo: buffer and use number of this chunk
             if (ROLE == 1) {
                 // ---- producer: the seven state-independent terms of the chunk's 8 x 32 cells into the ring
-                if (gcount >= 2) mbar_wait(bars + 2 + tb, ((gcount >> 1) - 1) & 1);      // the consumer is done with the buffer's previous chunk
+                if (gcount >= 2) pair_sync(bars + 2 + tb);                // the consumer is done with the buffer's previous chunk
 #pragma unroll 2
                 for (uint32_t u = 0; u < (uint32_t)kChunk; ++u) {
                     const uint32_t sst = s_begin + u;
@@ -831,12 +819,11 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
                     tv[160] = R.srgo * ulo32(b0) + R.srge * uhi32(b0) + R.srto * ulo32(b1) + R.srte * uhi32(b1);
                     tv[192] = R.srge * ulo32(b2) + R.srte * uhi32(b2);
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bars + tb);
+                pair_arrive(bars + tb);
                 ++gcount;
                 continue;
             }
-            if (ROLE == 2) mbar_wait(bars + tb, (gcount >> 1) & 1);   // the chunk's terms are in the ring
+            if (ROLE == 2) pair_sync(bars + tb);                      // the chunk's terms are in the ring
             const Cell* chunk = W.brow[m & 1];
             if (m == 0) {
                 // Column 0 of the stripe (profile_par.cpp:625-640) in closed form, so that the step below never sees
@@ -879,7 +866,7 @@ __device__ __forceinline__ void dp_stripes(const DpParams& P, const DpMeta& M, c
                     dp_step<VAR, T32, true>(W, R, chunk, u, s_begin + u, lane, WC, tbase + u, cur, up, go, ge, to, te, dk, last_out);
             }
             __syncwarp();
-            if (ROLE == 2) { if (lane == 0) mbar_arrive(bars + 2 + tb); ++gcount; }      // the ring buffer may be refilled
+            if (ROLE == 2) { pair_arrive(bars + 2 + tb); ++gcount; }    // the ring buffer may be refilled
             // park the eight cells lane 31 produced: 24 lanes tag and store one 16-byte unit each (value `which` of step cq)
             if (stripe_parks && lane < 24) {
                 const int j = (int)(s_begin + cq) - 31;
@@ -945,16 +932,13 @@ __global__ void __launch_bounds__((NW == 1 ? kDpWarps : NW) * 32, 1) k_dp_fill(c
 
 // Latency mode with producer / consumer pairs: eight warps per block, warp w < 4 consumes what warp w + 4 (same SM
 // sub-partition) produces.  ProfProf merges only; any other merge runs on the four consumer warps with the one-warp code.
-constexpr size_t kDuoSmem = 4 * sizeof(DuoShared) + 16 * sizeof(unsigned long long);
+constexpr size_t kDuoSmem = 4 * sizeof(DuoShared);
 __global__ void __launch_bounds__(256, 1) k_dp_fill_duo(const DpParams P)
 {
     extern __shared__ __align__(16) unsigned char sm_dyn[];
     const uint32_t warp = threadIdx.x / 32, pair = warp & 3, producer = warp >> 2;
     DuoShared& DS = reinterpret_cast<DuoShared*>(sm_dyn)[pair];
-    unsigned long long* all_bars = reinterpret_cast<unsigned long long*>(sm_dyn + 4 * sizeof(DuoShared));
-    if (threadIdx.x < 16) mbar_init(all_bars + threadIdx.x, 1);
-    __syncthreads();
-    unsigned long long* bars = all_bars + pair * 4;
+    const uint32_t bars = pair * 4;                                   // barrier ids of this pair
     const uint32_t CL = cooperative_groups::this_cluster().num_blocks(), cta_rank = cooperative_groups::this_cluster().block_rank();
     const uint32_t team_warp = pair * CL + cta_rank, TW = 4 * CL;
     const uint32_t slot = blockIdx.x / CL;
