@@ -73,7 +73,7 @@ int famsa_create(int device, famsa_ctx** out_ctx)
         for (auto& ev : ctx->ev) FB_CUDA(cudaEventCreate(&ev));
         FB_CUDA(cudaEventCreateWithFlags(&ctx->ev_busy, cudaEventDisableTiming));
         FB_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-        FB_CUDA(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+        for (auto& e : ctx->ev_copy) FB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : ctx->ev_join) FB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& a : ctx->aux_stream) FB_CUDA(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
         // per-call scratch and resident profiles are stream-ordered allocations: the pool keeps what it has
@@ -113,7 +113,10 @@ void famsa_destroy(famsa_ctx* ctx)
         if (ev) cudaEventDestroy(ev);
     if (ctx->ev_busy) cudaEventDestroy(ctx->ev_busy);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    for (auto& e : ctx->ev_copy)
+        if (e) cudaEventDestroy(e);
+    for (auto& st : ctx->peer_stream)
+        if (st) cudaStreamDestroy(st);
     for (auto& e : ctx->ev_join)
         if (e) cudaEventDestroy(e);
     for (auto& a : ctx->aux_stream)
@@ -362,13 +365,16 @@ int famsa_lcs_triangle_exchange(famsa_ctx* ctx, uint32_t row_begin, uint32_t row
         for (auto& e : ctx->ev_host) FB_CUDA(cudaEventCreate(&e));
     }
     auto tri = [](uint64_t r) { return r ? r * (r - 1) / 2 : 0; };
-    // pieces with equal numbers of pairs (a non-identity order cannot be cut by rows: one piece)
+    // Pieces (a non-identity order cannot be cut by rows: one piece).  The copy of the LAST piece is the only exposed part of
+    // the exchange, so the pieces shrink towards the end: 14 % of the pairs each at first, 8 % at last.
     const uint32_t np = ctx->lcs.identity_perm ? std::min(std::max(n_pieces, 1u), kPieces) : 1u;
     uint32_t bounds[kPieces + 1];
     bounds[0] = row_begin;
     const uint64_t pairs = tri(row_end) - tri(row_begin);
+    static const double kCut8[9] = {0.0, 0.14, 0.28, 0.42, 0.56, 0.70, 0.82, 0.92, 1.0};
     for (uint32_t b = 1; b < np; ++b) {
-        const double target = (double)tri(row_begin) + (double)pairs * b / np;
+        const double frac = np == 8 ? kCut8[b] : (double)b / np;
+        const double target = (double)tri(row_begin) + (double)pairs * frac;
         uint32_t r = (uint32_t)((1.0 + std::sqrt(1.0 + 8.0 * target)) / 2.0);
         r = (r + 16) / 32 * 32;                                        // on a mask-group boundary: no group is computed twice
         bounds[b] = std::min(std::max(r, bounds[b - 1]), row_end);
@@ -381,16 +387,26 @@ int famsa_lcs_triangle_exchange(famsa_ctx* ctx, uint32_t row_begin, uint32_t row
     // every finished piece goes to the same place of every peer's triangle while the next pieces are being computed: copy
     // engines over NVLink, no SM and no collective kernel involved
     if (n_peers) {
+        constexpr int kLanes = 1 + sizeof(ctx->peer_stream) / sizeof(ctx->peer_stream[0]);
+        cudaStream_t lanes[kLanes];
+        lanes[0] = ctx->copy_stream;
+        for (int a = 1; a < kLanes; ++a) {
+            if (!ctx->peer_stream[a - 1]) FB_CUDA(cudaStreamCreateWithFlags(&ctx->peer_stream[a - 1], cudaStreamNonBlocking));
+            lanes[a] = ctx->peer_stream[a - 1];
+        }
+        const int n_lanes = (int)std::min<uint32_t>(n_peers, kLanes);
         for (uint32_t b = 0; b < np; ++b) {
             const uint64_t off = tri(bounds[b]) * elem_bytes, bytes = (tri(bounds[b + 1]) - tri(bounds[b])) * elem_bytes;
             if (!bytes) continue;
-            FB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_block[b], 0));
+            for (int a = 0; a < n_lanes; ++a) FB_CUDA(cudaStreamWaitEvent(lanes[a], ctx->ev_block[b], 0));
             for (uint32_t k = 0; k < n_peers; ++k)
                 FB_CUDA(cudaMemcpyAsync(static_cast<char*>(d_peer_full[k]) + off, static_cast<char*>(d_full) + off, bytes,
-                                        cudaMemcpyDeviceToDevice, ctx->copy_stream));
+                                        cudaMemcpyDeviceToDevice, lanes[k % n_lanes]));
         }
-        FB_CUDA(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));     // the caller's stream continues after the last copy
-        FB_CUDA(cudaStreamWaitEvent(st, ctx->ev_copy, 0));
+        for (int a = 0; a < n_lanes; ++a) {                           // the caller's stream continues after the last copy
+            FB_CUDA(cudaEventRecord(ctx->ev_copy[a], lanes[a]));
+            FB_CUDA(cudaStreamWaitEvent(st, ctx->ev_copy[a], 0));
+        }
     }
     if (!stream) { FB_CUDA(cudaStreamSynchronize(st)); fb::scratch_release(ctx, st, true); return finish_timing(ctx); }
     return fb::scratch_release(ctx, st, false);

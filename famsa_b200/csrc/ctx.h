@@ -186,7 +186,8 @@ struct famsa_ctx {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;                 // D2H of finished row blocks (famsa_lcs_triangle)
     cudaEvent_t ev_block[8] = {};
-    cudaEvent_t ev_copy = nullptr;                      // end of the peer copies of famsa_lcs_triangle_exchange
+    cudaEvent_t ev_copy[4] = {};                        // end of the peer copies of famsa_lcs_triangle_exchange, per copy stream
+    cudaStream_t peer_stream[3] = {};                   // further copy streams: the peers of a piece are served side by side
     cudaEvent_t ev_host[2] = {};
     // The context-owned scratch (tile lists, DP scratch, ...) is shared by every call.  A *_device call on a caller
     // stream returns while its kernels are still queued, so it leaves `ev_busy` recorded behind them and the next call
