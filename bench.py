@@ -310,7 +310,7 @@ def bench_dp(eng, torch, dist, world, rank, steps, warmup, l2_flush, stream, wan
                                            "ranks sharing one host); kept for callers that hold profiles on the host"},
                "gpu_launches": int(launches),
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": dp_traffic, "peak_source": peak_src, "kernel": "fb::k_dp_prep + k_dp_fill<NW,CL> + k_dp_trace",
+                            "traffic": dp_traffic, "peak_source": peak_src, "kernel": "fb::k_dp_prep + k_dp_fill_compact<NW> + k_dp_trace",
                             "kernel_ms": kern_ms, "algorithmic_bytes": alg,
                             "note": "achieved = SURVEY 8d algorithmic bytes / time of the DP kernels of one batch; traffic = DRAM "
                                     "bytes of the same kernels from ncu (profiles/dp_fill_traffic.json): the column-pair scores T "
