@@ -1228,11 +1228,13 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_merge_fused(const DpPar
     __shared__ __align__(16) unsigned char sm_tile[2 * kTraceWin * 32];
     __shared__ ConShared sm_con;
     const uint32_t warp = threadIdx.x / 32;
+    uint32_t leaves_ready = 0xffffffffu;                               // job whose leaves are already materialised
     for (uint32_t lv = 0; lv < F.n_levels; ++lv) {
     for (uint32_t jid = F.level_start[lv] + blockIdx.x; jid < F.level_start[lv + 1]; jid += gridDim.x) {
     const FusedJob fj = F.jobs[jid];
-    for (int side = 0; side < 2; ++side)
-        if (fj.leaf[side].seq != 0xffffffffu) leaf_body(fj.leaf[side], F.codes, F.off, F.len, F.sm, P.go, P.ge, P.to, P.te);
+    if (jid != leaves_ready)                                          // (else: materialised during the previous level's traceback)
+        for (int side = 0; side < 2; ++side)
+            if (fj.leaf[side].seq != 0xffffffffu) leaf_body(fj.leaf[side], F.codes, F.off, F.len, F.sm, P.go, P.ge, P.to, P.te);
     __syncthreads();
     FB_PHASE(0);
     prep_body(P, jid);
@@ -1256,7 +1258,17 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_merge_fused(const DpPar
     }
     __syncthreads();
     FB_PHASE(3);
+    // the seven warps the traceback does not need materialise the leaves of this block's first merge of the next level
+    uint32_t nj = 0xffffffffu;
+    if (lv + 1 < F.n_levels && jid + gridDim.x >= F.level_start[lv + 1] && F.level_start[lv + 1] + blockIdx.x < F.level_start[lv + 2])
+        nj = F.level_start[lv + 1] + blockIdx.x;
     if (warp == 0) trace_body(P, jid, sm_tile, all_dirs);
+    else if (nj != 0xffffffffu) {
+        const FusedJob nf = F.jobs[nj];
+        for (int side = 0; side < 2; ++side)
+            if (nf.leaf[side].seq != 0xffffffffu) leaf_body(nf.leaf[side], F.codes, F.off, F.len, F.sm, P.go, P.ge, P.to, P.te, 1);
+    }
+    leaves_ready = nj;
     __syncthreads();
     FB_PHASE(4);
     ConJob J;

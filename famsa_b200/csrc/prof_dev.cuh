@@ -25,11 +25,13 @@ struct LeafDesc {
 __device__ __forceinline__ void leaf_body(const LeafDesc L, const int8_t* __restrict__ codes,
                                           const uint64_t* __restrict__ off, const uint32_t* __restrict__ len,
                                           const long long* __restrict__ sm, long long go, long long ge,
-                                          long long to, long long te)
+                                          long long to, long long te, int warp_first = 0)
 {
+    // the block's warps warp_first .. take part (all of them by default)
     const uint32_t n = len[L.seq];
     const int8_t* s = codes + off[L.seq];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = (int)(threadIdx.x >> 5) - warp_first, nwarps = (int)(blockDim.x >> 5) - warp_first;
+    if (warp < 0) return;
     const long long gapv = lane == kGO ? go : lane == kGE ? ge : lane == kTE ? te : lane == kTO ? to : 0;
     for (uint32_t c = warp; c <= n; c += nwarps) {
         long long sc = gapv;
