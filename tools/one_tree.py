@@ -28,12 +28,6 @@ torch.cuda.cudart().cudaProfilerStart()
 root, _, st = eng.align_tree(z["merges"], z["gaps"], want_paths=False)
 torch.cuda.cudart().cudaProfilerStop()
 print(st)
-if os.environ.get('TRY_NOWAIT'):
-    eng.prof_drop([root])
-    os.environ['FAMSA_TREE_NOWAIT'] = '1'
-    import time
-    t0 = time.time(); root, _, st2 = eng.align_tree(z['merges'], z['gaps'], want_paths=False); torch.cuda.synchronize(); print('NOWAIT wall incl. final sync: %.2f ms' % (1e3 * (time.time() - t0)), st2['n_batches'])
-    del os.environ['FAMSA_TREE_NOWAIT']
 import ctypes as C
 if os.environ.get('FAMSA_FUSED_TIMING'):
     out = (C.c_double * 8)()
