@@ -247,6 +247,49 @@ public:
     void Drop(const std::vector<uint32_t>& ids) { check(famsa_prof_drop(ctx_.get(), ids.data(), (uint32_t)ids.size())); }
 };
 
+// The whole merge loop of CFAMSA::ComputeAlignment (msa.cpp:360-438, with CProfileQueue, queues.cpp:17-187) as one call:
+// guide_tree = the reference's tree_structure (n_leaves leaf entries, then one (left, right) pair per internal node,
+// children before parents); leaves are the sequences of CLCSBP's upload.  merges[k] describes internal node n_leaves + k.
+struct TreeAlignment {
+    std::vector<AlignResult> merges;
+    uint32_t root_id = 0;              // resident id of the final profile (ResidentProfiles::Download / Drop)
+    famsa_tree_stats stats{};
+};
+inline TreeAlignment AlignTree(Context& ctx, const std::vector<std::pair<int, int>>& guide_tree, uint32_t n_leaves, const int64_t gaps[4])
+{
+    static_assert(sizeof(std::pair<int, int>) == 2 * sizeof(int32_t), "tree_structure is a vector of int pairs");
+    TreeAlignment out;
+    const size_t n_merges = guide_tree.size() > n_leaves ? guide_tree.size() - n_leaves : 0;
+    std::vector<famsa_dp_result> res(std::max<size_t>(1, n_merges));
+    uint64_t path_bytes = 0;
+    check(famsa_prof_align_tree(ctx.get(), reinterpret_cast<const int32_t*>(guide_tree.data() + n_leaves), n_leaves, gaps, res.data(),
+                                &out.root_id, &path_bytes, &out.stats));
+    std::vector<uint8_t> paths(std::max<uint64_t>(1, path_bytes));
+    check(famsa_prof_tree_paths(ctx.get(), paths.data(), paths.size()));
+    out.merges.resize(n_merges);
+    for (size_t k = 0; k < n_merges; ++k) {
+        const famsa_dp_result& r = res[k];
+        out.merges[k].path.assign(paths.begin() + r.path_offset, paths.begin() + r.path_offset + r.path_len);
+        out.merges[k].total_score = r.total_score;
+        std::copy(r.last, r.last + 3, out.merges[k].last);
+        out.merges[k].swapped = r.swapped != 0;
+        out.merges[k].variant = r.variant;
+    }
+    return out;
+}
+
+// UPGMA<distance>::run (UPGMA.cpp:39-51) on the device: the n - 1 merges, tree_structure's internal-node part
+inline std::vector<std::pair<int, int>> UPGMATree(Context& ctx, Distance measure, bool modified)
+{
+    const uint32_t n = famsa_lcs_n_seqs(ctx.get());
+    if (measure == Distance::pairwise_identity) throw std::runtime_error("famsa_b200: UPGMA is instantiated for the two indel distances only");
+    std::vector<int32_t> t(2 * (size_t)std::max<uint32_t>(n, 1));
+    check(famsa_lcs_upgma(ctx.get(), measure == Distance::indel075_div_lcs ? 0 : 1, modified ? 1 : 0, t.data()));
+    std::vector<std::pair<int, int>> out;
+    for (uint32_t k = 0; k + 1 < n; ++k) out.emplace_back(t[2 * k], t[2 * k + 1]);
+    return out;
+}
+
 // Level-synchronous order of the guide tree's merges (replaces CProfileQueue's one-at-a-time hand-out,
 // queues.cpp:17-187): tree = the reference's tree_structure, n leaves then internal nodes (left, right).
 // Returns, per level, the indices (into the internal-node part) of the merges whose children are finished.

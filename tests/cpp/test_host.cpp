@@ -148,6 +148,46 @@ int main()
         check(famsa_prof_stats(ctx.get(), &live, &bytes));
         REQUIRE(live == 0 && bytes == 0);
     }
+    // ---- the whole merge loop in one call (AlignTree) against the same tree run level by level (ResidentProfiles)
+    {
+        std::vector<int64_t> sm(24 * 24);
+        for (int a = 0; a < 24; ++a) for (int b = 0; b <= a; ++b) sm[a * 24 + b] = sm[b * 24 + a] = (a == b ? 5000 + 100 * a : (int64_t)((a * 7 + b * 13) % 9) * 500 - 2500);
+        const int64_t g[4] = {-14850, -1250, -660, -660};
+        // the UPGMA tree of the set, built on the device, as the guide tree: n leaf entries + n - 1 merges
+        auto up = UPGMATree(ctx, Distance::indel075_div_lcs, false);
+        REQUIRE(up.size() == n - 1);
+        std::vector<std::pair<int, int>> tree(n, std::make_pair(-1, -1));
+        tree.insert(tree.end(), up.begin(), up.end());
+        std::vector<int> used(2 * n - 1, 0);
+        for (uint32_t k = 0; k + 1 < n; ++k) {
+            REQUIRE(up[k].first >= 0 && up[k].second >= 0 && (uint32_t)up[k].first < n + k && (uint32_t)up[k].second < n + k);
+            ++used[up[k].first]; ++used[up[k].second];
+        }
+        for (uint32_t v = 0; v + 1 < 2 * n - 1; ++v) REQUIRE(used[v] == 1);                // every node but the root is merged exactly once
+        ResidentProfiles rp(ctx, sm.data(), lens);
+        TreeAlignment ta = AlignTree(ctx, tree, n, g);
+        REQUIRE(ta.merges.size() == n - 1 && ta.stats.cells > 0);
+        std::vector<uint32_t> node(2 * n - 1);
+        for (uint32_t i = 0; i < n; ++i) node[i] = ResidentProfiles::Leaf(i);
+        for (auto& level : ReadyLevels(tree, n)) {
+            std::vector<famsa_prof_merge> lvl;
+            for (uint32_t k : level) lvl.push_back({node[tree[n + k].first], node[tree[n + k].second]});
+            std::vector<uint32_t> ids;
+            auto r = rp.MergeLevel(lvl, g, ids);
+            for (size_t q = 0; q < level.size(); ++q) {
+                const AlignResult& a = ta.merges[level[q]];
+                REQUIRE(a.total_score == r[q].total_score && a.path == r[q].path && a.swapped == r[q].swapped);
+                node[n + level[q]] = ids[q];
+            }
+        }
+        uint32_t w = 0, card = 0;
+        check(famsa_prof_get(ctx.get(), ta.root_id, &w, &card, nullptr, nullptr));
+        REQUIRE(card == n && w == ta.merges.back().path.size());
+        rp.Drop({node[2 * n - 2], ta.root_id});
+        uint64_t live = 1, bytes = 1;
+        check(famsa_prof_stats(ctx.get(), &live, &bytes));
+        REQUIRE(live == 0 && bytes == 0);
+    }
     std::printf("host mirror ok\n");
     return 0;
 }
