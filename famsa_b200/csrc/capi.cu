@@ -455,7 +455,7 @@ int famsa_lcs_rows(famsa_ctx* ctx, const uint32_t* ref_ids, uint32_t n_ref, cons
     int rc = check_elem(ctx, elem_bytes);
     if (rc) return rc;
     if (!col_ids && n_col > ctx->lcs.n) { set_error("n_col exceeds the number of sequences"); return FAMSA_E_INVALID; }
-    if ((n_ref && !ref_ids) || ((uint64_t)n_ref * n_col && !out)) { set_error("NULL argument"); return FAMSA_E_INVALID; }
+    if ((n_ref && !ref_ids) || (n_ref && n_col && !out)) { set_error("NULL argument"); return FAMSA_E_INVALID; }
     if (col_ids)
         for (uint32_t k = 0; k < n_col; ++k)
             if (col_ids[k] >= ctx->lcs.n) { set_error("col id out of range"); return FAMSA_E_INVALID; }

@@ -895,7 +895,6 @@ int prof_align_tree(famsa_ctx* ctx, const int32_t* tree, uint32_t n_leaves, cons
             level_cost(&bound_cells, &path_need);
             if (path_cursor + path_need > P.h_tree_paths_cap) {      // nothing in flight now: the arena may move
                 uint8_t* old = P.h_tree_paths;
-                size_t old_cap = P.h_tree_paths_cap;
                 P.h_tree_paths = nullptr; P.h_tree_paths_cap = 0;
                 FB_TRY(pinned_reserve(reinterpret_cast<void**>(&P.h_tree_paths), &P.h_tree_paths_cap, (path_cursor + path_need) * 2));
                 memcpy(P.h_tree_paths, old, path_cursor);
