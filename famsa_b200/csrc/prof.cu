@@ -899,7 +899,6 @@ int prof_align_tree(famsa_ctx* ctx, const int32_t* tree, uint32_t n_leaves, cons
                 FB_TRY(pinned_reserve(reinterpret_cast<void**>(&P.h_tree_paths), &P.h_tree_paths_cap, (path_cursor + path_need) * 2));
                 memcpy(P.h_tree_paths, old, path_cursor);
                 cudaFreeHost(old);
-                (void)old_cap;
             }
         }
         std::vector<famsa_prof_merge> mg(level.size());
