@@ -550,10 +550,14 @@ __global__ void __launch_bounds__(1024) k_prim(const void* __restrict__ tri, int
             const size_t at = (size_t)hi * (hi - 1) / 2 + lo;
             return eb == 2 ? static_cast<const uint16_t*>(tri)[at] : static_cast<const uint32_t*>(tri)[at];
         };
+        // MSTPrim.cpp:450-467: a candidate is only computed when the distance it would have with LCS = the shorter length
+        // does not exceed its current one.  A no-op for a true LCS (<= the shorter length); with the dropped-carry corner the
+        // reference's LCS can be larger, and then the skip decides whether the candidate is relaxed.
         if (has0 && !vis0) {
             const uint32_t j = gtid;
-            const double d = transform_f64(kind, lookup(j), lv, len0, pow075, never);
-            if (d <= d0) {
+            const bool tried = transform_f64(kind, lv < len0 ? lv : len0, lv, len0, pow075, never) <= d0;
+            const double d = tried ? transform_f64(kind, lookup(j), lv, len0, pow075, never) : 1.7976931348623157e308;
+            if (tried && d <= d0) {
                 const unsigned long long a = v < j ? v : j, b = v < j ? j : v;
                 const unsigned long long k = ~((a << 32) + b);
                 if (d < d0 || k < k0) { d0 = d; k0 = k; }                                  // pair <, given d <= d0
@@ -562,10 +566,12 @@ __global__ void __launch_bounds__(1024) k_prim(const void* __restrict__ tri, int
         }
         for (uint32_t j = gtid + gthreads; j < n; j += gthreads) {                         // only when n > grid size
             if (visited[j]) continue;
-            const double d = transform_f64(kind, lookup(j), lv, lens[j], pow075, never);
             double cd = st[j].dist;
             unsigned long long ck = st[j].key;
-            if (d <= cd) {
+            const uint32_t lj = lens[j];
+            const bool tried = transform_f64(kind, lv < lj ? lv : lj, lv, lj, pow075, never) <= cd;
+            const double d = tried ? transform_f64(kind, lookup(j), lv, lj, pow075, never) : 1.7976931348623157e308;
+            if (tried && d <= cd) {
                 const unsigned long long a = v < j ? v : j, b = v < j ? j : v;
                 const unsigned long long k = ~((a << 32) + b);
                 if (d < cd || k < ck) { cd = d; ck = k; st[j].dist = cd; st[j].key = ck; }

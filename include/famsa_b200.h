@@ -156,7 +156,8 @@ int famsa_lcs_assign_shard(famsa_ctx* ctx, const uint32_t* seed_ids, uint32_t n_
  * device.  Per step: distances from the current vertex (as the row, seq0) to every unvisited sequence through
  * Transform<double, distance>, the relaxation  s = {d, ~ids_to_uint64(v, j)};  if (d <= best[j].first && s < best[j])
  * best[j] = s  (MSTPrim.cpp:492-503), and the election of the unvisited vertex with the smallest pair
- * (:366-386); the reference's lower-bound pruning (:450-467) does not change results and is not needed.
+ * (:366-386), including the lower-bound skip of :450-467 (a candidate whose distance with LCS = the shorter length
+ * cannot beat its current one is not computed: a no-op for true LCS values, decisive in the dropped-carry corner).
  * Because the pair is a strict total order on the edges, the tree is the unique MST under it: the library finds it with
  * parallel Boruvka rounds over a float64 distance triangle and replays Prim's visiting order on the n-1 tree edges
  * (the sequential loop itself runs when a sequence has orientation-dependent LCS values, the dropped-carry corner of

@@ -320,6 +320,44 @@ def make_lrr_sl():
     print("lrr_sl.npz:", n, "sequences, clades equal to LRR/sl.dnd, tree crc", crc)
 
 
+def make_prim_pruning_case():
+    """prim_pruning_case.npz -- a small set on which MSTPrim's lower-bound skip (MSTPrim.cpp:450-467) changes the tree:
+    sequences with 64-residue runs (the dropped-carry corner, LCS > shorter length) next to very short ones.  Searched with
+    a fixed seed; generation asserts reference tree == restated loop with the skip != restated loop without it."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from oracle import pyoracle
+    from treeutil import prim_restated
+    rng = np.random.default_rng(1)
+    AA = "ACDEFGHIKLMNPQRSTVWY"
+    for trial in range(400):
+        n = int(rng.integers(5, 14))
+        seqs = []
+        for _ in range(n):
+            kind = rng.integers(0, 3)
+            a = "ACDEFGHIKL"[rng.integers(0, 10)]
+            if kind == 0:
+                pre = "".join(AA[x] for x in rng.integers(0, 20, size=64 * rng.integers(0, 2)))
+                s = pre + a * int(64 * rng.integers(1, 4)) + "".join(AA[x] for x in rng.integers(0, 20, size=rng.integers(0, 5)))
+            else:
+                s = a * int(rng.integers(1, 6)) + "".join(AA[x] for x in rng.integers(0, 20, size=rng.integers(0, 4)))
+            seqs.append(s)
+        seqs.sort(key=lambda q: -len(q))
+        codes, off, lens = seqio.pack([seqio.encode(q) for q in seqs])
+        with_skip = prim_restated(codes, off, lens, 0, True)
+        without = prim_restated(codes, off, lens, 0, False)
+        if all(np.array_equal(x, y) for x, y in zip(with_skip, without)):
+            continue
+        ref = pyoracle.RefSeqSet(seqs).mst_prim_tree(1)
+        if np.array_equal(ref, pyoracle.mst_to_dendogram(*without)):
+            continue                                    # the edge lists differ but give the same tree: not a witness
+        assert np.array_equal(ref, pyoracle.mst_to_dendogram(*with_skip)), "restated loop with the skip differs from the reference"
+        np.savez_compressed(os.path.join(HERE, "prim_pruning_case.npz"), seqs=np.array(seqs), edge_from=with_skip[0], edge_to=with_skip[1],
+                            edge_dist=with_skip[2], prim_order=with_skip[3], tree=ref)
+        print("prim_pruning_case.npz: trial", trial, n, "sequences; reference == loop with the skip, != loop without")
+        return
+    raise SystemExit("no witness found")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         sys.path.insert(0, os.path.join(HERE, ".."))
@@ -331,3 +369,4 @@ if __name__ == "__main__":
     make_hemopexin_sl()
     make_hemopexin_dups()
     make_sl_tree()
+    make_prim_pruning_case()

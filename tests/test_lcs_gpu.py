@@ -364,40 +364,7 @@ def test_concurrent_callers_share_one_context(engine, adeno):
     assert not errors
 
 
-def _prim_restated(codes, offsets, lens, kind):
-    """MSTPrim<>::run_view's vertex loop (MSTPrim.cpp:280-549) restated with the oracle; validated against the
-    reference's own tree in test_gpu_prim_tree (kind 0) and used here for kind 1."""
-    n = len(lens)
-    lcs = pyoracle.lcs_rows(codes, offsets, lens, np.arange(n))          # lcs[v][j], v = row (seq0)
-    dist = np.full(n, np.finfo(np.float64).max)
-    key = np.zeros(n, dtype=np.uint64)
-    visited = np.zeros(n, dtype=bool)
-    order = np.full(n, n, dtype=np.int32)
-    full = np.uint64(0xFFFFFFFFFFFFFFFF)
-    v = 0
-    visited[0] = True
-    order[0] = 0
-    ef, et, ed = [], [], []
-    for step in range(1, n):
-        best = -1
-        for j in range(n):
-            if visited[j]:
-                continue
-            d = pyoracle.transform(kind, int(lcs[v, j]), int(lens[v]), int(lens[j]), True)
-            if d <= dist[j]:
-                a, b = (v, j) if v < j else (j, v)
-                k = full ^ np.uint64((a << 32) + b)
-                if d < dist[j] or k < key[j]:
-                    dist[j], key[j] = d, k
-            if best < 0 or dist[j] < dist[best] or (dist[j] == dist[best] and key[j] < key[best]):
-                best = j
-        p = int(full ^ key[best])
-        a, b = p >> 32, p & 0xFFFFFFFF
-        ef.append(min(a, b)); et.append(max(a, b)); ed.append(dist[best])
-        order[best] = step
-        visited[best] = True
-        v = best
-    return np.array(ef, np.int32), np.array(et, np.int32), np.array(ed), order
+from treeutil import prim_restated as _prim_restated  # noqa: E402
 
 
 @pytest.mark.skipif(not pyoracle.have_ref(), reason="oracle/_ref not built")
@@ -480,3 +447,16 @@ def test_gpu_prim_lrr_golden_tree():
         eng.close()
     tree = pyoracle.mst_to_dendogram(ef, et, ed, order)
     assert zlib.crc32(np.ascontiguousarray(tree[n:], dtype=np.int32).tobytes()) == int(z["tree_crc"][0])
+
+
+def test_gpu_prim_lower_bound_pruning_case(engine):
+    """MSTPrim skips a candidate whose best possible distance -- LCS = the shorter length -- cannot beat its current one
+    (MSTPrim.cpp:450-467).  With the dropped-carry corner the reference's LCS can exceed the shorter length, so the skip
+    changes the tree; fixture prim_pruning_case.npz holds a 13-sequence set where it does (generation asserts the
+    reference's tree equals the restated loop WITH the skip and differs from the one without) and the edges of that loop."""
+    z = np.load(os.path.join(GOLDEN, "prim_pruning_case.npz"))
+    codes, offsets, lens = seqio.pack([seqio.encode(str(s)) for s in z["seqs"]])
+    engine.upload(codes, offsets, lens)
+    ef, et, ed, order = engine.prim(0)
+    assert np.array_equal(ef, z["edge_from"]) and np.array_equal(et, z["edge_to"])
+    assert np.array_equal(ed, z["edge_dist"]) and np.array_equal(order, z["prim_order"])

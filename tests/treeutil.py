@@ -50,3 +50,44 @@ def parse_newick(text: str):
 def levels(n_leaves: int, merges):
     from famsa_b200.schedule import ready_levels
     return ready_levels(n_leaves, merges)
+
+
+def prim_restated(codes, offsets, lens, kind, prune=True):
+    """MSTPrim<>::run_view's vertex loop (MSTPrim.cpp:280-549) restated with the oracle, including the lower-bound skip of
+    :450-467 (a candidate is only computed when the distance it would have with LCS = the shorter length does not exceed
+    its current one; without the dropped-carry corner that never changes a result).  Validated against the reference's own
+    tree in test_gpu_prim_tree and at the generation of prim_pruning_case.npz."""
+    import numpy as np
+    from oracle import pyoracle
+    n = len(lens)
+    lcs = pyoracle.lcs_rows(codes, offsets, lens, np.arange(n))          # lcs[v][j], v = row (seq0)
+    dist = np.full(n, np.finfo(np.float64).max)
+    key = np.zeros(n, dtype=np.uint64)
+    visited = np.zeros(n, dtype=bool)
+    order = np.full(n, n, dtype=np.int32)
+    full = np.uint64(0xFFFFFFFFFFFFFFFF)
+    v = 0
+    visited[0] = True
+    order[0] = 0
+    ef, et, ed = [], [], []
+    for step in range(1, n):
+        best = -1
+        for j in range(n):
+            if visited[j]:
+                continue
+            if not prune or pyoracle.transform(kind, int(min(lens[v], lens[j])), int(lens[v]), int(lens[j]), True) <= dist[j]:
+                d = pyoracle.transform(kind, int(lcs[v, j]), int(lens[v]), int(lens[j]), True)
+                if d <= dist[j]:
+                    a, b = (v, j) if v < j else (j, v)
+                    k = full ^ np.uint64((a << 32) + b)
+                    if d < dist[j] or k < key[j]:
+                        dist[j], key[j] = d, k
+            if best < 0 or dist[j] < dist[best] or (dist[j] == dist[best] and key[j] < key[best]):
+                best = j
+        p = int(full ^ key[best])
+        a, b = p >> 32, p & 0xFFFFFFFF
+        ef.append(min(a, b)); et.append(max(a, b)); ed.append(dist[best])
+        order[best] = step
+        visited[best] = True
+        v = best
+    return np.array(ef, np.int32), np.array(et, np.int32), np.array(ed), order
